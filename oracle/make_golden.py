@@ -1,0 +1,427 @@
+"""TEST INFRASTRUCTURE — golden-vector generator.
+
+Runs the UNMODIFIED reference (`/root/reference/dprox`, imported through `oracle/refshim.py`) on
+small seeded inputs on CPU and stores inputs + outputs under `tests/golden/<case>.npz`.
+It only runs in the authoring container (the GPU box has no /root/reference); the committed
+`.npz` files are what `tests/` reads.
+
+    python oracle/make_golden.py            # regenerate every case
+    python oracle/make_golden.py admm_tv    # one case
+
+Every case below names the reference entry points it exercises.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+
+dp = refshim.import_reference()
+from dprox.contrib import blurring, point_spread_function  # noqa: E402
+from dprox.linalg import LinearSolveConfig  # noqa: E402
+from dprox.linalg.solve import cg as ref_cg, pcg as ref_pcg  # noqa: E402
+from dprox.proxfn.pnp.denoisers.base import Denoiser  # noqa: E402
+from dprox.proxfn.pnp.denoisers.models.network_ffdnet import FFDNet  # noqa: E402
+
+import dprox_oracle as orc  # noqa: E402  (only for the seeded FFDNet weight generator)
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def _deconv_inputs(B, C, H, W, ksize=5, ksigma=2.0, seed=0, lo=-0.3):
+    """img ~ U[lo, lo+1) so the nonneg constraint is active; b = blur(img) + 0.01 randn."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, C, H, W, generator=g) + lo
+    psf = point_spread_function(ksize, ksigma)
+    b = torch.cat([blurring(img[i:i + 1], psf) for i in range(B)], 0).float()
+    b = b + 0.01 * torch.randn(B, C, H, W, generator=g)
+    return img, psf, b
+
+
+def _full_state(state):
+    out = {}
+    names = ["s0", "s1", "s2"]
+    for name, s in zip(names, state):
+        if isinstance(s, (list, tuple)):
+            for i, e in enumerate(s):
+                out[f"{name}_{i}"] = _np(e)
+        else:
+            out[name] = _np(s)
+    return out
+
+
+def _run(fns, method, x0, T, rhos=None, lams=None, **compile_kw):
+    solver = dp.compile(fns, method=method, device="cpu", **compile_kw)
+    with torch.no_grad():
+        state = solver.solve(x0=x0, rhos=rhos, lams=lams, max_iter=T, return_full_states=True)
+    return _full_state(state)
+
+
+# ------------------------------------------------------------------------------------------------
+# a4/a6/a5/a7/a8: the five iterations on the headline objective  sum_squares(conv(x)-b)+nonneg(x)
+# ------------------------------------------------------------------------------------------------
+
+@case
+def admm_conv_nonneg():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "admm", b, 10)
+    return dict(psf=psf, b=_np(b), T=10, **out)
+
+
+@case
+def admm_conv_nonneg_50it():
+    """cfg1-class: 50 iterations (reference fp32 noise ~8e-6 at 50 it)."""
+    img, psf, b = _deconv_inputs(1, 3, 64, 64, ksize=15, ksigma=5.0, seed=1)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "admm", b, 50, rhos=0.5, lams=0.02)
+    return dict(psf=psf, b=_np(b), T=50, rho=0.5, **out)
+
+
+@case
+def hqs_conv_nonneg():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "hqs", b, 10)
+    return dict(psf=psf, b=_np(b), T=10, **out)
+
+
+@case
+def ladmm_conv_nonneg_b1():
+    img, psf, b = _deconv_inputs(1, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "ladmm", b, 10)
+    return dict(psf=psf, b=_np(b), T=10, **out)
+
+
+@case
+def vxu_conv_nonneg_b1():
+    img, psf, b = _deconv_inputs(1, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "admm_vxu", b, 10)
+    return dict(psf=psf, b=_np(b), T=10, **out)
+
+
+@case
+def pgd_conv_nonneg():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), "pgd", b, 16, rhos=0.8)
+    return dict(psf=psf, b=_np(b), T=16, rho=0.8, **out)
+
+
+@case
+def pgd_conv_norm1():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=-0.5)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf), b) + dp.norm1(x), "pgd", b, 12, rhos=0.9, lams=0.05)
+    return dict(psf=psf, b=_np(b), T=12, rho=0.9, lam=0.05, **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# a17/a19: prox wrapper chain, alpha scaling, two identity psi terms, per-sample schedules [B,T]
+# ------------------------------------------------------------------------------------------------
+
+@case
+def admm_two_psi_per_sample():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=-0.5)
+    g = torch.Generator().manual_seed(7)
+    T = 10
+    rhos = 0.5 + torch.rand(2, T, generator=g)
+    lam1 = 0.01 + 0.05 * torch.rand(2, T, generator=g)
+    lam2 = 0.02 * torch.ones(T)
+    x = dp.Variable()
+    f1, f2 = 0.5 * dp.norm1(x), dp.nonneg(x)
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, "admm", b, T, rhos=rhos, lams={f1: lam1, f2: lam2})
+    return dict(psf=psf, b=_np(b), T=T, rhos=_np(rhos), lam1=_np(lam1), lam2=_np(lam2), alpha1=0.5, **out)
+
+
+@case
+def hqs_two_psi_norm2():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=-0.5)
+    x = dp.Variable()
+    f1, f2 = dp.norm2(x), dp.norm1(x)
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, "hqs", b, 8, rhos=0.7, lams={f1: 0.1, f2: 0.03})
+    return dict(psf=psf, b=_np(b), T=8, rho=0.7, lam1=0.1, lam2=0.03, **out)
+
+
+@case
+def admm_psi_offset():
+    """psi linop with a constant: norm1(x - c) -> prox_translated path (proxfn/base.py:24-27,43-45)."""
+    img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=-0.5)
+    g = torch.Generator().manual_seed(11)
+    c = 0.2 * torch.randn(2, 3, 32, 48, generator=g)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.norm1(x - c), "admm", b, 8, rhos=0.8, lams=0.05)
+    return dict(psf=psf, b=_np(b), c=_np(c), T=8, rho=0.8, lam=0.05, **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# a23/a25: asymmetric (complex-OTF) kernels and grad psi linops (anisotropic TV)
+# ------------------------------------------------------------------------------------------------
+
+@case
+def admm_even_kernel():
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(2, 3, 32, 48, generator=g)
+    k = torch.rand(4, 6, generator=g).numpy().astype("float32")
+    k = (k / k.sum())[..., None]
+    x = dp.Variable()
+    op = dp.conv(x, k)
+    K = dp.CompGraph(op)
+    b = K.forward(img).float() + 0.01 * torch.randn(2, 3, 32, 48, generator=g)
+    out = _run(dp.sum_squares(dp.conv(x, k) - b) + dp.nonneg(x), "admm", b, 8, rhos=0.3)
+    return dict(kernel=k, b=_np(b), T=8, rho=0.3, **out)
+
+
+@case
+def admm_tv():
+    img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=0.0)
+    x = dp.Variable()
+    f1, f2 = dp.norm1(dp.grad(x, dim=0)), dp.norm1(dp.grad(x, dim=1))
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, "admm", b, 10, rhos=2.0, lams=0.01)
+    return dict(psf=psf, b=_np(b), T=10, rho=2.0, lam=0.01, **out)
+
+
+@case
+def hqs_tv_nonneg():
+    img, psf, b = _deconv_inputs(1, 1, 32, 32, lo=0.0)
+    x = dp.Variable()
+    f1, f2, f3 = dp.norm1(dp.grad(x, dim=0)), dp.norm1(dp.grad(x, dim=1)), dp.nonneg(x)
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2 + f3, "hqs", b, 10, rhos=1.5, lams=0.02)
+    return dict(psf=psf, b=_np(b), T=10, rho=1.5, lam=0.02, **out)
+
+
+@case
+def linops():
+    """conv / grad forward+adjoint and OTFs on a random tensor (a23, a25)."""
+    g = torch.Generator().manual_seed(5)
+    t = torch.randn(2, 3, 16, 24, generator=g)
+    psf = point_spread_function(5, 2)
+    k2 = torch.rand(4, 3, 1, generator=g).numpy().astype("float32")
+    x = dp.Variable()
+    out = dict(t=_np(t), psf=psf, k2=k2)
+    for name, op in [("conv", dp.conv(x, psf)), ("conv2", dp.conv(x, k2)), ("grad0", dp.grad(x, dim=0)),
+                     ("grad1", dp.grad(x, dim=1)), ("grad2", dp.grad(x, dim=2))]:
+        out[name + "_fwd"] = _np(op.forward(t))
+        out[name + "_adj"] = _np(op.adjoint(t))
+        fb = op._FB(tuple(t.shape))
+        out[name + "_otf"] = _np(fb)
+        out[name + "_diag"] = _np(op.get_diag(t, freq=True))
+    m = dp.mosaic(x)
+    out["mosaic_fwd"] = _np(m.forward(t))
+    out["mosaic_diag"] = _np(m.get_diag(t, freq=False))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a11 spatial-diag branch, a26: mosaic / mul_elementwise
+# ------------------------------------------------------------------------------------------------
+
+@case
+def admm_mosaic_spatial():
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(2, 3, 32, 48, generator=g)
+    x = dp.Variable()
+    b = dp.mosaic(x).forward(img) + 0.01 * torch.randn(2, 3, 32, 48, generator=g)
+    s = dp.compile(dp.sum_squares(dp.mosaic(x) - b) + dp.nonneg(x), method="admm", device="cpu")
+    flags = (bool(s.least_square.diagonalizable), bool(s.least_square.freq_diagonalizable))
+    out = _run(dp.sum_squares(dp.mosaic(x) - b) + dp.nonneg(x), "admm", b, 8, rhos=0.6)
+    return dict(b=_np(b), T=8, rho=0.6, flags=np.array(flags), **out)
+
+
+@case
+def hqs_mul_elementwise():
+    g = torch.Generator().manual_seed(10)
+    img = torch.rand(2, 3, 32, 48, generator=g)
+    w = (torch.rand(1, 3, 32, 48, generator=g) > 0.4).float() * (0.5 + torch.rand(1, 3, 32, 48, generator=g))
+    x = dp.Variable()
+    b = w * img
+    out = _run(dp.sum_squares(dp.mul_elementwise(x, w) - b) + dp.norm1(x), "hqs", b, 8, rhos=0.6, lams=0.03)
+    return dict(b=_np(b), w=_np(w), T=8, rho=0.6, lam=0.03, **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# a12/a13/a14: CG fallback (joint demosaic + deconv) and the raw solvers
+# ------------------------------------------------------------------------------------------------
+
+@case
+def admm_cg_mosaic_conv():
+    g = torch.Generator().manual_seed(12)
+    img = torch.rand(1, 3, 24, 32, generator=g)
+    psf = point_spread_function(5, 1.5)
+    x = dp.Variable()
+    op = dp.mosaic(dp.conv(x, psf))
+    b = dp.CompGraph(op).forward(img).float()
+    cfg = LinearSolveConfig(rtol=1e-6, max_iters=30, solver_type="cg")
+    out = _run(dp.sum_squares(dp.mosaic(dp.conv(x, psf)) - b) + dp.nonneg(x), "admm", b, 4, rhos=0.5,
+               linear_solve_config=cfg)
+    return dict(psf=psf, b=_np(b), T=4, rho=0.5, cg_iters=30, **out)
+
+
+@case
+def admm_pcg_mosaic_conv():
+    g = torch.Generator().manual_seed(13)
+    img = torch.rand(2, 3, 24, 32, generator=g)
+    psf = point_spread_function(5, 1.5)
+    x = dp.Variable()
+    b = dp.CompGraph(dp.mosaic(dp.conv(x, psf))).forward(img).float()
+    cfg = LinearSolveConfig(rtol=1e-6, max_iters=25, solver_type="pcg")
+    out = _run(dp.sum_squares(dp.mosaic(dp.conv(x, psf)) - b) + dp.nonneg(x), "admm", b, 3, rhos=0.5,
+               linear_solve_config=cfg)
+    return dict(psf=psf, b=_np(b), T=3, rho=0.5, cg_iters=25, **out)
+
+
+@case
+def linear_solvers():
+    """tests/linalg/test_linear_solver.py:57-111 style: SPD systems, fp64, plus a batched conv system."""
+    rs = np.random.RandomState(0)
+    M = rs.rand(5, 5)
+    A = M @ M.T + 5 * np.eye(5)
+    xs = rs.rand(5)
+    bvec = A @ xs
+    At, bt = torch.from_numpy(A), torch.from_numpy(bvec)
+    out = dict(A=A, b=bvec, x_true=xs)
+    out["cg"] = _np(ref_cg(lambda v: At @ v, bt, rtol=1e-8, max_iters=100))
+    out["pcg"] = _np(ref_pcg(lambda v: At @ v, bt, rtol=1e-8, max_iters=100))
+    # batched [B,C,H,W] system (I + 0.5 * K^T K) x = rhs with a conv K
+    g = torch.Generator().manual_seed(2)
+    psf = point_spread_function(5, 2)
+    x = dp.Variable()
+    cv = dp.conv(x, psf)
+    rhs = torch.rand(2, 3, 16, 24, generator=g)
+    Aop = lambda v: v + 0.5 * cv.adjoint(cv.forward(v))
+    out["psf"], out["rhs"] = psf, _np(rhs)
+    out["cg_conv"] = _np(ref_cg(Aop, rhs, rtol=1e-6, max_iters=12))
+    out["pcg_conv"] = _np(ref_pcg(Aop, rhs, rtol=1e-6, max_iters=12))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# known answers of the reference's own tests (tests/problem/test_ml_problems.py:5-44)
+# ------------------------------------------------------------------------------------------------
+
+@case
+def ml_problems():
+    out = {}
+    rhs = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    x = dp.Variable((3, 3))
+    dp.Problem(dp.sum_squares(2 * x - rhs)).solve("admm", device="cpu", x0=np.zeros((3, 3)))
+    out["lsq"] = _np(x.value)
+    x = dp.Variable((3, 3))
+    dp.Problem(dp.sum_squares(2 * x, rhs)).solve("admm", device="cpu", x0=np.zeros((3, 3)))
+    out["lsq1"] = _np(x.value)
+    x = dp.Variable((3, 3, 1))
+    rhs2 = np.array([[[1, 2, 3], [4, 5, 6], [7, 8, 9]]])
+    kernel = np.array([[1, 1], [1, 1]]) / 4
+    dp.Problem(dp.sum_squares(dp.conv(x, kernel) - rhs2)).solve("admm", device="cpu", x0=np.zeros((3, 3, 1)))
+    out["lsq2"] = _np(x.value)
+    out["lsq2_resid"] = _np(dp.eval(dp.conv(x, kernel) - rhs2, x.value, zero_out_constant=False))
+    x = dp.Variable((3))
+    rhs3 = np.array([1, 2, 3])
+    dp.Problem(dp.sum_squares(2 * x - rhs3)).solve("admm", device="cpu", x0=np.zeros(3))
+    out["lsq3"] = _np(x.value)
+    out["rhs"], out["rhs2"], out["rhs3"], out["kernel"] = rhs, rhs2, rhs3, kernel
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a24: conv_doe (learnable PSF) incl. the channel-roll and the even-pad off-by-one quirks
+# ------------------------------------------------------------------------------------------------
+
+@case
+def hqs_conv_doe():
+    out = {}
+    for tag, h in (("full", 32), ("padded", 24)):
+        g = torch.Generator().manual_seed(21)
+        img = torch.rand(2, 3, 32, 32, generator=g)
+        psf = torch.rand(1, 3, h, h, generator=g)
+        psf = psf / psf.sum(dim=(-2, -1), keepdim=True)
+        x = dp.Variable()
+        op = dp.conv_doe(x, psf, circular=True)
+        with torch.no_grad():
+            b = op.forward(img) + 0.01 * torch.randn(2, 3, 32, 32, generator=g)
+            res = _run(dp.sum_squares(dp.conv_doe(x, psf, circular=True) - b) + dp.nonneg(x), "hqs", b, 6, rhos=0.4)
+            out[f"{tag}_otf"] = _np(sys.modules['dprox.linop.conv'].psf2otf2(psf, (2, 3, 32, 32)))
+        out[f"{tag}_psf"], out[f"{tag}_b"] = _np(psf), _np(b)
+        for k, v in res.items():
+            out[f"{tag}_{k}"] = v
+    out["T"], out["rho"] = 6, 0.4
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a20: deep_prior -> FFDNet-color with seeded random weights (pretrained weights need network)
+# ------------------------------------------------------------------------------------------------
+
+class _RandFFDNetColor(Denoiser):
+    def __init__(self, seed):
+        super().__init__()
+        self.model = FFDNet(in_nc=3, out_nc=3, nc=96, nb=12, act_mode="R")
+        ws = orc.ffdnet_random_weights(seed)
+        sd = {}
+        for i, (w, b) in enumerate(ws):
+            sd[f"model.{2 * i}.weight"], sd[f"model.{2 * i}.bias"] = w, b
+        self.model.load_state_dict(sd, strict=True)
+
+    def _denoise(self, x, sigma):
+        return self.model(x, sigma)
+
+
+@case
+def admm_deep_prior_ffdnet():
+    """deep_prior + nonneg need a full lams dict (admm.py:56 indexes lam[fn] for every psi fn)."""
+    img, psf, b = _deconv_inputs(2, 3, 24, 30, lo=0.0)
+    den = _RandFFDNetColor(seed=4)
+    x = dp.Variable()
+    rhos, sigmas = dp.log_descent(35, 30, 4)
+    prior, nn_ = dp.deep_prior(x, denoiser=den), dp.nonneg(x)
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + prior + nn_, "admm", b, 4, rhos=rhos,
+               lams={prior: sigmas, nn_: 0.02})
+    return dict(psf=psf, b=_np(b), T=4, rhos=_np(rhos), sigmas=_np(sigmas), seed=4, **out)
+
+
+@case
+def ffdnet_forward():
+    den = _RandFFDNetColor(seed=4)
+    g = torch.Generator().manual_seed(6)
+    xin = torch.rand(2, 3, 15, 18, generator=g)              # odd H: exercises replicate pad + crop
+    sig = torch.tensor([0.05, 0.12])
+    with torch.no_grad():
+        y = den.denoise(xin, sig)
+    ws = orc.ffdnet_random_weights(4)
+    return dict(x=_np(xin), sigma=_np(sig), y=_np(y), w0_sum=float(ws[0][0].double().sum()),
+                wlast_sum=float(ws[-1][0].double().sum()))
+
+
+@case
+def schedules():
+    r1, s1 = dp.log_descent(35, 30, 24)
+    r2, s2 = dp.log_descent(49, 7.65, 10, sigma=7.65 / 255, sqrt=True)
+    return dict(r1=_np(r1), s1=_np(s1), r2=_np(r2), s2=_np(s2))
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        data = CASES[n]()
+        path = os.path.join(OUT, n + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{n:28s} -> {os.path.getsize(path) / 1024:8.1f} KiB  keys={sorted(data)[:6]}...")
