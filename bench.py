@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — ADMM iterations/sec on a batch of 2K x 2K deconvolution problems (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--batch B_per_gpu] [--iters T] [--size 2048] [--fft-backend 0|1|2]
+
+Workload (SURVEY.md §8d "headline"): per GPU, B problems [3,2048,2048] fp32,
+`sum_squares(conv(x, psf) - b) + nonneg(x)`, Gaussian PSF 15x15 sigma 5, x0 = b, rho = 1, lam = 0.02, ADMM.
+One *step* = one pass of the hot path over the batch = T ADMM iterations of all B problems (one `dpx_iters`
+call).  `value` = problem-iterations / second over all GPUs with every input already resident in HBM;
+`e2e` = the same metric through the public API with HOST (pinned) measurements: per step the H2D copy of b,
+the constant hoisting (K^T b, its FFT), state init, T iterations and the D2H copy of x are inside the timing.
+
+N > 1: one process per GPU under torchrun, independent problem shards, no data-path collective ("weak").
+`--impl reference` times the CPU oracle port (oracle/dprox_oracle.py, the reference's op sequence) on the
+host cores of this box on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "delta-prox_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ALG_BYTES_PER_ELEM = 24.0          # ADMM, one identity prox term: read v,u,F(b); write x,v,u (fp32)
+METRIC = "ADMM iters/sec, 2Kx2K deconv batch"
+UNIT = "problem-iters/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def psf_gaussian(k=15, sigma=5.0):
+    r = (k - 1) / 2.0
+    ax = np.arange(-r, r + 1)
+    xx, yy = np.meshgrid(ax, ax)
+    h = np.exp(-(xx * xx + yy * yy) / (2 * sigma * sigma))
+    h[h < np.finfo(float).eps * h.max()] = 0
+    return (h / h.sum())[..., None].astype("float32")
+
+
+def make_measurements(B, C, H, W, seed, device):
+    """b = blur(img) + 0.01 noise, synthesised on the device with a seeded generator (img ~ U[-0.3, 0.7))."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    img = torch.rand(B, C, H, W, device=device, generator=g) - 0.3
+    noise = 0.01 * torch.randn(B, C, H, W, device=device, generator=g)
+    return img, noise
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "samples": 0}
+        # "under load" = the upper half of the samples (the sampler also sees the idle edges)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+#  CPU arm: the oracle port timed on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_port_rate(H, W, iters, threads, seed=0):
+    """problem-iterations/s of the oracle (reference op sequence, torch CPU) on ONE [3,H,W] problem."""
+    import dprox_oracle as orc
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(1, 3, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(15, 5)
+    conv = orc.Conv(psf, orc.Identity())
+    b = conv.fwd(img) + 0.01 * torch.randn(1, 3, H, W, generator=g)
+    solver = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")], "admm")
+    solver.solve(b, rhos=1.0, lams=0.02, max_iter=2)                 # warm-up (FFT plans, OTF cache)
+    t0 = time.perf_counter()
+    solver.solve(b, rhos=1.0, lams=0.02, max_iter=iters)
+    dt = time.perf_counter() - t0
+    return iters / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    H = W = args.size
+    iters = args.ref_iters
+    rates = []
+    for _ in range(args.warmup):
+        cpu_port_rate(H, W, 1, threads)
+    t_all = 0.0
+    for _ in range(args.steps):
+        r, dt = cpu_port_rate(H, W, iters, threads)
+        rates.append(r)
+        t_all += dt
+    value = float(np.mean(rates))
+    sample = f"1 problem [3,{H},{W}] x {iters} ADMM iterations per step, {args.steps} steps, torch-CPU {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"admm deconv+nonneg [3,{H},{W}], psf gaussian 15/5, rho=1, lam=0.02 (CPU sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+#  GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_native(args):
+    import torch.distributed as dist
+    import dprox_b200 as dp
+    from dprox_b200 import _cabi as cabi
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cabi.lib()
+
+    B, C, H, W, T = args.batch, 3, args.size, args.size, args.iters
+    N = B * C * H * W
+    psf = psf_gaussian(15, 5.0)
+
+    # ---- problem batch of this rank: Placeholder-fed measurements so that a new batch re-uses the plan ----
+    x = dp.Variable()
+    y = dp.Placeholder()
+    data_op = dp.conv(x, psf)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method="admm", device=dev,
+                        fft_backend=args.fft_backend)
+    img, noise = make_measurements(B, C, H, W, seed=1234 + rank, device=dev)
+    b_dev = data_op.to(dev).forward(img)
+    b_dev.add_(noise)
+    del img, noise
+    y.value = b_dev
+    b_host = b_dev.cpu().pin_memory()
+    out_host = torch.empty_like(b_host).pin_memory()
+
+    rhos = torch.full((T,), 1.0)
+    lams = torch.full((T,), 0.02)
+
+    def resident_step(state):
+        return solver.iters(state, rhos, lams, T)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- resident-input throughput (`value`) -------------------------------------------------------
+    state = solver.initialize(b_dev)
+    for _ in range(args.warmup):
+        state = resident_step(state)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.dpx_launch_count()
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            state = resident_step(state)
+        ev1.record()
+        barrier()
+        time.sleep(0.15)
+    launches = lib.dpx_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t)
+    total_units = world * B * T * args.steps
+    value = total_units / (ms_max * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers (`e2e`) ---------------------------------
+    def e2e_step():
+        bd = b_host.to(dev, non_blocking=True)             # H2D of this step's measurements (pinned)
+        y.value = bd                                       # new batch -> constants re-hoisted on the same plan
+        xs = solver.solve(x0=bd, rhos=rhos, lams=lams, max_iter=T)
+        out_host.copy_(xs, non_blocking=True)              # D2H of the result
+        return xs
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_steps = max(1, args.steps // 2)
+    e0.record()
+    for _ in range(e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ems_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * e_steps / (float(ems_t) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused iteration + CPU baseline (rank 0) ----------------------------------------
+    peak, peak_src = load_peaks()
+    it_ms = ms_max / (T * args.steps)                      # average duration of one iteration of the whole batch
+    achieved = ALG_BYTES_PER_ELEM * N / (it_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "unit_of_work": f"one ADMM iteration of {B} problems = {ALG_BYTES_PER_ELEM:.0f} B x {N} elements",
+            "avg_iteration_ms": it_ms}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_iteration")
+        except Exception:
+            pass
+    cpu = None
+    if not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        r, dt = cpu_port_rate(H, W, args.ref_iters, threads)
+        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"1 problem [3,{H},{W}] x {args.ref_iters} ADMM iterations ({dt:.1f} s), oracle port, torch-CPU"}
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"admm deconv+nonneg, {B} problems/GPU [3,{H},{W}] fp32, psf gaussian 15/5, rho=1, lam=0.02, "
+                               f"{T} iterations per step", "batch_per_gpu": B, "iters_per_step": T,
+                   "l2_policy": f"state arrays are {N * 4 / 2**20:.0f} MiB each (> 126 MB L2) and every iteration streams all of them",
+                   "fft_backend": {0: "auto", 1: "cufft", 2: "fused"}[args.fft_backend], "parallelism": f"dp{world} (problem shards, no collective)"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4),
+                "steps": e_steps},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="problems per GPU")
+    ap.add_argument("--iters", type=int, default=50, help="ADMM iterations per step")
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--fft-backend", type=int, default=0)
+    ap.add_argument("--ref-iters", type=int, default=6, help="CPU-arm iterations per sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,35 @@
+// dpx_fft.cuh — FFT engines behind the Fourier-diagonal x-update (proxfn/sum_square.py:150-152).
+//
+//   CufftEngine : batched 2-D R2C / C2R cuFFT plans, any H x W (the general path).
+//   FusedEngine : hand-written sm_100a row/column FFT kernels with the spectral solve and the
+//                 prox/dual update fused into them (power-of-two H, W; see dpx_fused_fft.cu).
+#pragma once
+#include "dpx_kernels.cuh"
+
+namespace dpx {
+
+class FftEngine {
+ public:
+  virtual ~FftEngine() {}
+  // real [P,H,W] -> half spectrum [P,H,Wc] (unnormalised forward DFT, like torch.fft.fftn)
+  virtual int r2c(const float* in, float2* out, cudaStream_t s) = 0;
+  // half spectrum -> real (unnormalised inverse; callers fold 1/(H*W) into the spectrum). Destroys `in`.
+  virtual int c2r(float2* in, float* out, cudaStream_t s) = 0;
+  virtual size_t workspace_bytes() const = 0;
+  virtual void destroy() = 0;
+  // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true
+  virtual bool fused() const { return false; }
+  virtual int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2* fb, const float* dq,
+                          int dq_batch, float wid, float eps, const float* rho, int rho_stride, int it0, int n_iters,
+                          cudaStream_t s) {
+    (void)g; (void)psi; (void)hqs; (void)x; (void)fb; (void)dq; (void)dq_batch; (void)wid; (void)eps; (void)rho;
+    (void)rho_stride; (void)it0; (void)n_iters; (void)s;
+    set_error("fused iterations not available on this engine");
+    return DPX_ERR_STATE;
+  }
+};
+
+// backend: 0 auto, 1 cuFFT, 2 fused
+int make_fft_engine(const Geom& g, int backend, FftEngine** out);
+
+}  // namespace dpx

@@ -1,0 +1,371 @@
+"""Problem / compile() / Algorithm.solve — the reference's L2/L3 surface over the
+B200 engines of `dprox_b200.lowering`.
+
+What stays the same for callers: class names, constructor and `solve/iters/iter/initialize/pack/unpack`
+signatures, the partition rules, defaults (rho=1.0, lam=0.02 for every psi fn, max_iter=24), the
+`callback(iter=, state=, rho=, lam=)` hook, `Variable.value` holding the result after a solve.
+
+What is different underneath: the loop body is not Python.  When no callback/progress bar is requested
+and every prox is native, `solve()` makes ONE C-ABI call that runs all iterations on the GPU with the
+schedules resident on the device.  State tensors are updated in place.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Callable, Dict, Iterable, List, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi as cabi
+from .linalg import LinearSolveConfig
+from .linop import CompGraph, Variable, vstack
+from .lowering import GenericEngine, NativeEngine, PlanSpec, _placeholder_versions, analyze
+from .proxfn import ProxFn, ext_sum_squares, sum_squares
+from .tensors import to_torch_tensor
+
+
+def _isscalar(x):
+    return np.isscalar(x) or (isinstance(x, torch.Tensor) and x.ndim == 0)
+
+
+def _to_tensor(x, batch=False):
+    if isinstance(x, dict):
+        return {k: _to_tensor(v, batch) for k, v in x.items()}
+    return to_torch_tensor(x, batch)
+
+
+class ResidualStop:
+    """Opt-in residual stopping rule (absent from the reference's imaging loop; semantics follow
+    lp/solvers.py:324-336): stop when  |r| <= abstol*sqrt(n) + reltol*max(|Kx|,|v|)  and  |s| <= abstol*sqrt(n) +
+    reltol*|v|, with r = Kx - v and s = rho*(v - v_prev), summed over all psi terms, all samples and — through
+    `group` — all ranks (one NCCL all-reduce of 4 floats every `every` iterations)."""
+
+    def __init__(self, abstol=1e-4, reltol=1e-3, every=4, group=None):
+        self.abstol, self.reltol, self.every, self.group = abstol, reltol, max(1, int(every)), group
+        self.history = []
+
+    def converged(self, sums: torch.Tensor, n_elems: int) -> bool:
+        """sums = [sum|r|^2, sum|s|^2, sum|Kx|^2, sum|v|^2] (device or CPU tensor), already local-summed."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            tot = torch.cat([sums.double(), torch.tensor([float(n_elems)], dtype=torch.float64, device=sums.device)])
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            sums, n_elems = tot[:4], float(tot[4])
+        r, s, kx, v = [float(t) ** 0.5 for t in sums]
+        self.history.append((r, s))
+        eps_abs = self.abstol * (n_elems ** 0.5)
+        return r <= eps_abs + self.reltol * max(kx, v) and s <= eps_abs + self.reltol * v
+
+
+class Algorithm(nn.Module):
+    """Base class of the proximal solvers (dprox/algo/base.py:58-275)."""
+
+    method = None
+
+    @classmethod
+    def partition(cls, prox_fns: List[ProxFn]):
+        raise NotImplementedError
+
+    @classmethod
+    def create(cls, *args, **kwargs):
+        return cls(*args, **kwargs)
+
+    def __init__(self, psi_fns: List[ProxFn], omega_fns: List[ProxFn], try_diagonalize=True, try_freq_diagonalize=True,
+                 linear_solve_config: LinearSolveConfig = LinearSolveConfig(), fft_backend: int = cabi.FFT_AUTO):
+        super().__init__()
+        self.psi_fns = nn.ModuleList(psi_fns)
+        self.omega_fns = nn.ModuleList(omega_fns)
+        self.K = CompGraph(vstack([fn.linop for fn in psi_fns]))
+        self.Kall = CompGraph(vstack([fn.linop for fn in list(psi_fns) + list(omega_fns)]))
+        self.try_diagonalize, self.try_freq_diagonalize = try_diagonalize, try_freq_diagonalize
+        self.linear_solve_config = linear_solve_config
+        self.fft_backend = fft_backend
+        self._dev_anchor = nn.Parameter(torch.tensor(0.0), requires_grad=False)
+        self.spec: PlanSpec = analyze(list(psi_fns), list(omega_fns), self.method, try_diagonalize, try_freq_diagonalize)
+        self._engine = None
+
+    # reference attribute: `solver.least_square.{diagonalizable,freq_diagonalizable}`
+    @property
+    def least_square(self):
+        return self.spec
+
+    @property
+    def device(self):
+        return self._dev_anchor.device
+
+    # -- engine management ---------------------------------------------------------------------------
+    def engine(self, x0: torch.Tensor):
+        key = (tuple(x0.shape), str(x0.device))
+        ckey = _placeholder_versions(list(self.psi_fns) + list(self.omega_fns))
+        if self._engine is not None and self._engine.key == key and self._engine.const_key != ckey \
+                and isinstance(self._engine, NativeEngine):
+            # only Placeholder values changed (a new batch of measurements): keep the plan, re-hoist the constants
+            self._engine._set_constants(x0)
+            self._engine.const_key = ckey
+        if self._engine is None or self._engine.key != key or self._engine.const_key != ckey:
+            if not x0.is_cuda:
+                raise RuntimeError(f"dprox_b200 computes on CUDA devices only; the solver lives on {x0.device}. "
+                                   f"Use compile(..., device='cuda'). There is no CPU fallback.")
+            if self.spec.tier == "native":
+                eng = NativeEngine(self.spec, x0, fft_backend=self.fft_backend)
+            else:
+                eng = GenericEngine(self.spec, x0, self.linear_solve_config)
+            eng.key, eng.const_key = key, ckey
+            self._engine = eng
+        return self._engine
+
+    # -- argument handling (base.py:20-45, 205-218) ---------------------------------------------------
+    def defaults(self, x0=None, rhos=None, lams=None, max_iter=24):
+        if rhos is None:
+            rhos = 1.0
+        if lams is None:
+            lams = 0.02
+        if _isscalar(rhos):
+            rhos = _to_tensor([float(rhos)] * max_iter)
+        if _isscalar(lams):
+            lams = {fn: _to_tensor([float(lams)] * max_iter) for fn in self.psi_fns}
+        lams = {k: _to_tensor([float(v)] * max_iter) if _isscalar(v) else _to_tensor(v) for k, v in lams.items()}
+        missing = [str(fn) for fn in self.psi_fns if fn not in lams]
+        if missing:
+            raise KeyError(f"`lams` given as a dict must contain every psi fn (missing: {missing}); "
+                           f"the reference indexes lam[fn] for all of them (algo/admm.py:56)")
+        return x0, _to_tensor(rhos), lams, max_iter
+
+    def solve(self, x0=None, rhos=None, lams=None, max_iter: int = 24, pbar: bool = False, callback: Callable = None,
+              return_full_states: bool = False, stop: Optional[ResidualStop] = None, **kwargs) -> torch.Tensor:
+        """Algorithm.solve (base.py:85-126): fixed `max_iter` iterations unless an opt-in `stop` rule is given."""
+        x0 = _to_tensor(x0, batch=True)
+        x0, rhos, lams, max_iter = self.defaults(x0, rhos, lams, max_iter)
+        x0 = x0.to(self.device, torch.float32)
+        state = self.initialize(x0, **kwargs)
+        state = self.iters(state, rhos, lams, max_iter, pbar, callback=callback, stop=stop)
+        return state if return_full_states else state[0]
+
+    def initialize(self, x0, **kwargs):
+        x0 = _to_tensor(x0, batch=True).to(self.device, torch.float32)
+        return self.engine(x0).initialize(x0)
+
+    def iters(self, state, rhos, lams, max_iter, pbar=False, callback=None, stop: Optional[ResidualStop] = None):
+        """Algorithm.iters (base.py:128-156)."""
+        eng = self.engine(state[0])
+        if _isscalar(lams) or not isinstance(lams, dict):
+            lams = {fn: lams for fn in self.psi_fns}
+        dev = state[0].device
+        rhos = torch.as_tensor(rhos, dtype=torch.float32).to(dev)         # schedules live on the device
+        lams = {k: torch.as_tensor(v, dtype=torch.float32).to(dev) for k, v in lams.items()}
+        per_iter = callback is not None or pbar or isinstance(eng, GenericEngine)
+        if stop is not None and isinstance(eng, NativeEngine) and not eng.spec.has_external and not per_iter:
+            state = self._iters_with_stop(eng, state, rhos, lams, max_iter, stop)
+        elif not per_iter:
+            state = eng.run(state, rhos, lams, 0, max_iter)                 # ONE native call for the whole loop
+        else:
+            it_range = range(max_iter)
+            if pbar:
+                from tqdm import tqdm
+                it_range = tqdm(it_range)
+            for it in it_range:
+                rho = rhos[..., it]
+                lam = {k: v[..., it] for k, v in lams.items()}
+                self._notify_all_op_current_step(it)
+                if isinstance(eng, NativeEngine):
+                    state = eng.run(state, rhos, lams, it, 1)
+                else:
+                    state = eng.step(state, rho.to(self.device), {k: v.to(self.device) for k, v in lam.items()}, it)
+                if callback is not None:
+                    callback(iter=it, state=state, rho=rho, lam=lam)
+        self.Kall.update_vars([state[0]])
+        return state
+
+    def _iters_with_stop(self, eng, state, rhos, lams, max_iter, stop: ResidualStop):
+        B = eng.shape4[0]
+        n_elems = state[0].numel() * max(1, len(self.psi_fns))
+        it = 0
+        while it < max_iter:
+            n = min(stop.every, max_iter - it)
+            resid = torch.zeros(n, B, 4, device=state[0].device, dtype=torch.float32)
+            state = eng.run(state, rhos, lams, it, n, resid=resid)
+            it += n
+            if stop.converged(resid[-1].sum(dim=0), n_elems):
+                break
+        self.iterations_run = it
+        return state
+
+    def iter(self, state, rho, lam):
+        """One iteration with explicit (rho, lam) values (base.py:174-178); used by unrolled / DEQ callers."""
+        eng = self.engine(state[0])
+        rho = torch.as_tensor(rho, dtype=torch.float32)
+        lam = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in lam.items()}
+        if isinstance(eng, NativeEngine):
+            rhos = rho.reshape(-1, 1) if rho.ndim == 1 else rho.reshape(1)
+            lams = {k: (v.reshape(-1, 1) if v.ndim == 1 else v.reshape(1)) for k, v in lam.items()}
+            state = eng.run(state, rhos, lams, 0, 1)
+        else:
+            state = eng.step(state, rho.to(self.device), {k: v.to(self.device) for k, v in lam.items()}, self._step_hint)
+        self.Kall.update_vars([state[0]])
+        return state
+
+    _step_hint = 0
+
+    def _iter(self, state, rho, lam):
+        return self.iter(state, rho, lam)
+
+    def _notify_all_op_current_step(self, step):
+        self._step_hint = step
+        for fn in list(self.psi_fns) + list(self.omega_fns):
+            fn.step = step
+            stack = [fn.linop]
+            while stack:
+                n = stack.pop()
+                n.step = step
+                stack += list(n.input_nodes)
+
+    # -- helpers used by RL / DEQ wrappers (base.py:224-275) -------------------------------------------
+    def pack(self, state):
+        flat = []
+        for s in state:
+            flat += s if isinstance(s, list) else [s]
+        return torch.cat(flat, dim=1)
+
+    def unpack(self, tensor):
+        vars_ = list(torch.split(tensor, tensor.shape[1] // self.state_dim, dim=1))
+        out, start = [], 0
+        for d in self.state_split:
+            if d == 1:
+                out.append(vars_[start].contiguous())
+                start += 1
+            else:
+                out.append([t.contiguous() for t in vars_[start:start + d[0]]])
+                start += d[0]
+        return out
+
+    @property
+    def state_dim(self):
+        return sum(s[0] if isinstance(s, list) else s for s in self.state_split)
+
+    @property
+    def nparams(self):
+        return len(self.psi_fns) + 1
+
+    @property
+    def state_split(self):
+        raise NotImplementedError
+
+
+class ADMM(Algorithm):
+    """algo/admm.py:25-76."""
+    method = "admm"
+
+    @classmethod
+    def partition(cls, prox_fns: List[ProxFn]):
+        omega, took_ext = [], False
+        for fn in prox_fns:
+            if not took_ext and isinstance(fn, ext_sum_squares):
+                omega.append(fn)
+                took_ext = True
+            elif type(fn) == sum_squares:
+                omega.append(fn)
+        psi = [fn for fn in prox_fns if not any(fn is o for o in omega)]
+        return psi, omega
+
+    @property
+    def state_split(self):
+        return [1, [len(self.psi_fns)], [len(self.psi_fns)]]
+
+
+class LinearizedADMM(ADMM):
+    """algo/admm.py:79-100.  Identity psi linops: bit-for-bit the ADMM kernels (the reference's b_i collapses to
+    v_i - u_i there); other linops: the reference's exact (self-inconsistent, App. A-6) update via the generic engine."""
+    method = "ladmm"
+
+
+class ADMM_vxu(ADMM):
+    """algo/admm.py:103-120 (per-sample semantics; the reference's batch-index slip for a single psi fn,
+    App. A-17, is not reproduced)."""
+    method = "admm_vxu"
+
+
+class HQS(ADMM):
+    """algo/hqs.py."""
+    method = "hqs"
+
+    @property
+    def state_split(self):
+        return [1, [len(self.psi_fns)]]
+
+
+class ProximalGradientDescent(Algorithm):
+    """algo/pgd.py."""
+    method = "pgd"
+
+    @classmethod
+    def partition(cls, prox_fns: List[ProxFn]):
+        if len(prox_fns) != 2:
+            raise ValueError("Proximal gradient descent only supports two proximal functions for now.")
+        omega = [fn for fn in prox_fns if hasattr(fn, "grad")]
+        psi = [fn for fn in prox_fns if not any(fn is o for o in omega)]
+        if len(omega) == 0:
+            raise ValueError("Proximal gradient descent requires at least one proximal function is differentiable.")
+        return psi, omega
+
+    @property
+    def state_split(self):
+        return [1]
+
+
+SOLVERS = {"admm": ADMM, "admm_vxu": ADMM_vxu, "ladmm": LinearizedADMM, "hqs": HQS, "pgd": ProximalGradientDescent}
+
+
+def compile(prox_fns: List[ProxFn], method: str = "admm", device: Union[str, torch.device] = "cuda", **kwargs):  # noqa: A001
+    """Compile an objective into a solver (algo/primitives.py:40-67).  `device` must be a CUDA device for `solve()`."""
+    if method not in SOLVERS:
+        raise ValueError(f"unknown or unsupported method {method!r} (supported: {sorted(SOLVERS)}; "
+                         f"'pc' is listed as next in SURVEY §8f)")
+    if isinstance(prox_fns, ProxFn):
+        prox_fns = [prox_fns]
+    algorithm = SOLVERS[method]
+    device = torch.device(device) if isinstance(device, str) else device
+    psi_fns, omega_fns = algorithm.partition(prox_fns)
+    solver = algorithm.create(psi_fns, omega_fns, **kwargs)
+    return solver.to(device)
+
+
+def specialize(solver: Algorithm, method: str = "unroll", device="cuda", **kwargs):
+    """algo/primitives.py:70-95 — only the shared-parameter unrolling (`partial`-bound solve kwargs, unroll.py:14-18)."""
+    if method != "unroll" or kwargs.get("share", True) is not True:
+        raise NotImplementedError("only specialize(..., method='unroll', share=True) is available in this backend")
+    kwargs.pop("share", None)
+    solver.solve = partial(solver.solve, **kwargs)
+    return solver
+
+
+class Problem:
+    """algo/problem.py:13-58 (the LP branch is out of scope)."""
+
+    def __init__(self, prox_fns, constraints=[], absorb=True, merge=True, try_diagonalize=True, try_freq_diagonalize=True,
+                 linear_solve_config=LinearSolveConfig()):
+        if isinstance(prox_fns, ProxFn):
+            prox_fns = [prox_fns]
+        self.prox_fns = prox_fns
+        self.solver_args = dict(try_diagonalize=try_diagonalize, try_freq_diagonalize=try_freq_diagonalize,
+                                linear_solve_config=linear_solve_config)
+
+    @property
+    def objective(self):
+        return self.prox_fns
+
+    def solve(self, method="admm", device="cuda", **kwargs):
+        solver = compile(self.prox_fns, method=method, device=device, **self.solver_args)
+        return solver.solve(**kwargs)
+
+
+def log_descent(upper, lower, iter=24, sigma=0.255 / 255, w=1.0, lam=0.23, sqrt=False):
+    """rho/sigma schedules of DPIR (algo/tune/dpir.py:13-39)."""
+    s_log = np.logspace(np.log10(upper), np.log10(lower), iter).astype(np.float32)
+    s_lin = np.linspace(upper, lower, iter).astype(np.float32)
+    sigmas = (s_log * w + s_lin * (1 - w)) / 255.0
+    rhos = [lam * (sigma ** 2) / (s ** 2) for s in sigmas]
+    if not sqrt:
+        sigmas = sigmas ** 2
+    return torch.tensor(np.asarray(rhos)).float(), torch.tensor(np.asarray(sigmas)).float()

@@ -1,0 +1,120 @@
+"""Matrix-free linear solvers (mirrors dprox.linalg).
+
+The operator `A` is any Python callable on CUDA tensors (the plugin surface: LinOp trees, user
+BlackBoxes); everything *around* it — dot products, the x/r update, the direction update — runs in
+three fused sm_100a kernels (`dpx_cg_dot`, `dpx_cg_update`, `dpx_cg_direction`), so one CG step costs
+28 B/element of vector traffic instead of the reference's ~10 full-tensor passes, and there is no
+host synchronisation per step unless the stop test is asked for (`check_every`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from functools import partial
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass
+class LinearSolveConfig:
+    """dprox/linalg/custom.py:9-26."""
+    rtol: float = 1e-6
+    max_iters: int = 100
+    verbose: bool = False
+    solver_type: str = "cg"
+    solver_kwargs: dict = field(default_factory=dict)
+    use_analytic_grad: bool = True
+
+
+def cg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: float = 1e-6, max_iters: int = 100,
+       verbose: bool = False, check_every: int = 1):
+    """Conjugate gradients, batched over dim 0 (linalg/solve/solver_cg.py:56-136).
+
+    Stop test: per-sample ||r_b|| <= rtol * ||b_b|| for all b.  (The reference compares the *spectral*
+    norm of the [B,n] residual matrix with the per-sample tolerances, solver_cg.py:103-104; for B == 1
+    the two coincide — SURVEY App. A-7.)  The test needs one 4*B-byte device->host read; set
+    `check_every=k` to do it only every k steps (0 = never, always run `max_iters`).
+    """
+    x = torch.zeros_like(b) if x0 is None else x0.clone()
+    r = b.clone() if x0 is None else ops.axpby(1.0, b, -1.0, A(x))
+    n_it = int(min(max_iters, int(np.prod(b.shape))))
+    tol2 = None
+    if check_every:
+        bn2 = ops.dot(b, b)
+        tol2 = (rtol * rtol) * bn2
+    gamma = ops.dot(r, r)
+    p = None
+    it = 0
+    for it in range(n_it):
+        if check_every and it % check_every == 0 and bool(torch.all(gamma <= tol2)):
+            if verbose:
+                print("Converged at CG Iter %03d" % it)
+            break
+        if it == 0:
+            p = r.clone()
+        q = A(p)
+        pq = ops.dot(p, q)
+        gamma_new = ops.cg_update(x, r, p, q, gamma, pq)        # x += a p ; r -= a q ; <r,r>
+        ops.cg_direction(p, r, gamma_new, gamma)                # p = r + (g'/g) p
+        gamma = gamma_new
+    return x
+
+
+def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: float = 1e-6, max_iters: int = 100,
+        verbose: bool = False, Minv: Optional[Callable] = None, check_every: int = 1):
+    """Preconditioned CG with the reference's conventions (solver_cg.py:172-233): starts from ones,
+    whole-tensor dot products, absolute inf-norm stop `max|r| < rtol`.
+
+    With `Minv=None` it is algebraically CG started at ones with global dots: the same three fused
+    kernels are used with batch=1 (the residual tracked here is b - A x = -r_ref)."""
+    x = torch.ones_like(b) if x0 is None else x0.clone()
+    r = ops.axpby(1.0, b, -1.0, A(x))
+    if Minv is None:
+        gamma = ops.dot(r, r, per_sample=False)
+        p = r.clone()
+        for it in range(max_iters):
+            q = A(p)
+            pq = ops.dot(p, q, per_sample=False)
+            gamma_new = ops.cg_update(x, r, p, q, gamma, pq, per_sample=False)
+            ops.cg_direction(p, r, gamma_new, gamma, per_sample=False)
+            gamma = gamma_new
+            if check_every and (it + 1) % check_every == 0 and float(ops.absmax(r)) < rtol:
+                break
+        return x
+    # general preconditioner: y = Minv(r) is a user callable; dots/axpys stay native
+    y = Minv(r)
+    p = y.clone()
+    ry = ops.dot(r, y, per_sample=False)
+    for it in range(max_iters):
+        q = A(p)
+        pq = ops.dot(p, q, per_sample=False)
+        alpha = ry / pq
+        x = ops.lincomb(x, None, p, alpha)
+        r = ops.lincomb(r, None, q, -alpha)
+        y = Minv(r)
+        ry_new = ops.dot(r, y, per_sample=False)
+        p = ops.lincomb(y, None, p, ry_new / ry)
+        ry = ry_new
+        if check_every and (it + 1) % check_every == 0 and float(ops.absmax(r)) < rtol:
+            break
+    return x
+
+
+SOLVERS = {"cg": cg, "pcg": pcg}
+
+
+def _build_solver(config: LinearSolveConfig):
+    if config.solver_type not in SOLVERS:
+        raise NotImplementedError(f"solver_type={config.solver_type!r}: only {sorted(SOLVERS)} are lowered "
+                                  f"(minres/plss are out of scope, SURVEY §2 row 22)")
+    return partial(SOLVERS[config.solver_type], rtol=config.rtol, max_iters=config.max_iters, verbose=config.verbose,
+                   **config.solver_kwargs)
+
+
+def linear_solve(A: Callable, b: torch.Tensor, config: LinearSolveConfig = LinearSolveConfig()):
+    """Solve A x = b matrix-free (linalg/custom.py:65-82).  Forward only: the implicit-differentiation
+    backward of the reference (custom.py:48-62) is not part of this backend yet."""
+    return _build_solver(config)(A, b)

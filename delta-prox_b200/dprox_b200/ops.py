@@ -1,0 +1,171 @@
+"""Thin, typed wrappers over the stand-alone C-ABI kernels (no torch arithmetic here).
+
+Everything takes/returns CUDA fp32 torch tensors; torch is only the allocator and stream owner."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _cabi as cabi
+from .tensors import as_bchw
+
+_fft_plans = {}
+
+
+def _s(t):
+    return cabi.stream_ptr(t.device)
+
+
+def _new_like(x):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def axpby(a: float, x: torch.Tensor, b: float = 0.0, y: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
+    """out = a*x + b*y  (scale / sum / subtraction glue; linop/scale.py, linop/sum.py)."""
+    x = cabi.require_cuda_f32(x, "x")
+    if y is not None:
+        y = cabi.require_cuda_f32(y, "y")
+        if y.shape != x.shape:
+            y = y.expand_as(x).contiguous()
+    out = _new_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_axpby(cabi.ptr(out), float(a), cabi.ptr(x), float(b), cabi.ptr(y), x.numel(), _s(x)),
+                   "dpx_axpby")
+    return out
+
+
+def lincomb(x, a=None, y=None, b=None, z=None, c=None, out=None) -> torch.Tensor:
+    """out = a*x + b*y + c*z with per-sample ([B]) or shared ([1]) DEVICE coefficients (None = 1)."""
+    x = cabi.require_cuda_f32(x, "x")
+    B = x.shape[0]
+    per = x.numel() // B
+    coeffs = [t for t in (a, b, c) if t is not None]
+    cps = 1 if any(t.numel() > 1 for t in coeffs) else 0
+    fix = lambda t: None if t is None else cabi.require_cuda_f32(t.reshape(-1).expand(B) if (cps and t.numel() == 1) else t.reshape(-1), "coeff")
+    a, b, c = fix(a), fix(b), fix(c)
+    y = None if y is None else cabi.require_cuda_f32(y, "y")
+    z = None if z is None else cabi.require_cuda_f32(z, "z")
+    out = _new_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_lincomb(cabi.ptr(out), cabi.ptr(a), cabi.ptr(x), cabi.ptr(b), cabi.ptr(y), cabi.ptr(c),
+                                          cabi.ptr(z), cps, B, per, _s(x)), "dpx_lincomb")
+    return out
+
+
+def mul(x: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
+    """out = w * x with w of batch 1 or B (mosaic / mul_elementwise)."""
+    x = cabi.require_cuda_f32(x, "x")
+    w = cabi.require_cuda_f32(w.to(x.device), "w")
+    B = x.shape[0]
+    per = x.numel() // B
+    if w.numel() == x.numel():
+        wb = B
+    elif w.numel() == per:
+        wb = 1
+    else:
+        w = w.expand(1, *x.shape[1:]).contiguous() if w.shape[0] == 1 else w.expand_as(x).contiguous()
+        wb = w.shape[0]
+    out = _new_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_mul_apply(cabi.ptr(out), cabi.ptr(x), cabi.ptr(w), wb, B, per, _s(x)), "dpx_mul_apply")
+    return out
+
+
+def grad(x: torch.Tensor, axis: int, adjoint: bool = False, scale: float = 1.0) -> torch.Tensor:
+    """Circular forward difference along H (axis=0) or W (axis=1), or its adjoint (linop/grad.py:8-23)."""
+    x = cabi.require_cuda_f32(x, "x")
+    x4 = as_bchw(x)
+    out = _new_like(x)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_grad_apply(cabi.ptr(x), cabi.ptr(out), x4.shape[0] * x4.shape[1], x4.shape[2], x4.shape[3],
+                                             int(axis), int(adjoint), float(scale), _s(x)), "dpx_grad_apply")
+    return out
+
+
+def prox(kind: int, v: torch.Tensor, lam: torch.Tensor, alpha=1.0, beta=1.0, lo=0.0, hi=0.0, offset=None, out=None):
+    """ProxFn.prox with the wrapper chain for a native `_prox` body (proxfn/base.py:55-64)."""
+    v = cabi.require_cuda_f32(v, "v")
+    B = v.shape[0] if v.ndim > 0 else 1
+    lam = cabi.require_cuda_f32(lam.to(v.device, torch.float32).reshape(-1), "lam")
+    if lam.numel() not in (1, B):
+        raise ValueError(f"lam must have 1 or B={B} entries, got {lam.numel()}")
+    if offset is not None:
+        offset = cabi.require_cuda_f32(offset.to(v.device).expand_as(v), "offset")
+    out = _new_like(v) if out is None else out
+    with torch.cuda.device(v.device):
+        cabi.check(cabi.lib().dpx_prox_apply(int(kind), cabi.ptr(v), cabi.ptr(lam), int(lam.numel() > 1), float(alpha), float(beta),
+                                             float(lo), float(hi), cabi.ptr(offset), cabi.ptr(out), B, v.numel() // B, _s(v)),
+                   "dpx_prox_apply")
+    return out
+
+
+def fft_plan(shape, device) -> cabi.NativePlan:
+    """A constants-free FREQ_DIAG plan used as the FFT context of stand-alone spectral filters."""
+    key = (tuple(shape), str(device))
+    if key not in _fft_plans:
+        d = cabi.ProblemDesc()
+        d.abi_version = cabi.ABI_VERSION
+        d.batch, d.channels, d.height, d.width = shape
+        d.algo, d.xupdate, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, cabi.X_FREQ_DIAG, 0, 1e-7, cabi.FFT_CUFFT
+        _fft_plans[key] = cabi.NativePlan(d, torch.device(device))
+    return _fft_plans[key]
+
+
+def spectral_filter(x: torch.Tensor, otf: torch.Tensor, conj: bool = False, plan: Optional[cabi.NativePlan] = None):
+    """y = Re F^-1(otf * F x) (or conj(otf)): conv.forward / conv.adjoint (linop/conv.py:31-41).
+    `otf` is a complex64 half spectrum [1|B, C, H, W/2+1]."""
+    x = cabi.require_cuda_f32(x, "x")
+    x4 = as_bchw(x)
+    B, Cc, H, W = x4.shape
+    if otf.dtype != torch.complex64:
+        otf = otf.to(torch.complex64)
+    otf = otf.to(x.device).contiguous()
+    if tuple(otf.shape[-3:]) != (Cc, H, W // 2 + 1):
+        raise ValueError(f"OTF shape {tuple(otf.shape)} does not match input {tuple(x4.shape)}")
+    ob = otf.shape[0] if otf.ndim == 4 else 1
+    plan = plan or fft_plan((B, Cc, H, W), x.device)
+    out = _new_like(x)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_spectral_filter(plan.handle, cabi.ptr(x), C.c_void_p(otf.data_ptr()), ob, int(conj),
+                                                  cabi.ptr(out), _s(x)), "dpx_spectral_filter")
+    return out
+
+
+def dot(x: torch.Tensor, y: torch.Tensor, per_sample: bool = True) -> torch.Tensor:
+    """bdot (linalg/solve/solver_cg.py:7-22): per-sample <x_b, y_b> -> device [B] (or [1] when not per_sample)."""
+    x, y = cabi.require_cuda_f32(x, "x"), cabi.require_cuda_f32(y, "y")
+    B = x.shape[0] if per_sample else 1
+    out = torch.empty(B, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_cg_dot(cabi.ptr(x), cabi.ptr(y), cabi.ptr(out), B, x.numel() // B, _s(x)), "dpx_cg_dot")
+    return out
+
+
+def absmax(x: torch.Tensor, per_sample: bool = False) -> torch.Tensor:
+    x = cabi.require_cuda_f32(x, "x")
+    B = x.shape[0] if per_sample else 1
+    out = torch.empty(B, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_absmax(cabi.ptr(x), cabi.ptr(out), B, x.numel() // B, _s(x)), "dpx_absmax")
+    return out
+
+
+def cg_update(x, r, p, q, gamma, pq, per_sample=True) -> torch.Tensor:
+    """alpha = gamma/pq; x += alpha p; r -= alpha q; returns the new <r,r> (device [B])."""
+    B = x.shape[0] if per_sample else 1
+    gn = torch.empty(B, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_cg_update(cabi.ptr(x), cabi.ptr(r), cabi.ptr(p), cabi.ptr(q), cabi.ptr(gamma), cabi.ptr(pq),
+                                            cabi.ptr(gn), B, x.numel() // B, _s(x)), "dpx_cg_update")
+    return gn
+
+
+def cg_direction(p, r, gamma_new, gamma_old, per_sample=True):
+    """p = r + (gamma_new/gamma_old) p, in place."""
+    B = p.shape[0] if per_sample else 1
+    with torch.cuda.device(p.device):
+        cabi.check(cabi.lib().dpx_cg_direction(cabi.ptr(p), cabi.ptr(r), cabi.ptr(gamma_new), cabi.ptr(gamma_old), B,
+                                               p.numel() // B, _s(p)), "dpx_cg_direction")
+    return p

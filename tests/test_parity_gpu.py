@@ -1,0 +1,320 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+Every test drives the product path — Python host mirror -> ctypes -> libdprox_b200.so -> sm_100a kernels —
+and compares with (i) golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+(ii) the CPU oracle on the same seeded inputs.  Tolerance: 1e-5 relative L2 in fp32 (BASELINE.json
+north_star) on the primal variable; the sparse auxiliary variables (v, u after a threshold) get 5e-5 because
+their norm is tiny relative to the absolute fp32 round-off of x.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dprox_oracle as orc
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL_X, TOL_AUX = 1e-5, 5e-5
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import dprox_b200
+    from dprox_b200 import _cabi
+    _cabi.lib()                                   # fail loudly if the native library is missing
+    return dprox_b200
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def check_state(state, g, prefix="", tol_x=TOL_X, tol_aux=TOL_AUX):
+    for name, s in zip(["s0", "s1", "s2"], state):
+        if isinstance(s, (list, tuple)):
+            for i, e in enumerate(s):
+                r = rel(e, g[f"{prefix}{name}_{i}"])
+                assert r < tol_aux, (name, i, r)
+        else:
+            r = rel(s, g[prefix + name])
+            assert r < tol_x, (name, r)
+
+
+def run(dp, fns, method, x0, T_, rhos=None, lams=None, **kw):
+    solver = dp.compile(fns, method=method, device="cuda", **kw)
+    return solver, solver.solve(x0=x0, rhos=rhos, lams=lams, max_iter=T_, return_full_states=True)
+
+
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case,method", [("admm_conv_nonneg", "admm"), ("hqs_conv_nonneg", "hqs"),
+                                         ("ladmm_conv_nonneg_b1", "ladmm"), ("vxu_conv_nonneg_b1", "admm_vxu"),
+                                         ("admm_even_kernel", "admm")])
+@pytest.mark.parametrize("backend", [1, 0])       # 1 = cuFFT engine, 0 = auto (fused sm_100a FFT when the shape allows)
+def test_headline_objective(dp, case, method, backend):
+    g = load(case)
+    k = g["psf"] if "psf" in g else g["kernel"]
+    x = dp.Variable()
+    b = T(g["b"])
+    solver, st = run(dp, dp.sum_squares(dp.conv(x, k) - b) + dp.nonneg(x), method, b, int(g["T"]),
+                     rhos=float(g["rho"]) if "rho" in g else None, fft_backend=backend)
+    assert solver.spec.tier == "native"
+    check_state(st, g)
+    assert rel(x.value, g["s0"]) < TOL_X          # Variable.value holds the result (examples read x.value)
+
+
+def test_admm_50_iterations_and_fp64_arbiter(dp):
+    g = load("admm_conv_nonneg_50it")
+    x = dp.Variable()
+    b = T(g["b"])
+    _, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x), "admm", b, 50, rhos=0.5, lams=0.02)
+    check_state(st, g, tol_x=1.5e-5, tol_aux=1e-4)      # reference's own fp32 noise is 8e-6 at 50 it
+    data = orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), c=torch.from_numpy(g["b"]))
+    x64 = orc.Solver([data, orc.Term("nonneg")], "admm", dtype=torch.float64).solve(
+        torch.from_numpy(g["b"]).double(), rhos=0.5, lams=0.02, max_iter=50)
+    ours, ref = rel(st[0], x64), rel(g["s0"], x64)
+    assert ours < 1e-5 and ours < 2 * ref + 1e-6, (ours, ref)
+
+
+@pytest.mark.parametrize("case,kind", [("pgd_conv_nonneg", "nonneg"), ("pgd_conv_norm1", "norm1")])
+def test_pgd(dp, case, kind):
+    g = load(case)
+    x = dp.Variable()
+    b = T(g["b"])
+    prox = dp.nonneg(x) if kind == "nonneg" else dp.norm1(x)
+    _, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]), b) + prox, "pgd", b, int(g["T"]), rhos=float(g["rho"]),
+                lams=float(g["lam"]) if "lam" in g else None)
+    check_state(st, g)
+
+
+def test_two_psi_per_sample_schedules(dp):
+    g = load("admm_two_psi_per_sample")
+    x = dp.Variable()
+    b = T(g["b"])
+    f1, f2 = float(g["alpha1"]) * dp.norm1(x), dp.nonneg(x)
+    _, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + f1 + f2, "admm", b, int(g["T"]), rhos=T(g["rhos"], "cpu"),
+                lams={f1: T(g["lam1"], "cpu"), f2: T(g["lam2"], "cpu")})
+    check_state(st, g)
+
+
+def test_hqs_two_psi(dp):
+    g = load("hqs_two_psi_norm2")
+    x = dp.Variable()
+    b = T(g["b"])
+    f1, f2 = dp.norm2(x), dp.norm1(x)
+    _, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + f1 + f2, "hqs", b, int(g["T"]), rhos=float(g["rho"]),
+                lams={f1: float(g["lam1"]), f2: float(g["lam2"])})
+    check_state(st, g)
+
+
+def test_psi_offset(dp):
+    g = load("admm_psi_offset")
+    x = dp.Variable()
+    b, c = T(g["b"]), T(g["c"])
+    _, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(x - c), "admm", b, int(g["T"]), rhos=float(g["rho"]),
+                lams=float(g["lam"]))
+    check_state(st, g)
+
+
+@pytest.mark.parametrize("case,method,extra", [("admm_tv", "admm", False), ("hqs_tv_nonneg", "hqs", True)])
+def test_tv_stencil_closed_form(dp, case, method, extra):
+    g = load(case)
+    x = dp.Variable()
+    b = T(g["b"])
+    fns = dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(dp.grad(x, dim=0)) + dp.norm1(dp.grad(x, dim=1))
+    if extra:
+        fns = fns + dp.nonneg(x)
+    solver, st = run(dp, fns, method, b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert solver.spec.tier == "native"
+    check_state(st, g)
+
+
+def test_linops_against_reference(dp):
+    g = load("linops")
+    t = T(g["t"])
+    x = dp.Variable()
+    for name, op in [("conv", dp.conv(x, g["psf"])), ("conv2", dp.conv(x, g["k2"])), ("grad0", dp.grad(x, dim=0)),
+                     ("grad1", dp.grad(x, dim=1))]:
+        assert rel(op.forward(t), g[name + "_fwd"]) < 2e-6, name
+        assert rel(op.adjoint(t), g[name + "_adj"]) < 2e-6, name
+        fb = op._FB(tuple(t.shape)).numpy()
+        assert np.abs(fb - g[name + "_otf"]).max() < 1e-5, name
+    assert rel(dp.mosaic(x).forward(t), g["mosaic_fwd"]) == 0.0
+    # dot-product (adjointness) tests, tests/test_linop.py:10-103
+    for op in (dp.conv(x, g["psf"]), dp.grad(x, dim=0) + dp.grad(x, dim=1), dp.mosaic(x),
+               dp.vstack([dp.mosaic(x), dp.grad(x)])):
+        assert dp.CompGraph(op).sanity_check()
+
+
+def test_offset_value_algebra(dp):
+    """tests/test_linop.py:26-40."""
+    x = dp.Variable()
+    y = 3 * (x - torch.tensor([2, 2, 2]))
+    x.value = torch.tensor([1.0, 2.0, 3.0], device="cuda")
+    y = y.to("cuda")
+    assert torch.allclose(y.value.cpu(), 3 * (torch.tensor([1.0, 2.0, 3.0]) - 2))
+    assert torch.allclose(y.offset.cpu(), -3 * torch.tensor([2.0, 2.0, 2.0]))
+    out = dp.eval(y, torch.tensor([1.0, 2.0, 3.0], device="cuda"), zero_out_constant=False)
+    assert torch.allclose(out.cpu(), torch.tensor([-3.0, 0.0, 3.0]))
+
+
+def test_spatial_diag_paths(dp):
+    g = load("admm_mosaic_spatial")
+    x = dp.Variable()
+    b = T(g["b"])
+    solver, st = run(dp, dp.sum_squares(dp.mosaic(x) - b) + dp.nonneg(x), "admm", b, int(g["T"]), rhos=float(g["rho"]))
+    assert (solver.spec.diagonalizable, solver.spec.freq_diagonalizable) == tuple(bool(v) for v in g["flags"])
+    assert solver.spec.xupdate == "spatial"
+    check_state(st, g)
+    g = load("hqs_mul_elementwise")
+    x = dp.Variable()
+    b = T(g["b"])
+    _, st = run(dp, dp.sum_squares(dp.mul_elementwise(x, T(g["w"])) - b) + dp.norm1(x), "hqs", b, int(g["T"]),
+                rhos=float(g["rho"]), lams=float(g["lam"]))
+    check_state(st, g)
+
+
+@pytest.mark.parametrize("case,solver", [("admm_cg_mosaic_conv", "cg"), ("admm_pcg_mosaic_conv", "pcg")])
+def test_cg_fallback(dp, case, solver):
+    g = load(case)
+    x = dp.Variable()
+    b = T(g["b"])
+    cfg = dp.LinearSolveConfig(rtol=1e-6, max_iters=int(g["cg_iters"]), solver_type=solver)
+    s, st = run(dp, dp.sum_squares(dp.mosaic(dp.conv(x, g["psf"])) - b) + dp.nonneg(x), "admm", b, int(g["T"]),
+                rhos=float(g["rho"]), linear_solve_config=cfg)
+    assert s.spec.tier == "generic" and s.spec.xupdate == "cg"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+
+
+def test_linear_solvers_known_answers(dp):
+    g = load("linear_solvers")
+    x = dp.Variable()
+    cv = dp.conv(x, g["psf"])
+    rhs = T(g["rhs"])
+    Aop = lambda v: dp.linalg.ops.axpby(1.0, v, 0.5, cv.adjoint(cv.forward(v)))
+    assert rel(dp.linalg.cg(Aop, rhs, rtol=1e-6, max_iters=12), g["cg_conv"]) < 1e-5
+    assert rel(dp.linalg.pcg(Aop, rhs, rtol=1e-6, max_iters=12), g["pcg_conv"]) < 1e-5
+    # converged solve: residual of the normal equations
+    xs = dp.linalg.cg(Aop, rhs, rtol=1e-6, max_iters=100)
+    assert rel(Aop(xs), rhs) < 5e-6
+
+
+def test_ml_problems_known_answers(dp):
+    """tests/problem/test_ml_problems.py:5-44 with device='cuda'."""
+    rhs = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    x = dp.Variable((3, 3))
+    dp.Problem(dp.sum_squares(2 * x - rhs)).solve("admm", x0=np.zeros((3, 3)))
+    assert (x.value.cpu().numpy() == rhs / 2).all()
+    x = dp.Variable((3, 3))
+    dp.Problem(dp.sum_squares(2 * x, rhs)).solve("admm", x0=np.zeros((3, 3)))
+    assert (x.value.cpu().numpy() == rhs / 2).all()
+    x = dp.Variable((3, 3, 1))
+    rhs2 = np.array([[[1, 2, 3], [4, 5, 6], [7, 8, 9]]])
+    kernel = np.array([[1, 1], [1, 1]]) / 4
+    dp.Problem(dp.sum_squares(dp.conv(x, kernel) - rhs2)).solve("admm", x0=np.zeros((3, 3, 1)))
+    out = dp.eval(dp.conv(x, kernel) - rhs2, x.value, zero_out_constant=False)
+    assert (out.cpu().numpy() < 1e-5).all()
+    x = dp.Variable((3))
+    rhs3 = np.array([1, 2, 3])
+    dp.Problem(dp.sum_squares(2 * x - rhs3)).solve("admm", x0=np.zeros(3))
+    assert (x.value.cpu().numpy() == rhs3 / 2).all()
+
+
+def test_conv_doe(dp):
+    g = load("hqs_conv_doe")
+    for tag in ("full", "padded"):
+        psf, b = T(g[f"{tag}_psf"]), T(g[f"{tag}_b"])
+        x = dp.Variable()
+        _, st = run(dp, dp.sum_squares(dp.conv_doe(x, psf, circular=True) - b) + dp.nonneg(x), "hqs", b, int(g["T"]),
+                    rhos=float(g["rho"]))
+        check_state(st, g, prefix=tag + "_")
+
+
+def test_deep_prior_external_prox(dp):
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    g = load("ffdnet_forward")
+    den = FFDNetColorDenoiser(seed=4).cuda()
+    y = den.denoise(T(g["x"]), T(g["sigma"]))
+    assert rel(y, g["y"]) < 1e-5
+    g = load("admm_deep_prior_ffdnet")
+    x = dp.Variable()
+    b = T(g["b"])
+    prior, nn_ = dp.deep_prior(x, denoiser=den), dp.nonneg(x)
+    s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + prior + nn_, "admm", b, int(g["T"]), rhos=T(g["rhos"], "cpu"),
+                lams={prior: T(g["sigmas"], "cpu"), nn_: 0.02})
+    assert s.spec.tier == "native" and s.spec.has_external
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+
+
+def test_callback_and_iter_api(dp):
+    """callback(iter=, state=, rho=, lam=) per iteration (base.py:149-156) and the single-step `iter` used by unrolling."""
+    g = load("admm_conv_nonneg")
+    x = dp.Variable()
+    b = T(g["b"])
+    fn_nn = dp.nonneg(x)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - b) + fn_nn, method="admm", device="cuda")
+    seen = []
+    out = solver.solve(x0=b, max_iter=int(g["T"]), callback=lambda iter, state, rho, lam: seen.append((iter, float(rho))))
+    assert [i for i, _ in seen] == list(range(int(g["T"]))) and all(r == 1.0 for _, r in seen)
+    assert rel(out, g["s0"]) < TOL_X
+    state = solver.initialize(b)
+    for _ in range(int(g["T"])):
+        state = solver.iter(state, torch.tensor(1.0), {fn_nn: torch.tensor(0.02)})
+    assert rel(state[0], g["s0"]) < TOL_X
+    packed = solver.pack(state)
+    assert packed.shape[1] == 3 * b.shape[1]
+    un = solver.unpack(packed)
+    assert torch.equal(un[0], state[0]) and torch.equal(un[2][0], state[2][0])
+
+
+def test_residual_stop_and_host_entry(dp):
+    g = load("admm_conv_nonneg")
+    x = dp.Variable()
+    b = T(g["b"])
+    solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x), method="admm", device="cuda")
+    stop = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=5)
+    solver.solve(x0=b, max_iter=200, stop=stop)
+    assert solver.iterations_run < 200 and len(stop.history) == solver.iterations_run // 5
+    assert stop.history[-1][0] < stop.history[0][0]
+    # host-buffer entry point (the e2e leg of bench.py): H2D + T iterations + D2H through one C-ABI call
+    eng = solver.engine(b)
+    x0h = torch.from_numpy(g["b"]).pin_memory()
+    T_ = int(g["T"])
+    out = eng.solve_host(x0h, torch.full((T_,), 1.0), torch.full((T_,), 0.02), T_)
+    assert rel(out, g["s0"]) < TOL_X
+
+
+# ---- size-independent properties at the headline size (BASELINE configs[1] shape) ------------------------
+
+def test_headline_size_properties(dp):
+    """[2,3,2048,2048]: (i) a fixed point stays fixed: with b = K x*, x* >= 0, ADMM started at (x*, v=x*, u=0) returns x*;
+    (ii) linearity of the x-update in (Ktb, v-u); (iii) agreement with the oracle on a 64x64 crop-free sub-problem
+    is covered above, so here we check conv adjointness at full size."""
+    torch.manual_seed(0)
+    B, Cc, H, W = 2, 3, 2048, 2048
+    psf = orc.point_spread_function(15, 5)
+    x = dp.Variable()
+    op = dp.conv(x, psf)
+    xs = torch.rand(B, Cc, H, W, device="cuda")
+    b = op.forward(xs)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), method="admm", device="cuda")
+    out = solver.solve(x0=xs, rhos=1.0, lams=0.02, max_iter=5)
+    assert rel(out, xs) < 5e-6
+    y = torch.rand(B, Cc, H, W, device="cuda")
+    lhs = float(dp.linalg.ops.dot(op.forward(xs), y, per_sample=False))
+    rhs = float(dp.linalg.ops.dot(xs, op.adjoint(y), per_sample=False))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
