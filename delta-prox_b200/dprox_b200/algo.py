@@ -126,6 +126,8 @@ class Algorithm(nn.Module):
             rhos = _to_tensor([float(rhos)] * max_iter)
         if _isscalar(lams):
             lams = {fn: _to_tensor([float(lams)] * max_iter) for fn in self.psi_fns}
+        elif not isinstance(lams, dict):                               # one schedule shared by every psi fn
+            lams = {fn: lams for fn in self.psi_fns}
         lams = {k: _to_tensor([float(v)] * max_iter) if _isscalar(v) else _to_tensor(v) for k, v in lams.items()}
         missing = [str(fn) for fn in self.psi_fns if fn not in lams]
         if missing:
@@ -144,7 +146,7 @@ class Algorithm(nn.Module):
         return state if return_full_states else state[0]
 
     def initialize(self, x0, **kwargs):
-        x0 = _to_tensor(x0, batch=True).to(self.device, torch.float32)
+        x0 = torch.as_tensor(x0).to(self.device, torch.float32)      # already batched by solve() (base.py:20-33)
         return self.engine(x0).initialize(x0)
 
     def iters(self, state, rhos, lams, max_iter, pbar=False, callback=None, stop: Optional[ResidualStop] = None):
