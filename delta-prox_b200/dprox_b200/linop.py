@@ -796,6 +796,9 @@ def evaluate(node: LinOp, env: dict, zero_constants: bool, memo: Optional[dict] 
         out = env[node]
     elif isinstance(node, Constant):
         out = None if zero_constants else node.value
+        dev = next((t.device for t in env.values() if isinstance(t, torch.Tensor)), None)
+        if out is not None and dev is not None and out.device != dev:
+            out = out.to(dev)                            # constants follow the variable's device
     else:
         ins = [evaluate(c, env, zero_constants, memo) for c in node.input_nodes]
         if isinstance(node, (sum,)):

@@ -399,6 +399,20 @@ def admm_deep_prior_ffdnet():
 
 
 @case
+def admm_deep_prior_wellcond():
+    """Same objective with rho = 0.3: well conditioned, so fp32 implementations agree to ~1e-6 (the
+    log_descent schedule above has rho ~ 1e-5, where the reference itself is 1e-3 away from fp64)."""
+    img, psf, b = _deconv_inputs(2, 3, 24, 30, lo=0.0)
+    den = _RandFFDNetColor(seed=4)
+    x = dp.Variable()
+    _, sigmas = dp.log_descent(35, 30, 4)
+    prior, nn_ = dp.deep_prior(x, denoiser=den), dp.nonneg(x)
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + prior + nn_, "admm", b, 4, rhos=0.3,
+               lams={prior: sigmas, nn_: 0.02})
+    return dict(psf=psf, b=_np(b), T=4, rho=0.3, sigmas=_np(sigmas), seed=4, **out)
+
+
+@case
 def ffdnet_forward():
     den = _RandFFDNetColor(seed=4)
     g = torch.Generator().manual_seed(6)

@@ -201,13 +201,15 @@ def test_ffdnet_and_deep_prior():
     y = orc.ffdnet_forward(ws, T(g["x"]), T(g["sigma"]))
     assert rel(y.numpy(), g["y"]) < 1e-5
 
-    g = load("admm_deep_prior_ffdnet")
-    prior = orc.Term("deep_prior", denoiser=lambda v, s: orc.ffdnet_forward(ws, v, s))
-    nn_ = orc.Term("nonneg")
-    s = orc.Solver(deconv_terms(g, [prior, nn_]), "admm")
-    st = s.solve(T(g["b"]), rhos=T(g["rhos"]), lams={prior: T(g["sigmas"]), nn_: 0.02}, max_iter=int(g["T"]),
-                 return_full_states=True)
-    check_state(st, g, 1e-5)
+    for case in ("admm_deep_prior_ffdnet", "admm_deep_prior_wellcond"):
+        g = load(case)
+        prior = orc.Term("deep_prior", denoiser=lambda v, s: orc.ffdnet_forward(ws, v, s))
+        nn_ = orc.Term("nonneg")
+        s = orc.Solver(deconv_terms(g, [prior, nn_]), "admm")
+        rhos = T(g["rhos"]) if "rhos" in g else float(g["rho"])
+        st = s.solve(T(g["b"]), rhos=rhos, lams={prior: T(g["sigmas"]), nn_: 0.02}, max_iter=int(g["T"]),
+                     return_full_states=True)
+        check_state(st, g, 1e-5)
 
 
 def test_schedules():
