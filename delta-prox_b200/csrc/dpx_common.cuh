@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../include/dprox_b200.h"
+#include "dpx_types.cuh"
 
 namespace dpx {
 
@@ -95,34 +96,6 @@ __device__ __forceinline__ void block_sum(float (&vals)[K], float* red) {
       vals[k] = warp_sum(s);
     }
   }
-}
-
-// `_prox` bodies: proxfn/nonneg.py:10-11, proxfn/norm.py:6-27 (+ box).
-__device__ __forceinline__ float prox_body(int kind, float w, float lam, float lo, float hi) {
-  switch (kind) {
-    case DPX_PROX_NONNEG:
-      return fmaxf(w, 0.f);
-    case DPX_PROX_L1:
-      return copysignf(fmaxf(fabsf(w) - lam, 0.f), w);
-    case DPX_PROX_L2SQ:
-      return w / (1.f + 2.f * lam);
-    case DPX_PROX_BOX:
-      return fminf(fmaxf(w, lo), hi);
-    default:
-      return w;
-  }
-}
-
-// ProxFn.prox wrapper chain, proxfn/base.py:12-27,55-64:
-//   translated(affine(scaled(_prox, alpha), beta), off)(v, lam)
-//     = 1/beta * _prox(beta*(v-off), beta*beta*lam*alpha) + off
-struct ProxSpec {
-  int kind;
-  float alpha, beta, inv_beta, lo, hi;
-};
-__device__ __forceinline__ float prox_wrapped(const ProxSpec& s, float v, float lam, float off) {
-  const float lam_eff = s.beta * s.beta * lam * s.alpha;
-  return s.inv_beta * prox_body(s.kind, s.beta * (v - off), lam_eff, s.lo, s.hi) + off;
 }
 
 #endif  // __CUDACC__

@@ -48,6 +48,16 @@ class CufftEngine final : public FftEngine {
 
 int make_fused_engine(const Geom& g, FftEngine** out);   // dpx_fused_fft.cu (returns DPX_ERR_INVALID if unsupported)
 
+int make_cufft_engine(const Geom& g, FftEngine** out) {
+  *out = nullptr;
+  CufftEngine* e = new (std::nothrow) CufftEngine();
+  if (!e) { set_error("out of host memory"); return DPX_ERR_NOMEM; }
+  int rc = e->init(g);
+  if (rc) { e->destroy(); return rc; }
+  *out = e;
+  return DPX_OK;
+}
+
 int make_fft_engine(const Geom& g, int backend, FftEngine** out) {
   *out = nullptr;
   if (backend == 0 || backend == 2) {
@@ -56,12 +66,7 @@ int make_fft_engine(const Geom& g, int backend, FftEngine** out) {
     if (rc == DPX_OK) { *out = f; return DPX_OK; }
     if (backend == 2) return rc;
   }
-  CufftEngine* e = new (std::nothrow) CufftEngine();
-  if (!e) { set_error("out of host memory"); return DPX_ERR_NOMEM; }
-  int rc = e->init(g);
-  if (rc) { e->destroy(); return rc; }
-  *out = e;
-  return DPX_OK;
+  return make_cufft_engine(g, out);
 }
 
 }  // namespace dpx

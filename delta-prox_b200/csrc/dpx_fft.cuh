@@ -17,6 +17,12 @@ class FftEngine {
   virtual int c2r(float2* in, float* out, cudaStream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
   virtual void destroy() = 0;
+  // called whenever the plan's Fourier-diagonal constants change (standard R2C layouts): engines that keep
+  // their own copies (the fused engine packs them) refresh them here
+  virtual int set_constants(const float2* fb_std, const float* dq_std, int dq_batch, cudaStream_t s) {
+    (void)fb_std; (void)dq_std; (void)dq_batch; (void)s;
+    return DPX_OK;
+  }
   // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true
   virtual bool fused() const { return false; }
   virtual int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2* fb, const float* dq,

@@ -1,0 +1,198 @@
+// dpx_fft_core.cuh — in-shared-memory power-of-two FFT building blocks for the fused engine.
+//
+// Compiles under nvcc (device code) and under g++ with -DDPX_EMU (tests/emu: a thread-per-CUDA-thread
+// emulator used to verify the index arithmetic on the CPU box, where there is no GPU).
+//
+// A tile holds COLS independent length-N complex sequences, element (n, c) at float2 index
+//     phys(n, c) = (n + (n >> 3)) * COLS + c
+// (columns interleaved; one padding point-row after every 8 points, which makes every pass below
+// shared-memory bank-conflict free per half-warp for COLS in {2,4} and a radix-8 last pass).
+//
+// Forward transform = decimation in frequency with radices (RA, RB, RC), N = RA*RB*RC:
+//     natural order in  ->  digit-reversed order out:  frequency k = qa + RA*qb + RA*RB*qc  sits at
+//     position pos(k) = qa*(N/RA) + qb*RC + qc.
+// Inverse transform = the same passes run backwards with conjugated twiddles (decimation in time):
+//     digit-reversed in -> natural order out, unnormalised.
+// Working in digit-reversed order between the two costs nothing here because everything done in the
+// frequency domain (the spectral solve) is element-wise: its constants are simply stored pre-permuted.
+#pragma once
+
+#ifdef DPX_EMU
+#include "../../tests/emu/cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define DPX_HD __device__ __forceinline__
+#endif
+
+namespace dpx {
+namespace fft {
+
+DPX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DPX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DPX_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+DPX_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+// multiply by -i (forward) / +i (inverse)
+template <bool INV>
+DPX_HD float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+// exp(-2 pi i k / 16), k = 0..15 (cos, sin tables; sign handled by the caller)
+#define DPX_C16_1 0.92387953251128674f
+#define DPX_S16_1 0.38268343236508977f
+#define DPX_R2 0.70710678118654752f
+
+template <bool INV>
+DPX_HD float2 w16(int k) {   // w16^k forward, conj for inverse; k compile-time after unrolling
+  const float c[16] = {1.f, DPX_C16_1, DPX_R2, DPX_S16_1, 0.f, -DPX_S16_1, -DPX_R2, -DPX_C16_1,
+                       -1.f, -DPX_C16_1, -DPX_R2, -DPX_S16_1, 0.f, DPX_S16_1, DPX_R2, DPX_C16_1};
+  const float s[16] = {0.f, DPX_S16_1, DPX_R2, DPX_C16_1, 1.f, DPX_C16_1, DPX_R2, DPX_S16_1,
+                       0.f, -DPX_S16_1, -DPX_R2, -DPX_C16_1, -1.f, -DPX_C16_1, -DPX_R2, -DPX_S16_1};
+  return make_float2(c[k & 15], INV ? s[k & 15] : -s[k & 15]);
+}
+
+// ---- small DFTs in registers: out[q] = sum_m a[m] w_R^{mq}, natural order in and out ----------------
+template <bool INV>
+DPX_HD void dft2(float2& a0, float2& a1) {
+  const float2 t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+template <bool INV>
+DPX_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+  const float2 s13 = cadd(a1, a3), d13 = mul_mi<INV>(csub(a1, a3));   // (-i)(a1-a3) forward
+  a0 = cadd(s02, s13);
+  a2 = csub(s02, s13);
+  a1 = cadd(d02, d13);
+  a3 = csub(d02, d13);
+}
+
+template <int R, bool INV>
+struct Dft;
+
+template <bool INV>
+struct Dft<2, INV> {
+  static DPX_HD void run(float2 (&a)[2]) { dft2<INV>(a[0], a[1]); }
+};
+template <bool INV>
+struct Dft<4, INV> {
+  static DPX_HD void run(float2 (&a)[4]) { dft4<INV>(a[0], a[1], a[2], a[3]); }
+};
+// R = A*B with m = B*m1 + m2, q = q1 + A*q2:
+//   y[m2][q1] = DFT_A over m1 of a[B*m1+m2];  y *= w_R^{m2 q1};  out[q1 + A*q2] = DFT_B over m2 of y[m2][q1]
+template <bool INV>
+struct Dft<8, INV> {   // A = 4, B = 2
+  static DPX_HD void run(float2 (&a)[8]) {
+    dft4<INV>(a[0], a[2], a[4], a[6]);      // m2 = 0 : y[0][q1] in a[2*q1]
+    dft4<INV>(a[1], a[3], a[5], a[7]);      // m2 = 1 : y[1][q1] in a[2*q1+1]
+    a[3] = cmul(a[3], w16<INV>(2));         // w8^1
+    a[5] = mul_mi<INV>(a[5]);               // w8^2 = -i
+    a[7] = cmul(a[7], w16<INV>(6));         // w8^3
+    // out[q1 + 4*q2] = y[0][q1] +/- y[1][q1]
+    float2 o[8];
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {
+      o[q1] = cadd(a[2 * q1], a[2 * q1 + 1]);
+      o[q1 + 4] = csub(a[2 * q1], a[2 * q1 + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = o[i];
+  }
+};
+template <bool INV>
+struct Dft<16, INV> {  // A = 4, B = 4
+  static DPX_HD void run(float2 (&a)[16]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 4; ++m2) dft4<INV>(a[m2], a[4 + m2], a[8 + m2], a[12 + m2]);   // y[m2][q1] in a[4*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 4; ++q1) {
+#pragma unroll
+      for (int m2 = 1; m2 < 4; ++m2) a[4 * q1 + m2] = cmul(a[4 * q1 + m2], w16<INV>(m2 * q1));
+    }
+    float2 o[16];
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {
+      float2 y0 = a[4 * q1], y1 = a[4 * q1 + 1], y2 = a[4 * q1 + 2], y3 = a[4 * q1 + 3];
+      dft4<INV>(y0, y1, y2, y3);
+      o[q1] = y0; o[q1 + 4] = y1; o[q1 + 8] = y2; o[q1 + 12] = y3;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = o[i];
+  }
+};
+
+// ---- tile geometry ------------------------------------------------------------------------------------
+template <int N_, int RA_, int RB_, int RC_, int COLS_>
+struct Tile {
+  static constexpr int N = N_, RA = RA_, RB = RB_, RC = RC_, COLS = COLS_;
+  static_assert(RA_ * RB_ * RC_ == N_, "N must equal RA*RB*RC");
+  static constexpr int MA = N / RA;          // stride of pass A
+  static constexpr int MB = MA / RB;         // stride of pass B  (== RC)
+  static constexpr int PADDED_N = N + (N >> 3);
+  static constexpr int SMEM_FLOAT2 = PADDED_N * COLS;
+  static DPX_HD int phys(int n, int c) { return (n + (n >> 3)) * COLS + c; }
+  // position of frequency k after the forward (DIF) transform
+  static DPX_HD int pos_of_freq(int k) {
+    const int qa = k % RA, qb = (k / RA) % RB, qc = k / (RA * RB);
+    return qa * MA + qb * MB + qc;
+  }
+  static DPX_HD int freq_of_pos(int p) {
+    const int qa = p / MA, qb = (p % MA) / MB, qc = p % MB;
+    return qa + RA * qb + RA * RB * qc;
+  }
+};
+
+// One shared-memory pass of radix R over sub-blocks of length L (stride M = L/R) for all COLS columns.
+//   forward (INV=false): gather, DFT_R, multiply output q by w_N^{j*q*(N/L)}, scatter back (same places).
+//   inverse (INV=true) : gather, multiply input q by conj(w_N^{j*q*(N/L)}), inverse DFT_R, scatter back.
+// `tw` is the table exp(-2 pi i t / N), t in [0, N).  All threads of the CTA must call this; the caller
+// places __syncthreads() between passes.
+template <class T, int R, int L, bool INV, bool TWIDDLE>
+DPX_HD void smem_pass(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
+  constexpr int M = L / R;
+  constexpr int NTASK = T::COLS * T::N / R;
+  for (int task = tid; task < NTASK; task += nthreads) {
+    const int c = task % T::COLS;
+    const int t2 = task / T::COLS;
+    const int j = t2 % M;
+    const int base = (t2 / M) * L + j;
+    float2 a[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) a[m] = sm[T::phys(base + m * M, c)];
+    if (INV && TWIDDLE) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = cmulc(a[q], tw[j * q * (T::N / L)]);
+    }
+    Dft<R, INV>::run(a);
+    if (!INV && TWIDDLE) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], tw[j * q * (T::N / L)]);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) sm[T::phys(base + m * M, c)] = a[m];
+  }
+}
+
+// Whole transforms on a tile resident in shared memory (used by the row kernel; the column kernel fuses its
+// first/last pass with the global loads/stores and its middle with the spectral solve).
+template <class T>
+DPX_HD void tile_fft_forward(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
+  smem_pass<T, T::RA, T::N, false, true>(sm, tw, tid, nthreads);
+  __syncthreads();
+  smem_pass<T, T::RB, T::MA, false, true>(sm, tw, tid, nthreads);
+  __syncthreads();
+  smem_pass<T, T::RC, T::MB, false, false>(sm, tw, tid, nthreads);
+  __syncthreads();
+}
+template <class T>
+DPX_HD void tile_fft_inverse(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
+  smem_pass<T, T::RC, T::MB, true, false>(sm, tw, tid, nthreads);
+  __syncthreads();
+  smem_pass<T, T::RB, T::MA, true, true>(sm, tw, tid, nthreads);
+  __syncthreads();
+  smem_pass<T, T::RA, T::N, true, true>(sm, tw, tid, nthreads);
+  __syncthreads();
+}
+
+}  // namespace fft
+}  // namespace dpx

@@ -1,0 +1,95 @@
+// dpx_fused_driver.cuh — size dispatch + launch sequencing of the fused engine, shared between the CUDA
+// engine (dpx_fused_fft.cu) and the CPU emulator library (tests/emu/emu_fused.cpp): both provide a
+// `Launcher` with   template<class K> void operator()(K kernel_functor, dim3 grid, size_t smem)   semantics.
+#pragma once
+#include <type_traits>
+
+#include "dpx_fused_kernels.cuh"
+
+namespace dpx {
+namespace fused {
+
+template <int N, int COLS> struct TileFor;
+#define DPX_TILE_FOR(N, A, B, C) \
+  template <int COLS> struct TileFor<N, COLS> { using type = fft::Tile<N, A, B, C, COLS>; };
+DPX_TILE_FOR(64, 4, 4, 4)
+DPX_TILE_FOR(128, 8, 4, 4)
+DPX_TILE_FOR(256, 8, 8, 4)
+DPX_TILE_FOR(512, 8, 8, 8)
+DPX_TILE_FOR(1024, 16, 8, 8)
+DPX_TILE_FOR(2048, 16, 16, 8)
+DPX_TILE_FOR(4096, 16, 16, 16)
+#undef DPX_TILE_FOR
+
+inline bool size_supported(int n) {
+  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
+}
+
+// calls f(std::integral_constant<int, N>{}) for the matching supported N; returns false if unsupported
+template <class F>
+inline bool dispatch_size(int n, F&& f) {
+  switch (n) {
+    case 64: f(std::integral_constant<int, 64>{}); return true;
+    case 128: f(std::integral_constant<int, 128>{}); return true;
+    case 256: f(std::integral_constant<int, 256>{}); return true;
+    case 512: f(std::integral_constant<int, 512>{}); return true;
+    case 1024: f(std::integral_constant<int, 1024>{}); return true;
+    case 2048: f(std::integral_constant<int, 2048>{}); return true;
+    case 4096: f(std::integral_constant<int, 4096>{}); return true;
+    default: return false;
+  }
+}
+
+inline size_t s_elems(int P, int H, int W) { return (size_t)P * ((W / 2) / CG + 1) * H * CG; }     // float2 count of S
+inline size_t packed_elems(int planes, int H, int W) { return (size_t)planes * ((W / 2) / CG + 1) * H * CG; }
+
+// Backends implement:  row<TW,MODE>(grid, smem_bytes, RowParams), col<TH>(grid, smem_bytes, ColParams),
+//                      pack<TH,V>(blocks, src, dst, planes, H, W, G, zero)
+template <class Backend>
+struct Driver {
+  Backend& be;
+  explicit Driver(Backend& b) : be(b) {}
+
+  // packs F(K^T b) (complex, [P,H,Wc]) and sum|OTF|^2 (real, [Cd,H,Wc]) into k_col's record layout
+  void pack_constants(int P, int Cd, int H, int W, const float2* fb_std, float2* fbp, const float* dq_std, float* dqp) {
+    const int G = (W / 2) / CG;
+    dispatch_size(H, [&](auto hn) {
+      using TH = typename TileFor<decltype(hn)::value, CG>::type;
+      if (fb_std) be.template pack<TH, float2>(fb_std, fbp, P, H, W, G, make_float2(0.f, 0.f));
+      if (dq_std) be.template pack<TH, float>(dq_std, dqp, Cd, H, W, G, 0.f);
+    });
+  }
+
+  // n_iters iterations of ADMM (hqs=0) / HQS (hqs=1); state in psi.t[i].v/.u and x; schedules indexed from it0
+  void iterate(int B, int C, int H, int W, float2* S, const PsiPack& psi, int hqs, float* x, const float2* fbp,
+               const float* dqp, int dq_batch, float wid, float eps, const float* rho, int rho_stride, int it0,
+               int n_iters, const float2* tw_h, const float2* tw_w) {
+    if (n_iters <= 0) return;
+    const int P = B * C, G = (W / 2) / CG;
+    dispatch_size(W, [&](auto wn) {
+      dispatch_size(H, [&](auto hn) {
+        using TW = typename TileFor<decltype(wn)::value, ROWS / 2>::type;
+        using TH = typename TileFor<decltype(hn)::value, CG>::type;
+        RowParams rp;
+        rp.C = C; rp.H = H; rp.W = W; rp.G = G; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
+        ColParams cp;
+        cp.C = C; cp.H = H; cp.W = W; cp.G = G; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
+        cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
+        cp.rho.p = rho; cp.rho.stride = rho_stride; cp.tw = tw_h;
+        const dim3 rgrid(H / ROWS, P), cgrid(G + 1, P);
+        const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2), csm = TH::SMEM_FLOAT2 * sizeof(float2);
+        be.template row<TW, ROW_FIRST>(rgrid, rsm, rp);
+        for (int k = 0; k < n_iters; ++k) {
+          cp.rho.it = it0 + k;
+          be.template col<TH>(cgrid, csm, cp);
+          rp.it = it0 + k;
+          if (k + 1 < n_iters) be.template row<TW, ROW_MID>(rgrid, rsm, rp);
+          else be.template row<TW, ROW_LAST>(rgrid, rsm, rp);
+        }
+      });
+    });
+  }
+};
+
+}  // namespace fused
+}  // namespace dpx

@@ -4,33 +4,6 @@
 
 namespace dpx {
 
-struct Geom {
-  int B, C, H, W, Wc;        // Wc = W/2+1
-  int P;                     // planes = B*C
-  size_t plane;              // H*W
-  size_t splane;             // H*Wc
-};
-
-struct PsiTerm {
-  int prox, linop;
-  float scale, alpha, beta, inv_beta, lo, hi;
-  float* v;
-  float* u;
-  const float* off;          // constant inside the linop (A x - off) or nullptr
-  const float* lam;          // schedule; value for (sample b, iteration it) = lam[b*lam_stride + it]
-  int lam_stride;
-};
-struct PsiPack {
-  int n;
-  PsiTerm t[DPX_MAX_PSI];
-};
-
-struct RhoRef {
-  const float* p;            // value for (b, it) = p[b*stride + it]
-  int stride;
-  int it;
-};
-
 // t = sum_i scale_i * A_i^T (v_i - u_i)         [ADMM: hqs=false]   /  A_i^T v_i   [HQS: hqs=true]
 int launch_rhs(const Geom& g, const PsiPack& psi, bool hqs, float* t, cudaStream_t s);
 

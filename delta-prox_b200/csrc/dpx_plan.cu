@@ -214,6 +214,10 @@ int dpx_plan_set_freq_constants(dpx_plan* p, const float* ktb, const float* dq, 
     if (rc) return rc;
     DPX_CUDA(cudaMemcpyAsync(p->dpsi, dpsi, n, cudaMemcpyDeviceToDevice, s));
   }
+  {
+    int rc = p->fft->set_constants(p->fb, p->dq, p->dq ? p->dq_batch : 1, s);
+    if (rc) return rc;
+  }
   p->consts_set = true;
   return DPX_OK;
 }

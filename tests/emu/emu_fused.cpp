@@ -1,0 +1,62 @@
+// emu_fused.cpp — TEST INFRASTRUCTURE: runs the fused FFT engine's kernels (same source as the GPU build)
+// on the CPU through tests/emu/cuda_emu.h.  Built by tests/test_fused_emulator.py with g++ and driven via ctypes.
+#define DPX_EMU
+#include <cmath>
+#include <vector>
+
+#include "dpx_fused_driver.cuh"
+
+using namespace dpx;
+using namespace dpx::fused;
+
+namespace {
+struct EmuBackend {
+  template <class TW, int MODE>
+  void row(dim3 grid, size_t smem, RowParams p) {
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_row<TW, MODE>(p); });
+  }
+  template <class TH>
+  void col(dim3 grid, size_t smem, ColParams p) {
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_col<TH>(p); });
+  }
+  template <class TH, typename V>
+  void pack(const V* src, V* dst, int planes, int H, int W, int G, V zero) {
+    const size_t total = (size_t)planes * (G + 1) * H * CG;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_pack<TH, V>(src, dst, planes, H, W, G, zero); });
+  }
+};
+std::vector<float2> twiddles(int n) {
+  std::vector<float2> t(n);
+  for (int i = 0; i < n; ++i) t[i] = make_float2((float)std::cos(2.0 * M_PI * i / n), (float)-std::sin(2.0 * M_PI * i / n));
+  return t;
+}
+}  // namespace
+
+extern "C" int emu_fused_supported(int n) { return size_supported(n) ? 1 : 0; }
+
+// x, v[i], u[i]: [B,C,H,W] fp32 (updated in place); fb_std: complex64 [B*C,H,W/2+1]; dq_std: [Cd,H,W/2+1], Cd = C or B*C
+// psi_*: per-term arrays; lam: [n_psi][T]; rho: [T]; offsets off[i] may be null
+extern "C" int emu_fused_run(int B, int C, int H, int W, int n_psi, const int* prox, const float* scale, const float* alpha,
+                             const float* beta, float* x, float** v, float** u, const float** off, const float* fb_std,
+                             const float* dq_std, int dq_batch, float wid, float eps, const float* rho, const float* lam, int T,
+                             int hqs) {
+  if (!size_supported(H) || !size_supported(W)) return 1;
+  const int P = B * C, Cd = dq_batch > 1 ? P : C;
+  std::vector<float2> S(s_elems(P, H, W), make_float2(0.f, 0.f));
+  std::vector<float2> fbp(packed_elems(P, H, W));
+  std::vector<float> dqp(packed_elems(Cd, H, W));
+  auto twh = twiddles(H), tww = twiddles(W);
+  EmuBackend be;
+  Driver<EmuBackend> drv(be);
+  drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
+  PsiPack pk;
+  pk.n = n_psi;
+  for (int i = 0; i < n_psi; ++i) {
+    PsiTerm& t = pk.t[i];
+    t.prox = prox[i]; t.linop = 0; t.scale = scale[i]; t.alpha = alpha[i]; t.beta = beta[i]; t.inv_beta = 1.f / beta[i];
+    t.lo = 0.f; t.hi = 1.f; t.v = v[i]; t.u = hqs ? nullptr : u[i]; t.off = off ? off[i] : nullptr;
+    t.lam = lam + (size_t)i * T; t.lam_stride = 0;
+  }
+  drv.iterate(B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), dq_batch, wid, eps, rho, 0, 0, T, twh.data(), tww.data());
+  return 0;
+}

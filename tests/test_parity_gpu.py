@@ -335,3 +335,51 @@ def test_headline_size_properties(dp):
     lhs = float(dp.linalg.ops.dot(op.forward(xs), y, per_sample=False))
     rhs = float(dp.linalg.ops.dot(xs, op.adjoint(y), per_sample=False))
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+# ---- fused sm_100a FFT engine (two kernels per iteration) vs cuFFT engine vs oracle --------------------------
+
+@pytest.mark.parametrize("H,W", [(64, 64), (128, 256), (512, 64)])
+@pytest.mark.parametrize("method", ["admm", "hqs", "ladmm"])
+def test_fused_engine_matches_oracle(dp, H, W, method):
+    g = torch.Generator().manual_seed(H * 7 + W)
+    B, Cc, T_ = 2, 3, 6
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(7, 2.0)
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)
+    c = 0.1 * torch.randn(B, Cc, H, W, generator=g)
+    rhos = 0.5 + torch.rand(B, T_, generator=g)
+    lam1 = 0.01 + 0.05 * torch.rand(B, T_, generator=g)
+    o1, o2 = orc.Term("norm1", alpha=0.5, c=c), orc.Term("nonneg")
+    data = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b)
+    want = orc.Solver([data, o1, o2], method).solve(b.clone(), rhos=rhos, lams={o1: lam1, o2: 0.02}, max_iter=T_,
+                                                    return_full_states=True)
+    outs = {}
+    for backend in (2, 1):
+        x = dp.Variable()
+        bd = b.cuda()
+        f1, f2 = 0.5 * dp.norm1(x - c.cuda()), dp.nonneg(x)
+        s, st = run(dp, dp.sum_squares(dp.conv(x, psf) - bd) + f1 + f2, method, bd, T_, rhos=rhos, lams={f1: lam1, f2: 0.02},
+                    fft_backend=backend)
+        assert s.spec.tier == "native"
+        outs[backend] = st
+        assert rel(st[0], want[0]) < TOL_X, (backend, rel(st[0], want[0]))
+        for i in range(2):
+            assert rel(st[1][i], want[1][i]) < TOL_AUX
+            if method != "hqs":
+                assert rel(st[2][i], want[2][i]) < TOL_AUX
+    assert rel(outs[2][0], outs[1][0]) < 5e-6
+
+
+def test_fused_engine_headline_size_vs_cufft(dp):
+    """[1,3,2048,2048], 5 ADMM iterations: the fused engine and the cuFFT engine agree to fp32 round-off."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    b = torch.rand(1, 3, 2048, 2048, device="cuda", generator=g)
+    psf = orc.point_spread_function(15, 5)
+    res = {}
+    for backend in (2, 1):
+        x = dp.Variable()
+        s = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), method="admm", device="cuda", fft_backend=backend)
+        res[backend] = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=5, return_full_states=True)
+    assert rel(res[2][0], res[1][0]) < 5e-6
+    assert rel(res[2][1][0], res[1][1][0]) < 5e-5 and rel(res[2][2][0], res[1][2][0]) < 5e-5
