@@ -122,15 +122,31 @@ struct Dft<16, INV> {  // A = 4, B = 4
 };
 
 // ---- tile geometry ------------------------------------------------------------------------------------
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+
 template <int N_, int RA_, int RB_, int RC_, int COLS_>
 struct Tile {
   static constexpr int N = N_, RA = RA_, RB = RB_, RC = RC_, COLS = COLS_;
   static_assert(RA_ * RB_ * RC_ == N_, "N must equal RA*RB*RC");
   static constexpr int MA = N / RA;          // stride of pass A
   static constexpr int MB = MA / RB;         // stride of pass B  (== RC)
-  static constexpr int PADDED_N = N + (N >> 3);
+  static constexpr int LOG_MA = ilog2(MA);
+  static_assert(MA % 8 == 0, "pass-A stride must be a multiple of 8");
+  // padded point index: one spare point after every 8 points and one more after every MA points.  With the
+  // thread->task maps used below this makes every pass AND the digit-reversal scatter/gather of the row kernel
+  // free of shared-memory bank conflicts per half-warp (COLS in {2,4}).
+  static DPX_HD int pn(int n) { return n + (n >> 3) + (n >> LOG_MA); }
+  static constexpr int PADDED_N = N + N / 8 + RA;
   static constexpr int SMEM_FLOAT2 = PADDED_N * COLS;
-  static DPX_HD int phys(int n, int c) { return (n + (n >> 3)) * COLS + c; }
+  static DPX_HD int phys(int n, int c) { return pn(n) * COLS + c; }
+  // offset (in points) of element m of a butterfly whose elements are M apart, relative to its first element;
+  // valid for M == MA, for M a multiple of 8 inside one MA-block, and for M == 1 on an RC-aligned block
+  template <int M>
+  static constexpr bool linear() { return M == MA || M % 8 == 0 || M == 1; }
+  template <int M>
+  static DPX_HD int delta(int m) {
+    return M == MA ? m * (MA + MA / 8 + 1) : (M == 1 ? m + (m >> 3) : m * (M + M / 8));
+  }
   // position of frequency k after the forward (DIF) transform
   static DPX_HD int pos_of_freq(int k) {
     const int qa = k % RA, qb = (k / RA) % RB, qc = k / (RA * RB);
@@ -142,44 +158,71 @@ struct Tile {
   }
 };
 
+// Twiddle records: for a pass of radix R over sub-blocks of length L, the factors of butterfly j are stored
+// contiguously, rec[j*R + q] = exp(-2 pi i j q / L), q = 0..R-1 (q = 0 is 1), so a thread fetches them with
+// R/2 128-bit loads.  (tables are built on the host in double precision, see make_twiddle_records)
+template <int R>
+DPX_HD void load_twiddles(const float2* __restrict__ rec, float2 (&w)[R]) {
+  const float4* r4 = reinterpret_cast<const float4*>(rec);
+#pragma unroll
+  for (int q = 0; q < R / 2; ++q) {
+    const float4 v = r4[q];
+    w[2 * q] = make_float2(v.x, v.y);
+    w[2 * q + 1] = make_float2(v.z, v.w);
+  }
+}
+
 // One shared-memory pass of radix R over sub-blocks of length L (stride M = L/R) for all COLS columns.
-//   forward (INV=false): gather, DFT_R, multiply output q by w_N^{j*q*(N/L)}, scatter back (same places).
-//   inverse (INV=true) : gather, multiply input q by conj(w_N^{j*q*(N/L)}), inverse DFT_R, scatter back.
-// `tw` is the table exp(-2 pi i t / N), t in [0, N).  All threads of the CTA must call this; the caller
-// places __syncthreads() between passes.
+//   forward (INV=false): gather, DFT_R, multiply output q by w_L^{j q}, scatter back (same places).
+//   inverse (INV=true) : gather, multiply input q by conj(w_L^{j q}), inverse DFT_R, scatter back.
+// `rec` = twiddle records of this pass (unused when !TWIDDLE).  All threads of the CTA must call this; the
+// caller places __syncthreads() between passes.
 template <class T, int R, int L, bool INV, bool TWIDDLE>
-DPX_HD void smem_pass(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
+DPX_HD void smem_pass(float2* sm, const float2* __restrict__ rec, int tid, int nthreads) {
   constexpr int M = L / R;
   constexpr int NTASK = T::COLS * T::N / R;
+  constexpr bool LIN = T::template linear<M>();
   for (int task = tid; task < NTASK; task += nthreads) {
     const int c = task % T::COLS;
     const int t2 = task / T::COLS;
     const int j = t2 % M;
     const int base = (t2 / M) * L + j;
+    const int p0 = T::phys(base, c);
     float2 a[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) a[m] = sm[T::phys(base + m * M, c)];
-    if (INV && TWIDDLE) {
+    for (int m = 0; m < R; ++m) a[m] = sm[LIN ? p0 + T::template delta<M>(m) * T::COLS : T::phys(base + m * M, c)];
+    if (TWIDDLE) {
+      float2 w[R];
+      load_twiddles<R>(rec + j * R, w);
+      if (INV) {
 #pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmulc(a[q], tw[j * q * (T::N / L)]);
+        for (int q = 1; q < R; ++q) a[q] = cmulc(a[q], w[q]);
+        Dft<R, true>::run(a);
+      } else {
+        Dft<R, false>::run(a);
+#pragma unroll
+        for (int q = 1; q < R; ++q) a[q] = cmul(a[q], w[q]);
+      }
+    } else {
+      Dft<R, INV>::run(a);
     }
-    Dft<R, INV>::run(a);
-    if (!INV && TWIDDLE) {
 #pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], tw[j * q * (T::N / L)]);
-    }
-#pragma unroll
-    for (int m = 0; m < R; ++m) sm[T::phys(base + m * M, c)] = a[m];
+    for (int m = 0; m < R; ++m) sm[LIN ? p0 + T::template delta<M>(m) * T::COLS : T::phys(base + m * M, c)] = a[m];
   }
 }
 
-// Whole transforms on a tile resident in shared memory (used by the row kernel; the column kernel fuses its
-// first/last pass with the global loads/stores and its middle with the spectral solve).
+// twiddle-record table of a tile: [pass A: MA*RA float2][pass B: MB*RB float2]
+template <class T>
+struct TwiddleLayout {
+  static constexpr int A_OFF = 0, B_OFF = T::MA * T::RA, TOTAL = T::MA * T::RA + T::MB * T::RB;
+};
+
+// Whole transforms on a tile resident in shared memory.
 template <class T>
 DPX_HD void tile_fft_forward(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
-  smem_pass<T, T::RA, T::N, false, true>(sm, tw, tid, nthreads);
+  smem_pass<T, T::RA, T::N, false, true>(sm, tw + TwiddleLayout<T>::A_OFF, tid, nthreads);
   __syncthreads();
-  smem_pass<T, T::RB, T::MA, false, true>(sm, tw, tid, nthreads);
+  smem_pass<T, T::RB, T::MA, false, true>(sm, tw + TwiddleLayout<T>::B_OFF, tid, nthreads);
   __syncthreads();
   smem_pass<T, T::RC, T::MB, false, false>(sm, tw, tid, nthreads);
   __syncthreads();
@@ -188,9 +231,9 @@ template <class T>
 DPX_HD void tile_fft_inverse(float2* sm, const float2* __restrict__ tw, int tid, int nthreads) {
   smem_pass<T, T::RC, T::MB, true, false>(sm, tw, tid, nthreads);
   __syncthreads();
-  smem_pass<T, T::RB, T::MA, true, true>(sm, tw, tid, nthreads);
+  smem_pass<T, T::RB, T::MA, true, true>(sm, tw + TwiddleLayout<T>::B_OFF, tid, nthreads);
   __syncthreads();
-  smem_pass<T, T::RA, T::N, true, true>(sm, tw, tid, nthreads);
+  smem_pass<T, T::RA, T::N, true, true>(sm, tw + TwiddleLayout<T>::A_OFF, tid, nthreads);
   __syncthreads();
 }
 

@@ -1,8 +1,12 @@
 // dpx_fused_driver.cuh — size dispatch + launch sequencing of the fused engine, shared between the CUDA
-// engine (dpx_fused_fft.cu) and the CPU emulator library (tests/emu/emu_fused.cpp): both provide a
-// `Launcher` with   template<class K> void operator()(K kernel_functor, dim3 grid, size_t smem)   semantics.
+// engine (dpx_fused_fft.cu) and the CPU emulator library (tests/emu/emu_fused.cpp).  A `Backend` provides
+//   row<TW,MODE>(grid, smem_bytes, RowParams), col<TH>(grid, smem_bytes, ColParams),
+//   pack<TH,V>(src, dst, planes, H, W, G, zero).
 #pragma once
+#include <math.h>
+
 #include <type_traits>
+#include <vector>
 
 #include "dpx_fused_kernels.cuh"
 
@@ -43,8 +47,30 @@ inline bool dispatch_size(int n, F&& f) {
 inline size_t s_elems(int P, int H, int W) { return (size_t)P * ((W / 2) / CG + 1) * H * CG; }     // float2 count of S
 inline size_t packed_elems(int planes, int H, int W) { return (size_t)planes * ((W / 2) / CG + 1) * H * CG; }
 
-// Backends implement:  row<TW,MODE>(grid, smem_bytes, RowParams), col<TH>(grid, smem_bytes, ColParams),
-//                      pack<TH,V>(blocks, src, dst, planes, H, W, G, zero)
+// host-side twiddle records (double precision, rounded once): see fft::TwiddleLayout
+template <class T>
+inline std::vector<float2> make_twiddle_records() {
+  using L = fft::TwiddleLayout<T>;
+  std::vector<float2> t(L::TOTAL);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int j = 0; j < T::MA; ++j)
+    for (int q = 0; q < T::RA; ++q) {
+      const double a = two_pi * (double)j * q / T::N;
+      t[L::A_OFF + j * T::RA + q] = make_float2((float)cos(a), (float)-sin(a));
+    }
+  for (int j = 0; j < T::MB; ++j)
+    for (int q = 0; q < T::RB; ++q) {
+      const double a = two_pi * (double)j * q / T::MA;
+      t[L::B_OFF + j * T::RB + q] = make_float2((float)cos(a), (float)-sin(a));
+    }
+  return t;
+}
+inline std::vector<float2> twiddle_records_for(int n) {
+  std::vector<float2> out;
+  dispatch_size(n, [&](auto nn) { out = make_twiddle_records<typename TileFor<decltype(nn)::value, 1>::type>(); });
+  return out;
+}
+
 template <class Backend>
 struct Driver {
   Backend& be;
@@ -71,13 +97,13 @@ struct Driver {
         using TW = typename TileFor<decltype(wn)::value, ROWS / 2>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         RowParams rp;
-        rp.C = C; rp.H = H; rp.W = W; rp.G = G; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
+        rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
         ColParams cp;
-        cp.C = C; cp.H = H; cp.W = W; cp.G = G; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
+        cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
-        cp.rho.p = rho; cp.rho.stride = rho_stride; cp.tw = tw_h;
+        cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
         const dim3 rgrid(H / ROWS, P), cgrid(G + 1, P);
-        const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2), csm = TH::SMEM_FLOAT2 * sizeof(float2);
+        const size_t rsm = RowSmem<TW>::BYTES, csm = TH::SMEM_FLOAT2 * sizeof(float2);
         be.template row<TW, ROW_FIRST>(rgrid, rsm, rp);
         for (int k = 0; k < n_iters; ++k) {
           cp.rho.it = it0 + k;

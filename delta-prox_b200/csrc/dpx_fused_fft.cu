@@ -114,10 +114,9 @@ class FusedEngine final : public FftEngine {
 
  private:
   static int upload_twiddles(int n, float2** out) {
-    std::vector<float2> t(n);
-    for (int i = 0; i < n; ++i) t[i] = make_float2((float)cos(2.0 * M_PI * i / n), (float)-sin(2.0 * M_PI * i / n));
-    DPX_CUDA(cudaMalloc(out, n * sizeof(float2)));
-    DPX_CUDA(cudaMemcpy(*out, t.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    const std::vector<float2> t = twiddle_records_for(n);
+    DPX_CUDA(cudaMalloc(out, t.size() * sizeof(float2)));
+    DPX_CUDA(cudaMemcpy(*out, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
     return DPX_OK;
   }
   Geom g_{};

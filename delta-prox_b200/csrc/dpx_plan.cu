@@ -376,7 +376,10 @@ int dpx_iters(dpx_plan* p, float* x, float* const* v, float* const* u, const flo
   PsiPack pk = make_pack(p, v, u, lam, lam_stride);
   if (resid) DPX_CUDA(cudaMemsetAsync(resid, 0, sizeof(float) * (size_t)n_iters * g.B * 4, s));
 
-  if (freq && p->fft->fused() && (is_admm_like(a) || hqs) && p->all_identity && !resid) {
+  bool vec_ok = aligned16(x);
+  for (int i = 0; i < pk.n; ++i)
+    vec_ok = vec_ok && aligned16(pk.t[i].v) && (hqs || aligned16(pk.t[i].u)) && (!pk.t[i].off || aligned16(pk.t[i].off));
+  if (freq && p->fft->fused() && (is_admm_like(a) || hqs) && p->all_identity && !resid && vec_ok && pk.n > 0) {
     return p->fft->fused_iters(g, pk, hqs, x, p->fb, p->dq, p->dq_batch, p->wid, p->d.eps, rho, rho_stride, it0, n_iters, s);
   }
 

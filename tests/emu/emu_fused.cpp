@@ -25,11 +25,6 @@ struct EmuBackend {
     emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_pack<TH, V>(src, dst, planes, H, W, G, zero); });
   }
 };
-std::vector<float2> twiddles(int n) {
-  std::vector<float2> t(n);
-  for (int i = 0; i < n; ++i) t[i] = make_float2((float)std::cos(2.0 * M_PI * i / n), (float)-std::sin(2.0 * M_PI * i / n));
-  return t;
-}
 }  // namespace
 
 extern "C" int emu_fused_supported(int n) { return size_supported(n) ? 1 : 0; }
@@ -45,7 +40,7 @@ extern "C" int emu_fused_run(int B, int C, int H, int W, int n_psi, const int* p
   std::vector<float2> S(s_elems(P, H, W), make_float2(0.f, 0.f));
   std::vector<float2> fbp(packed_elems(P, H, W));
   std::vector<float> dqp(packed_elems(Cd, H, W));
-  auto twh = twiddles(H), tww = twiddles(W);
+  auto twh = twiddle_records_for(H), tww = twiddle_records_for(W);
   EmuBackend be;
   Driver<EmuBackend> drv(be);
   drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
