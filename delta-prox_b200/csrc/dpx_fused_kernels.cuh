@@ -61,33 +61,118 @@ DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
   return (((size_t)p * (G + 1) + g) * H + h) * CG + c;
 }
 
-DPX_HD float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-DPX_HD void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming global loads: data touched once per kernel must not evict the twiddle records from the small L1
+// that is left next to ~220 KB of shared memory
+#ifdef DPX_EMU
+DPX_HD float2 ld_stream2(const float2* p) { return *p; }
+DPX_HD float4 ld_stream4(const float4* p) { return *p; }
+#else
+DPX_HD float2 ld_stream2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+DPX_HD float4 ld_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+#endif
 
 template <class TW>
 struct RowSmem {
-  static constexpr int RS = TW::N + 8;                    // row-buffer stride (floats): rows land on different bank halves
+  // tile (padded, pairs interleaved) + twiddle records re-laid out for conflict-free 128-bit shared loads:
+  //   twA_s[(q/2)*MA + j] = (w^{j q}, w^{j (q+1)}),  twB_s[(q/2)*MB + j] likewise
+  static constexpr int TWA_F4 = (TW::RA / 2) * TW::MA, TWB_F4 = (TW::RB / 2) * TW::MB;
   static constexpr size_t TILE_BYTES = TW::SMEM_FLOAT2 * sizeof(float2);
-  static constexpr size_t BYTES = TILE_BYTES + ROWS * RS * sizeof(float);
+  static constexpr size_t BYTES = TILE_BYTES + (TWA_F4 + TWB_F4) * sizeof(float4);
 };
+
+// shared-memory pass with twiddles taken from the transposed shared table `tws` ([q/2][j] float4)
+template <class T, int R, int L, bool INV>
+DPX_HD void smem_pass_stw(float2* sm, const float4* tws, int tid, int nthreads) {
+  constexpr int M = L / R;
+  constexpr int NTASK = T::COLS * T::N / R;
+  constexpr bool LIN = T::template linear<M>();
+  for (int task = tid; task < NTASK; task += nthreads) {
+    const int c = task % T::COLS;
+    const int t2 = task / T::COLS;
+    const int j = t2 % M;
+    const int base = (t2 / M) * L + j;
+    const int p0 = T::phys(base, c);
+    float2 a[R], w[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) a[m] = sm[LIN ? p0 + T::template delta<M>(m) * T::COLS : T::phys(base + m * M, c)];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {
+      const float4 v = tws[q * M + j];
+      w[2 * q] = make_float2(v.x, v.y); w[2 * q + 1] = make_float2(v.z, v.w);
+    }
+    if (INV) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = fft::cmulc(a[q], w[q]);
+      fft::Dft<R, true>::run(a);
+    } else {
+      fft::Dft<R, false>::run(a);
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = fft::cmul(a[q], w[q]);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) sm[LIN ? p0 + T::template delta<M>(m) * T::COLS : T::phys(base + m * M, c)] = a[m];
+  }
+}
+
+// prox + dual update of every psi term on one image element x; returns that element of the next rhs t.
+// MODE == ROW_FIRST only forms t = sum_i s_i (v_i - u_i) from the stored state.
+template <int MODE>
+DPX_HD float row_element(const PsiPack& psi, int hqs, int b, int it, size_t e, float x) {
+  float t = 0.f;
+  for (int i = 0; i < psi.n; ++i) {
+    const PsiTerm& tm = psi.t[i];
+    if (MODE == ROW_FIRST) {
+      float d = tm.v[e];
+      if (!hqs) d -= tm.u[e];
+      t += tm.scale * d;
+      continue;
+    }
+    const float off = tm.off ? tm.off[e] : 0.f;
+    float w = tm.scale * x - off;
+    if (!hqs) w += tm.u[e];
+    const float lam = tm.lam[(size_t)b * tm.lam_stride + it];
+    const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
+    const float vn = prox_wrapped(ps, w, lam, off);
+    const float un = w - vn;
+    if (!hqs) tm.u[e] = un;
+    if (MODE == ROW_LAST) tm.v[e] = vn;
+    t += tm.scale * (hqs ? vn : vn - un);
+  }
+  return t;
+}
 
 // ------------------------------------------------------------------------------------------------
 //  Row kernel
 // ------------------------------------------------------------------------------------------------
 template <class TW, int MODE>
-__global__ void __launch_bounds__(kThreads) k_row(RowParams P) {
+__global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 4 : 2) k_row(RowParams P) {
   static_assert(TW::COLS == ROWS / 2, "row tile holds one complex sequence per row pair");
-  constexpr int W = TW::N, NPAIR = TW::COLS, G = W / 2 / CG, RS = RowSmem<TW>::RS;
-  constexpr int RA = TW::RA, MA = TW::MA;
+  constexpr int W = TW::N, NPAIR = TW::COLS, G = W / 2 / CG;
+  constexpr int RA = TW::RA, RB = TW::RB, MA = TW::MA, MB = TW::MB;
   DPX_DYN_SMEM(float2, sm);
-  float* rowbuf = reinterpret_cast<float*>(sm + TW::SMEM_FLOAT2);       // [ROWS][RS] real rows (x, then t)
+  float4* twA_s = reinterpret_cast<float4*>(sm + TW::SMEM_FLOAT2);
+  float4* twB_s = twA_s + RowSmem<TW>::TWA_F4;
   const int tid = threadIdx.x;
   const int p = blockIdx.y;
   const int r0 = blockIdx.x * ROWS;
   const int b = p / P.C;
   const int H = P.H;
-  const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
-  const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
+
+  // ---- 0. twiddle records -> shared memory, transposed to [q/2][j] ---------------------------------------------
+  {
+    const float4* gA = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::A_OFF);   // [j][q/2]
+    for (int t = tid; t < RowSmem<TW>::TWA_F4; t += kThreads) twA_s[(t % (RA / 2)) * MA + t / (RA / 2)] = gA[t];
+    const float4* gB = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::B_OFF);
+    for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[(t % (RB / 2)) * MB + t / (RB / 2)] = gB[t];
+  }
 
   if (MODE != ROW_FIRST) {
     // ---- 1. half spectra of the 4 rows -> Z = Xa + i Xb per pair, scattered to digit-reversed positions ----
@@ -110,89 +195,54 @@ __global__ void __launch_bounds__(kThreads) k_row(RowParams P) {
       sm[TW::phys(TW::pos_of_freq(W / 2), tid)] = make_float2(xa.x - xb.y, xa.y + xb.x);
     }
     __syncthreads();
-    // ---- 2. inverse row FFT; its last pass writes the real rows x straight into the row buffers ---------------
+    // ---- 2. inverse row FFT, passes C and B ------------------------------------------------------------------
     fft::smem_pass<TW, TW::RC, TW::MB, true, false>(sm, nullptr, tid, kThreads);
     __syncthreads();
-    fft::smem_pass<TW, TW::RB, TW::MA, true, true>(sm, twB, tid, kThreads);
-    __syncthreads();
-    for (int t = tid; t < NPAIR * MA; t += kThreads) {
-      const int c = t % NPAIR, j = t / NPAIR;
-      const int p0 = TW::phys(j, c);
-      float2 a[RA], w[RA];
+    smem_pass_stw<TW, RB, MA, true>(sm, twB_s, tid, kThreads);
+  }
+  __syncthreads();
+
+  // ---- 3. fused in registers: last inverse pass -> x;  prox / dual / next rhs on x;  first forward pass ----------
+  for (int t = tid; t < NPAIR * MA; t += kThreads) {
+    const int c = t % NPAIR, j = t / NPAIR;
+    const int p0 = TW::phys(j, c);
+    float2 a[RA];
+    if (MODE != ROW_FIRST) {
 #pragma unroll
       for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NPAIR];
-      fft::load_twiddles<RA>(twA + j * RA, w);
 #pragma unroll
-      for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
-      fft::Dft<RA, true>::run(a);
-#pragma unroll
-      for (int m = 0; m < RA; ++m) {
-        rowbuf[(2 * c) * RS + j + m * MA] = a[m].x;
-        rowbuf[(2 * c + 1) * RS + j + m * MA] = a[m].y;
+      for (int q = 0; q < RA / 2; ++q) {
+        const float4 v = twA_s[q * MA + j];
+        if (q > 0) a[2 * q] = fft::cmulc(a[2 * q], make_float2(v.x, v.y));
+        a[2 * q + 1] = fft::cmulc(a[2 * q + 1], make_float2(v.z, v.w));
       }
+      fft::Dft<RA, true>::run(a);                       // a[m] = (x[row a][j + m MA], x[row b][j + m MA])
     }
-    __syncthreads();
-  }
-
-  // ---- 3. prox / dual / next rhs: 128-bit element-wise pass over the 4 rows -------------------------------------
-  for (int t = tid; t < ROWS * (W / 4); t += kThreads) {
-    const int i4 = (t % (W / 4)) * 4, r = t / (W / 4);
-    const size_t e = ((size_t)p * H + r0 + r) * W + i4;
-    float xv[4] = {0.f, 0.f, 0.f, 0.f}, tv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (MODE != ROW_FIRST) {
-      const float4 x4 = *reinterpret_cast<const float4*>(rowbuf + r * RS + i4);
-      xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
-    }
-    for (int i = 0; i < P.psi.n; ++i) {
-      const PsiTerm& tm = P.psi.t[i];
-      if (MODE == ROW_FIRST) {
-        const float4 v4 = ldg4(tm.v + e);
-        float d[4] = {v4.x, v4.y, v4.z, v4.w};
-        if (!P.hqs) {
-          const float4 u4 = ldg4(tm.u + e);
-          d[0] -= u4.x; d[1] -= u4.y; d[2] -= u4.z; d[3] -= u4.w;
-        }
+    const size_t ea = ((size_t)p * H + r0 + 2 * c) * W + j, eb = ea + W;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tv[k] += tm.scale * d[k];
-        continue;
-      }
-      float off[4] = {0.f, 0.f, 0.f, 0.f}, uo[4] = {0.f, 0.f, 0.f, 0.f}, vn[4], un[4];
-      if (tm.off) { const float4 o4 = ldg4(tm.off + e); off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w; }
-      if (!P.hqs) { const float4 u4 = ldg4(tm.u + e); uo[0] = u4.x; uo[1] = u4.y; uo[2] = u4.z; uo[3] = u4.w; }
-      const float lam = tm.lam[(size_t)b * tm.lam_stride + P.it];
-      const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float w = tm.scale * xv[k] - off[k] + uo[k];
-        vn[k] = prox_wrapped(ps, w, lam, off[k]);
-        un[k] = w - vn[k];
-        tv[k] += tm.scale * (P.hqs ? vn[k] : vn[k] - un[k]);
-      }
-      if (!P.hqs) stg4(tm.u + e, make_float4(un[0], un[1], un[2], un[3]));
-      if (MODE == ROW_LAST) stg4(tm.v + e, make_float4(vn[0], vn[1], vn[2], vn[3]));
+    for (int m = 0; m < RA; ++m) {
+      const float xa = MODE != ROW_FIRST ? a[m].x : 0.f, xb = MODE != ROW_FIRST ? a[m].y : 0.f;
+      const float ta = row_element<MODE>(P.psi, P.hqs, b, P.it, ea + m * MA, xa);
+      const float tb = row_element<MODE>(P.psi, P.hqs, b, P.it, eb + m * MA, xb);
+      if (MODE == ROW_LAST) { P.x[ea + m * MA] = xa; P.x[eb + m * MA] = xb; }
+      a[m] = make_float2(ta, tb);
     }
-    if (MODE == ROW_LAST) stg4(P.x + e, make_float4(xv[0], xv[1], xv[2], xv[3]));
-    else *reinterpret_cast<float4*>(rowbuf + r * RS + i4) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+    if (MODE == ROW_LAST) continue;
+    fft::Dft<RA, false>::run(a);
+#pragma unroll
+    for (int q = 0; q < RA / 2; ++q) {                  // twiddles re-read from shared memory: cheaper than 32 live registers
+      const float4 v = twA_s[q * MA + j];
+      if (q > 0) a[2 * q] = fft::cmul(a[2 * q], make_float2(v.x, v.y));
+      a[2 * q + 1] = fft::cmul(a[2 * q + 1], make_float2(v.z, v.w));
+    }
+#pragma unroll
+    for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NPAIR] = a[m];
   }
   if (MODE == ROW_LAST) return;
   __syncthreads();
 
-  // ---- 4. forward row FFT of t; its first pass reads the row buffers ------------------------------------------------
-  for (int t = tid; t < NPAIR * MA; t += kThreads) {
-    const int c = t % NPAIR, j = t / NPAIR;
-    const int p0 = TW::phys(j, c);
-    float2 a[RA], w[RA];
-#pragma unroll
-    for (int m = 0; m < RA; ++m) a[m] = make_float2(rowbuf[(2 * c) * RS + j + m * MA], rowbuf[(2 * c + 1) * RS + j + m * MA]);
-    fft::Dft<RA, false>::run(a);
-    fft::load_twiddles<RA>(twA + j * RA, w);
-#pragma unroll
-    for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
-#pragma unroll
-    for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NPAIR] = a[m];
-  }
-  __syncthreads();
-  fft::smem_pass<TW, TW::RB, TW::MA, false, true>(sm, twB, tid, kThreads);
+  // ---- 4. forward row FFT, passes B and C ---------------------------------------------------------------------
+  smem_pass_stw<TW, RB, MA, false>(sm, twB_s, tid, kThreads);
   __syncthreads();
   fft::smem_pass<TW, TW::RC, TW::MB, false, false>(sm, nullptr, tid, kThreads);
   __syncthreads();
@@ -245,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     const int p0 = TH::phys(j, c);
     float2 a[RA], w[RA];
 #pragma unroll
-    for (int m = 0; m < RA; ++m) a[m] = tile[(size_t)(j + m * MA) * CG + c];
+    for (int m = 0; m < RA; ++m) a[m] = ld_stream2(tile + (size_t)(j + m * MA) * CG + c);
     fft::Dft<RA, false>::run(a);
     fft::load_twiddles<RA>(twA + j * RA, w);
 #pragma unroll
@@ -276,12 +326,12 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     float d[RC];
 #pragma unroll
     for (int m = 0; m < RC / 2; ++m) {
-      const float4 v = fb4[m];
+      const float4 v = ld_stream4(fb4 + m);
       f[2 * m] = make_float2(v.x, v.y); f[2 * m + 1] = make_float2(v.z, v.w);
     }
 #pragma unroll
     for (int m = 0; m < RC / 4; ++m) {
-      const float4 v = dq4[m];
+      const float4 v = ld_stream4(dq4 + m);
       d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
     }
 #pragma unroll
