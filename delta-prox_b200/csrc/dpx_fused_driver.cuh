@@ -104,13 +104,18 @@ struct Driver {
         cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
         const dim3 rgrid(H / ROWS, P), cgrid(G + 1, P);
         const size_t rsm = RowSmem<TW>::BYTES, csm = TH::SMEM_FLOAT2 * sizeof(float2);
-        be.template row<TW, ROW_FIRST>(rgrid, rsm, rp);
+        auto row = [&](auto mode) {
+          constexpr int MODE = decltype(mode)::value;
+          if (psi.n == 1) be.template row<TW, MODE, true>(rgrid, rsm, rp);
+          else be.template row<TW, MODE, false>(rgrid, rsm, rp);
+        };
+        row(std::integral_constant<int, ROW_FIRST>{});
         for (int k = 0; k < n_iters; ++k) {
           cp.rho.it = it0 + k;
           be.template col<TH>(cgrid, csm, cp);
           rp.it = it0 + k;
-          if (k + 1 < n_iters) be.template row<TW, ROW_MID>(rgrid, rsm, rp);
-          else be.template row<TW, ROW_LAST>(rgrid, rsm, rp);
+          if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
+          else row(std::integral_constant<int, ROW_LAST>{});
         }
       });
     });

@@ -35,11 +35,11 @@ struct CudaBackend {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess && rc == DPX_OK) { set_error("fused kernel launch failed: %s", cudaGetErrorString(e)); rc = DPX_ERR_CUDA; }
   }
-  template <class TW, int MODE>
+  template <class TW, int MODE, bool SINGLE>
   void row(dim3 grid, size_t smem, const RowParams& p) {
     if (rc) return;
-    prep(k_row<TW, MODE>, smem);
-    k_row<TW, MODE><<<grid, kThreads, smem, s>>>(p);
+    prep(k_row<TW, MODE, SINGLE>, smem);
+    k_row<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
     after();
   }
   template <class TH>

@@ -33,6 +33,8 @@ namespace fused {
 constexpr int CG = 4;            // spectrum columns per column tile
 constexpr int ROWS = 4;          // image rows per row tile (2 pairs)
 constexpr int kThreads = 256;
+constexpr int kPrefetchAhead = 148 * 3;   // ~ number of k_col CTAs resident on the chip
+constexpr int kPrefetchAhead4 = 148 * 4;  // ~ number of k_row CTAs resident on the chip
 
 enum RowMode { ROW_FIRST = 0, ROW_MID = 1, ROW_LAST = 2 };
 
@@ -66,7 +68,10 @@ DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
 #ifdef DPX_EMU
 DPX_HD float2 ld_stream2(const float2* p) { return *p; }
 DPX_HD float4 ld_stream4(const float4* p) { return *p; }
+DPX_HD void prefetch_l2(const void*) {}
 #else
+// pull one 128-byte line into L2 ahead of the CTA that will stream it (software pipelining across CTAs)
+DPX_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 DPX_HD float2 ld_stream2(const float2* p) {
   float2 r;
   asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
@@ -122,38 +127,52 @@ DPX_HD void smem_pass_stw(float2* sm, const float4* tws, int tid, int nthreads) 
   }
 }
 
-// prox + dual update of every psi term on one image element x; returns that element of the next rhs t.
-// MODE == ROW_FIRST only forms t = sum_i s_i (v_i - u_i) from the stored state.
-template <int MODE>
-DPX_HD float row_element(const PsiPack& psi, int hqs, int b, int it, size_t e, float x) {
-  float t = 0.f;
-  for (int i = 0; i < psi.n; ++i) {
-    const PsiTerm& tm = psi.t[i];
-    if (MODE == ROW_FIRST) {
-      float d = tm.v[e];
-      if (!hqs) d -= tm.u[e];
-      t += tm.scale * d;
-      continue;
+// One psi term applied to the 2*RA image elements a thread holds after the last inverse pass
+// (a[m] = (x[row a][n_m], x[row b][n_m]), n_m = j + m*MA): prox + dual update (admm.py:54-57 / hqs.py:13-15) and the
+// term's contribution scale*(v - u) (ADMM) / scale*z (HQS) to the next right-hand side.  Parameters are read once.
+// ACCUM: add the contribution to acc[] (several terms); otherwise overwrite a[] in place (single term).
+// MODE == ROW_FIRST only forms the contribution from the stored state.
+template <int MODE, bool ACCUM, int RA, int MA>
+DPX_HD void row_term(const PsiTerm& tm, int hqs, int b, int it, size_t ea, size_t eb, float2 (&a)[RA], float2 (&acc)[RA]) {
+  const float scale = tm.scale;
+  float* __restrict__ up = tm.u;
+  float* __restrict__ vp = tm.v;
+  const float* __restrict__ op = tm.off;
+  if (MODE == ROW_FIRST) {
+#pragma unroll
+    for (int m = 0; m < RA; ++m) {
+      float da = vp[ea + m * MA], db = vp[eb + m * MA];
+      if (!hqs) { da -= up[ea + m * MA]; db -= up[eb + m * MA]; }
+      if (ACCUM) { acc[m].x += scale * da; acc[m].y += scale * db; }
+      else a[m] = make_float2(scale * da, scale * db);
     }
-    const float off = tm.off ? tm.off[e] : 0.f;
-    float w = tm.scale * x - off;
-    if (!hqs) w += tm.u[e];
-    const float lam = tm.lam[(size_t)b * tm.lam_stride + it];
-    const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
-    const float vn = prox_wrapped(ps, w, lam, off);
-    const float un = w - vn;
-    if (!hqs) tm.u[e] = un;
-    if (MODE == ROW_LAST) tm.v[e] = vn;
-    t += tm.scale * (hqs ? vn : vn - un);
+    return;
   }
-  return t;
+  const float lam = tm.lam[(size_t)b * tm.lam_stride + it];
+  const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
+#pragma unroll
+  for (int m = 0; m < RA; ++m) {
+    const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
+    float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
+    if (!hqs) { wa += up[ea + m * MA]; wb += up[eb + m * MA]; }
+    const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
+    const float ua = wa - va, ub = wb - vb;
+    if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
+    if (MODE == ROW_LAST) { vp[ea + m * MA] = va; vp[eb + m * MA] = vb; }
+    const float ca = scale * (hqs ? va : va - ua), cb = scale * (hqs ? vb : vb - ub);
+    if (ACCUM) { acc[m].x += ca; acc[m].y += cb; }
+    else a[m] = make_float2(ca, cb);
+    // keep at most half of the dual loads in flight per thread: more would spill registers at 3 CTAs/SM
+    if (m == RA / 2 - 1) asm volatile("" ::: "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 //  Row kernel
 // ------------------------------------------------------------------------------------------------
-template <class TW, int MODE>
-__global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 4 : 2) k_row(RowParams P) {
+// SINGLE: exactly one psi term (the common case) — its update runs in place on the thread's registers.
+template <class TW, int MODE, bool SINGLE>
+__global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k_row(RowParams P) {
   static_assert(TW::COLS == ROWS / 2, "row tile holds one complex sequence per row pair");
   constexpr int W = TW::N, NPAIR = TW::COLS, G = W / 2 / CG;
   constexpr int RA = TW::RA, RB = TW::RB, MA = TW::MA, MB = TW::MB;
@@ -172,6 +191,20 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 4 : 2) k_row(RowPara
     for (int t = tid; t < RowSmem<TW>::TWA_F4; t += kThreads) twA_s[(t % (RA / 2)) * MA + t / (RA / 2)] = gA[t];
     const float4* gB = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::B_OFF);
     for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[(t % (RB / 2)) * MB + t / (RB / 2)] = gB[t];
+  }
+
+  {  // L2 prefetch for the CTA `kPrefetchAhead4` blocks later: its S segments and the dual rows it will update
+    const size_t lin = (size_t)p * gridDim.x + blockIdx.x + kPrefetchAhead4;
+    if (lin < (size_t)gridDim.x * gridDim.y) {
+      const int p2 = (int)(lin / gridDim.x), q2 = (int)(lin % gridDim.x) * ROWS;
+      if (MODE != ROW_FIRST)
+        for (int g = tid; g <= G; g += kThreads) prefetch_l2(P.S + s_index(p2, g, q2, 0, H, G));
+      const size_t e2 = ((size_t)p2 * H + q2) * W;
+      for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
+        const float* base = (P.hqs && MODE != ROW_FIRST) ? nullptr : (P.hqs ? P.psi.t[i].v : P.psi.t[i].u);
+        if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) prefetch_l2(base + e2 + o);
+      }
+    }
   }
 
   if (MODE != ROW_FIRST) {
@@ -219,13 +252,19 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 4 : 2) k_row(RowPara
       fft::Dft<RA, true>::run(a);                       // a[m] = (x[row a][j + m MA], x[row b][j + m MA])
     }
     const size_t ea = ((size_t)p * H + r0 + 2 * c) * W + j, eb = ea + W;
+    if (MODE == ROW_LAST) {
 #pragma unroll
-    for (int m = 0; m < RA; ++m) {
-      const float xa = MODE != ROW_FIRST ? a[m].x : 0.f, xb = MODE != ROW_FIRST ? a[m].y : 0.f;
-      const float ta = row_element<MODE>(P.psi, P.hqs, b, P.it, ea + m * MA, xa);
-      const float tb = row_element<MODE>(P.psi, P.hqs, b, P.it, eb + m * MA, xb);
-      if (MODE == ROW_LAST) { P.x[ea + m * MA] = xa; P.x[eb + m * MA] = xb; }
-      a[m] = make_float2(ta, tb);
+      for (int m = 0; m < RA; ++m) { P.x[ea + m * MA] = a[m].x; P.x[eb + m * MA] = a[m].y; }
+    }
+    if (SINGLE) {
+      row_term<MODE, false, RA, MA>(P.psi.t[0], P.hqs, b, P.it, ea, eb, a, a);
+    } else {
+      float2 acc[RA];
+#pragma unroll
+      for (int m = 0; m < RA; ++m) acc[m] = make_float2(0.f, 0.f);
+      for (int i = 0; i < P.psi.n; ++i) row_term<MODE, true, RA, MA>(P.psi.t[i], P.hqs, b, P.it, ea, eb, a, acc);
+#pragma unroll
+      for (int m = 0; m < RA; ++m) a[m] = acc[m];
     }
     if (MODE == ROW_LAST) continue;
     fft::Dft<RA, false>::run(a);
@@ -286,6 +325,14 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   const int G = P.W / 2 / CG;
   const int b = p / P.C;
   float2* tile = P.S + s_index(p, g, 0, 0, H, G);
+  {  // L2 prefetch of the tile + constants that the CTA `kPrefetchAhead` blocks later will stream
+    const size_t lin = (size_t)p * (G + 1) + g + kPrefetchAhead;
+    if (lin < (size_t)gridDim.y * (G + 1)) {
+      const char* nt = reinterpret_cast<const char*>(P.S + lin * H * CG);
+      const char* nf = reinterpret_cast<const char*>(P.fbp + lin * H * CG);
+      for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) { prefetch_l2(nt + o); prefetch_l2(nf + o); }
+    }
+  }
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
 
@@ -295,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     const int p0 = TH::phys(j, c);
     float2 a[RA], w[RA];
 #pragma unroll
-    for (int m = 0; m < RA; ++m) a[m] = ld_stream2(tile + (size_t)(j + m * MA) * CG + c);
+    for (int m = 0; m < RA; ++m) a[m] = tile[(size_t)(j + m * MA) * CG + c];
     fft::Dft<RA, false>::run(a);
     fft::load_twiddles<RA>(twA + j * RA, w);
 #pragma unroll
@@ -318,20 +365,21 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
 #pragma unroll
     for (int m = 0; m < RC; ++m) a[m] = sm[p0 + TH::template delta<1>(m) * CG];
     fft::Dft<RC, false>::run(a);
-    const size_t rec = (((size_t)p * (G + 1) + g) * (H / RC) + blk) * CG + c;
-    const size_t recd = (((size_t)pd * (G + 1) + g) * (H / RC) + blk) * CG + c;
-    const float4* fb4 = reinterpret_cast<const float4*>(P.fbp + rec * RC);
-    const float4* dq4 = reinterpret_cast<const float4*>(P.dqp + recd * RC);
+    // constants of this block: record [m/2][task] (float4 = two spectrum values) / [m/4][task] (four diagonals), so
+    // consecutive threads read consecutive 16-byte words
+    constexpr int NT = CG * (H / RC);
+    const float4* fb4 = reinterpret_cast<const float4*>(P.fbp) + ((size_t)p * (G + 1) + g) * (H * CG / 2) + t;
+    const float4* dq4 = reinterpret_cast<const float4*>(P.dqp) + ((size_t)pd * (G + 1) + g) * (H * CG / 4) + t;
     float2 f[RC];
     float d[RC];
 #pragma unroll
     for (int m = 0; m < RC / 2; ++m) {
-      const float4 v = ld_stream4(fb4 + m);
+      const float4 v = fb4[m * NT];
       f[2 * m] = make_float2(v.x, v.y); f[2 * m + 1] = make_float2(v.z, v.w);
     }
 #pragma unroll
     for (int m = 0; m < RC / 4; ++m) {
-      const float4 v = ld_stream4(dq4 + m);
+      const float4 v = dq4[m * NT];
       d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
     }
 #pragma unroll
@@ -369,15 +417,19 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
 template <class TH, typename V>
 __global__ void k_pack(const V* __restrict__ src, V* __restrict__ dst, int planes, int H, int W, int G, V zero) {
   constexpr int RC = TH::RC;
+  constexpr int GRP = (int)(sizeof(float4) / sizeof(V));       // values per 16-byte word: 2 (float2) or 4 (float)
+  const int NT = CG * (H / RC);
   const size_t total = (size_t)planes * (G + 1) * H * CG;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int m = (int)(i % RC);
-  size_t r = i / RC;
-  const int c = (int)(r % CG); r /= CG;
-  const int blk = (int)(r % (H / RC)); r /= (H / RC);
+  // dst[tile][m / GRP][task][m % GRP],  task = blk * CG + c
+  const int lane = (int)(i % GRP);
+  size_t r = i / GRP;
+  const int task = (int)(r % NT); r /= NT;
+  const int mg = (int)(r % (RC / GRP)); r /= (RC / GRP);
   const int g = (int)(r % (G + 1));
   const int p = (int)(r / (G + 1));
+  const int m = mg * GRP + lane, c = task % CG, blk = task / CG;
   const int h = TH::freq_of_pos(blk * RC + m);
   const int k = g < G ? g * CG + c : (c == 0 ? W / 2 : -1);
   dst[i] = k >= 0 ? src[((size_t)p * H + h) * (W / 2 + 1) + k] : zero;

@@ -11,9 +11,9 @@ using namespace dpx::fused;
 
 namespace {
 struct EmuBackend {
-  template <class TW, int MODE>
+  template <class TW, int MODE, bool SINGLE>
   void row(dim3 grid, size_t smem, RowParams p) {
-    emu::launch(grid, dim3(kThreads), smem, [=]() { k_row<TW, MODE>(p); });
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_row<TW, MODE, SINGLE>(p); });
   }
   template <class TH>
   void col(dim3 grid, size_t smem, ColParams p) {

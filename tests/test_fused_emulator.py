@@ -82,3 +82,20 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
     assert rel(v[0], want[1][0].numpy()) < 5e-5 and rel(v[1], want[1][1].numpy()) < 5e-5
     if method == "admm":
         assert rel(u[0], want[2][0].numpy()) < 5e-5 and rel(u[1], want[2][1].numpy()) < 5e-5
+
+
+@pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs")])
+def test_fused_kernels_single_term_fast_path(emu, H, W, method):
+    """One psi term: the in-place register path of k_row (template SINGLE)."""
+    g = torch.Generator().manual_seed(H * 3 + W)
+    B, Cc, T = 1, 3, 5
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(5, 1.5)
+    b = (orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    f = orc.Term("nonneg")
+    data = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=torch.from_numpy(b))
+    want = orc.Solver([data, f], method).solve(torch.from_numpy(b), rhos=1.0, lams=0.02, max_iter=T, return_full_states=True)
+    x, v, u = run_emu(emu, b, psf, [0], [1.0], [1.0], 1.0, [0.02], T, method == "hqs")
+    assert rel(x, want[0].numpy()) < 5e-6 and rel(v[0], want[1][0].numpy()) < 5e-5
+    if method == "admm":
+        assert rel(u[0], want[2][0].numpy()) < 5e-5
