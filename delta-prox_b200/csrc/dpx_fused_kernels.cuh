@@ -193,20 +193,6 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
     for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[(t % (RB / 2)) * MB + t / (RB / 2)] = gB[t];
   }
 
-  {  // L2 prefetch for the CTA `kPrefetchAhead4` blocks later: its S segments and the dual rows it will update
-    const size_t lin = (size_t)p * gridDim.x + blockIdx.x + kPrefetchAhead4;
-    if (lin < (size_t)gridDim.x * gridDim.y) {
-      const int p2 = (int)(lin / gridDim.x), q2 = (int)(lin % gridDim.x) * ROWS;
-      if (MODE != ROW_FIRST)
-        for (int g = tid; g <= G; g += kThreads) prefetch_l2(P.S + s_index(p2, g, q2, 0, H, G));
-      const size_t e2 = ((size_t)p2 * H + q2) * W;
-      for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
-        const float* base = (P.hqs && MODE != ROW_FIRST) ? nullptr : (P.hqs ? P.psi.t[i].v : P.psi.t[i].u);
-        if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) prefetch_l2(base + e2 + o);
-      }
-    }
-  }
-
   if (MODE != ROW_FIRST) {
     // ---- 1. half spectra of the 4 rows -> Z = Xa + i Xb per pair, scattered to digit-reversed positions ----
     for (int t = tid; t < G * NPAIR; t += kThreads) {
@@ -325,14 +311,6 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   const int G = P.W / 2 / CG;
   const int b = p / P.C;
   float2* tile = P.S + s_index(p, g, 0, 0, H, G);
-  {  // L2 prefetch of the tile + constants that the CTA `kPrefetchAhead` blocks later will stream
-    const size_t lin = (size_t)p * (G + 1) + g + kPrefetchAhead;
-    if (lin < (size_t)gridDim.y * (G + 1)) {
-      const char* nt = reinterpret_cast<const char*>(P.S + lin * H * CG);
-      const char* nf = reinterpret_cast<const char*>(P.fbp + lin * H * CG);
-      for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) { prefetch_l2(nt + o); prefetch_l2(nf + o); }
-    }
-  }
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
 

@@ -86,7 +86,7 @@ def lib():
             f"dprox_b200: native library not found at {LIB_PATH}. Build it with "
             f"`make -C delta-prox_b200/csrc` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
             f"There is no CPU / eager fallback.")
-    handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    handle = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)
         fn.restype, fn.argtypes = res, args

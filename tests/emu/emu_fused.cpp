@@ -27,11 +27,11 @@ struct EmuBackend {
 };
 }  // namespace
 
-extern "C" int emu_fused_supported(int n) { return size_supported(n) ? 1 : 0; }
+extern "C" __attribute__((visibility("default"))) int emu_fused_supported(int n) { return size_supported(n) ? 1 : 0; }
 
 // x, v[i], u[i]: [B,C,H,W] fp32 (updated in place); fb_std: complex64 [B*C,H,W/2+1]; dq_std: [Cd,H,W/2+1], Cd = C or B*C
 // psi_*: per-term arrays; lam: [n_psi][T]; rho: [T]; offsets off[i] may be null
-extern "C" int emu_fused_run(int B, int C, int H, int W, int n_psi, const int* prox, const float* scale, const float* alpha,
+extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C, int H, int W, int n_psi, const int* prox, const float* scale, const float* alpha,
                              const float* beta, float* x, float** v, float** u, const float** off, const float* fb_std,
                              const float* dq_std, int dq_batch, float wid, float eps, const float* rho, const float* lam, int T,
                              int hqs) {

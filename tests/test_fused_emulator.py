@@ -28,7 +28,8 @@ def emu():
     deps = [src, os.path.join(EMU_DIR, "cuda_emu.h")] + [os.path.join(csrc, f) for f in (
         "dpx_fused_kernels.cuh", "dpx_fused_driver.cuh", "dpx_fft_core.cuh", "dpx_types.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-I", csrc, "-I", EMU_DIR, src, "-o", SO])
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-fvisibility=hidden", "-Wl,-Bsymbolic",
+                               "-I", csrc, "-I", EMU_DIR, src, "-o", SO])
     lib = C.CDLL(SO)
     lib.emu_fused_run.restype = C.c_int
     return lib
