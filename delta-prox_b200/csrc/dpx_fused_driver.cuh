@@ -114,7 +114,11 @@ struct Driver {
           cp.rho.it = it0 + k;
           be.template col<TH>(cgrid, csm, cp);
           rp.it = it0 + k;
-          if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
+          if (k + 1 < n_iters) {
+            if (psi.n == 1 && be.persistent_ctas() > 0)
+              be.template row_persist<TW>(dim3(be.persistent_ctas()), RowPersistSmem<TW>::BYTES, rp, (H / ROWS) * P);
+            else row(std::integral_constant<int, ROW_MID>{});
+          }
           else row(std::integral_constant<int, ROW_LAST>{});
         }
       });

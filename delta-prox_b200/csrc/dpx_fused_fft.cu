@@ -4,6 +4,7 @@
 // Generic transforms (constant hoisting, stand-alone spectral filters, algorithms the fused kernels do not
 // cover) are delegated to an embedded cuFFT engine, so this engine is a strict superset of it.
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
@@ -42,6 +43,15 @@ struct CudaBackend {
     k_row<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
     after();
   }
+  int n_persist = 0;                                  // CTAs of the persistent row kernel (2 per SM); 0 disables it
+  int persistent_ctas() const { return n_persist; }
+  template <class TW>
+  void row_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
+    if (rc) return;
+    prep(k_row_mid_persist<TW>, smem);
+    k_row_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
+    after();
+  }
   template <class TH>
   void col(dim3 grid, size_t smem, const ColParams& p) {
     if (rc) return;
@@ -70,6 +80,13 @@ class FusedEngine final : public FftEngine {
     DPX_CUDA(cudaMalloc(&fbp_, ns * sizeof(float2)));
     DPX_CUDA(cudaMemset(fbp_, 0, ns * sizeof(float2)));
     bytes_ = 2 * ns * sizeof(float2);
+    {
+      int dev = 0, sms = 0;
+      DPX_CUDA(cudaGetDevice(&dev));
+      DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const char* env = getenv("DPX_ROW_PERSIST");            // 0 disables the persistent row kernel (for A/B runs)
+      persist_ctas_ = (env && env[0] == '0') ? 0 : 2 * sms;
+    }
     rc = upload_twiddles(g.H, &tw_h_);
     if (!rc) rc = upload_twiddles(g.W, &tw_w_);
     return rc;
@@ -106,6 +123,7 @@ class FusedEngine final : public FftEngine {
                   float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
     if (!dqp_) { set_error("fused engine: constants not packed"); return DPX_ERR_STATE; }
     CudaBackend be{s};
+    be.n_persist = persist_ctas_;
     Driver<CudaBackend> drv(be);
     drv.iterate(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it0, n_iters,
                 tw_h_, tw_w_);
@@ -125,6 +143,7 @@ class FusedEngine final : public FftEngine {
   float* dqp_ = nullptr;
   size_t dqp_cap_ = 0, bytes_ = 0;
   int dq_batch_ = 1;
+  int persist_ctas_ = 0;
 };
 
 }  // namespace

@@ -84,6 +84,20 @@ DPX_HD float4 ld_stream4(const float4* p) {
 }
 #endif
 
+// asynchronous 16-byte global->shared copies (LDGSTS): the next tile streams in while the current one is computed
+#ifdef DPX_EMU
+DPX_HD void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+DPX_HD void cp_async_commit() {}
+DPX_HD void cp_async_wait_all() {}
+#else
+DPX_HD void cp_async16(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+DPX_HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DPX_HD void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 template <class TW>
 struct RowSmem {
   // tile (padded, pairs interleaved) + twiddle records re-laid out for conflict-free 128-bit shared loads:
@@ -193,6 +207,14 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
     for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[(t % (RB / 2)) * MB + t / (RB / 2)] = gB[t];
   }
 
+  {  // pull this CTA's own dual rows into L2 now; they are consumed two FFT passes later (step 3)
+    const size_t e0 = ((size_t)p * H + r0) * W;
+    for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
+      const float* base = P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u;
+      if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) prefetch_l2(base + e0 + o);
+    }
+  }
+
   if (MODE != ROW_FIRST) {
     // ---- 1. half spectra of the 4 rows -> Z = Xa + i Xb per pair, scattered to digit-reversed positions ----
     for (int t = tid; t < G * NPAIR; t += kThreads) {
@@ -299,6 +321,177 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
 }
 
 // ------------------------------------------------------------------------------------------------
+//  Persistent middle row kernel (one psi term): the same arithmetic as k_row<TW, ROW_MID, true>, but every CTA
+//  loops over row tiles and the NEXT tile's inputs (its 257 S segments and its 4 dual rows) are staged into
+//  shared memory with cp.async while the current tile is transformed, so DRAM latency is off the critical path.
+//  2 CTAs/SM:  padded tile 36 KB + S stage 32 KB + u stage 32 KB each; twiddle records come through L1.
+// ------------------------------------------------------------------------------------------------
+template <class TW>
+struct RowPersistSmem {
+  static constexpr int G = TW::N / 2 / CG;
+  static constexpr int SEG_F2 = ROWS * CG;                       // float2 per S segment (4 rows x 4 columns = 128 B)
+  static constexpr int STS_F2 = (G + 1) * SEG_F2;
+  static constexpr int RSU = TW::N + 8;                          // staged dual-row stride (floats)
+  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + ROWS * RSU * sizeof(float);
+};
+
+template <class TW>
+DPX_HD void row_stage_S(const RowParams& P, int tile, float2* stS, int tid) {
+  constexpr int G = TW::N / 2 / CG;
+  const int tiles_per_plane = P.H / ROWS;
+  const int p = tile / tiles_per_plane, r0 = (tile % tiles_per_plane) * ROWS;
+  // segment g = 128 contiguous bytes (rows r0..r0+3 of group g); 8 x 16-byte chunks each
+  for (int t = tid; t < (G + 1) * 8; t += kThreads) {
+    const int g = t >> 3, ch = t & 7;
+    cp_async16(reinterpret_cast<char*>(stS + g * (ROWS * CG)) + ch * 16,
+               reinterpret_cast<const char*>(P.S + s_index(p, g, r0, 0, P.H, G)) + ch * 16);
+  }
+}
+template <class TW>
+DPX_HD void row_stage_u(const RowParams& P, int tile, float* stU, int tid) {
+  constexpr int W = TW::N, RSU = RowPersistSmem<TW>::RSU;
+  const int tiles_per_plane = P.H / ROWS;
+  const int p = tile / tiles_per_plane, r0 = (tile % tiles_per_plane) * ROWS;
+  const float* u = P.psi.t[0].u + ((size_t)p * P.H + r0) * W;
+  for (int t = tid; t < ROWS * (W / 4); t += kThreads) {
+    const int r = t / (W / 4), i4 = (t % (W / 4)) * 4;
+    cp_async16(stU + r * RSU + i4, u + (size_t)r * W + i4);
+  }
+}
+
+template <class TW>
+__global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, int n_tiles) {
+  constexpr int W = TW::N, NPAIR = TW::COLS, G = W / 2 / CG;
+  constexpr int RA = TW::RA, MA = TW::MA, RSU = RowPersistSmem<TW>::RSU, SEG = ROWS * CG;
+  DPX_DYN_SMEM(float2, sm);
+  float2* stS = sm + TW::SMEM_FLOAT2;
+  float* stU = reinterpret_cast<float*>(stS + RowPersistSmem<TW>::STS_F2);
+  const int tid = threadIdx.x;
+  const int H = P.H;
+  const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
+  const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
+  const PsiTerm& tm = P.psi.t[0];
+  const int hqs = P.hqs;
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) {
+    row_stage_S<TW>(P, tile, stS, tid);
+    if (!hqs) row_stage_u<TW>(P, tile, stU, tid);
+  }
+  cp_async_commit();
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int tiles_per_plane = H / ROWS;
+    const int p = tile / tiles_per_plane, r0 = (tile % tiles_per_plane) * ROWS;
+    const int b = p / P.C;
+    const int next = tile + gridDim.x;
+    cp_async_wait_all();
+    __syncthreads();                                   // staged inputs of `tile` are visible; tile buffer is free
+
+    // ---- 1. staged half spectra -> Z = Xa + i Xb per pair, scattered to digit-reversed positions ----------------
+    for (int t = tid; t < G * NPAIR * 2; t += kThreads) {
+      const int half = t & 1, pair = (t >> 1) % NPAIR, g = t / (2 * NPAIR);
+      const float4 av = *reinterpret_cast<const float4*>(stS + g * SEG + (2 * pair) * CG + 2 * half);       // row a, c = 2h, 2h+1
+      const float4 bv = *reinterpret_cast<const float4*>(stS + g * SEG + (2 * pair + 1) * CG + 2 * half);   // row b
+      const float2 xa[2] = {make_float2(av.x, av.y), make_float2(av.z, av.w)};
+      const float2 xb[2] = {make_float2(bv.x, bv.y), make_float2(bv.z, bv.w)};
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int k = g * CG + 2 * half + cc;
+        sm[TW::phys(TW::pos_of_freq(k), pair)] = make_float2(xa[cc].x - xb[cc].y, xa[cc].y + xb[cc].x);
+        if (k > 0) sm[TW::phys(TW::pos_of_freq(W - k), pair)] = make_float2(xa[cc].x + xb[cc].y, xb[cc].x - xa[cc].y);
+      }
+    }
+    if (tid < NPAIR) {                                                          // Nyquist column k = W/2
+      const float2 xa = stS[G * SEG + (2 * tid) * CG], xb = stS[G * SEG + (2 * tid + 1) * CG];
+      sm[TW::phys(TW::pos_of_freq(W / 2), tid)] = make_float2(xa.x - xb.y, xa.y + xb.x);
+    }
+    __syncthreads();                                   // stS consumed
+    if (next < n_tiles) row_stage_S<TW>(P, next, stS, tid);
+    cp_async_commit();
+
+    // ---- 2. inverse row FFT, passes C and B ------------------------------------------------------------------
+    fft::smem_pass<TW, TW::RC, TW::MB, true, false>(sm, nullptr, tid, kThreads);
+    __syncthreads();
+    fft::smem_pass<TW, TW::RB, TW::MA, true, true>(sm, twB, tid, kThreads);
+    __syncthreads();
+
+    // ---- 3. last inverse pass -> x;  prox / dual / next rhs in registers (dual rows from the stage);  first forward pass
+    {
+      const float scale = tm.scale;
+      const float lam = tm.lam[(size_t)b * tm.lam_stride + P.it];
+      const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
+      float* __restrict__ up = tm.u;
+      const float* __restrict__ op = tm.off;
+      for (int t = tid; t < NPAIR * MA; t += kThreads) {
+        const int c = t % NPAIR, j = t / NPAIR;
+        const int p0 = TW::phys(j, c);
+        float2 a[RA], w[RA];
+#pragma unroll
+        for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NPAIR];
+        fft::load_twiddles<RA>(twA + j * RA, w);
+#pragma unroll
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
+        fft::Dft<RA, true>::run(a);
+        const size_t ea = ((size_t)p * H + r0 + 2 * c) * W + j, eb = ea + W;
+        const float* ua_s = stU + (2 * c) * RSU + j;
+        const float* ub_s = ua_s + RSU;
+#pragma unroll
+        for (int m = 0; m < RA; ++m) {
+          const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
+          float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
+          if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
+          const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
+          const float ua = wa - va, ub = wb - vb;
+          if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
+          a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
+        }
+        fft::Dft<RA, false>::run(a);
+#pragma unroll
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
+#pragma unroll
+        for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NPAIR] = a[m];
+      }
+    }
+    __syncthreads();                                   // stU consumed, tile holds pass-A output
+    if (next < n_tiles && !hqs) row_stage_u<TW>(P, next, stU, tid);
+    cp_async_commit();
+
+    // ---- 4. forward row FFT, passes B and C ---------------------------------------------------------------------
+    fft::smem_pass<TW, TW::RB, TW::MA, false, true>(sm, twB, tid, kThreads);
+    __syncthreads();
+    fft::smem_pass<TW, TW::RC, TW::MB, false, false>(sm, nullptr, tid, kThreads);
+    __syncthreads();
+
+    // ---- 5. split the pair spectrum back into the two half spectra and store ---------------------------------------------
+    for (int t = tid; t < G * NPAIR; t += kThreads) {
+      const int pair = t % NPAIR, g = t / NPAIR;
+      float2 xa[4], xb[4];
+#pragma unroll
+      for (int c = 0; c < CG; ++c) {
+        const int k = g * CG + c;
+        const float2 zk = sm[TW::phys(TW::pos_of_freq(k), pair)];
+        const float2 zm = sm[TW::phys(TW::pos_of_freq((W - k) % W), pair)];
+        xa[c] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        xb[c] = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+      }
+      float4* dst = reinterpret_cast<float4*>(P.S + s_index(p, g, r0 + 2 * pair, 0, H, G));
+      dst[0] = make_float4(xa[0].x, xa[0].y, xa[1].x, xa[1].y);
+      dst[1] = make_float4(xa[2].x, xa[2].y, xa[3].x, xa[3].y);
+      dst[2] = make_float4(xb[0].x, xb[0].y, xb[1].x, xb[1].y);
+      dst[3] = make_float4(xb[2].x, xb[2].y, xb[3].x, xb[3].y);
+    }
+    if (tid < NPAIR) {
+      const float2 z = sm[TW::phys(TW::pos_of_freq(W / 2), tid)];
+      const size_t si = s_index(p, G, r0 + 2 * tid, 0, H, G);
+      P.S[si] = make_float2(z.x, 0.f);
+      P.S[si + CG] = make_float2(z.y, 0.f);
+    }
+  }
+  cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
 //  Column kernel
 // ------------------------------------------------------------------------------------------------
 template <class TH>
@@ -313,6 +506,10 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   float2* tile = P.S + s_index(p, g, 0, 0, H, G);
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
+  {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
+    const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * (G + 1) + g) * H * CG);
+    for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) prefetch_l2(nf + o);
+  }
 
   // ---- pass A of the forward FFT, fed straight from global memory ---------------------------------------------
   for (int t = tid; t < CG * MA; t += kThreads) {

@@ -15,6 +15,12 @@ struct EmuBackend {
   void row(dim3 grid, size_t smem, RowParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_row<TW, MODE, SINGLE>(p); });
   }
+  int persist = 5;                                    // emulated persistent grid (forces every CTA to loop)
+  int persistent_ctas() const { return persist; }
+  template <class TW>
+  void row_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_row_mid_persist<TW>(p, n_tiles); });
+  }
   template <class TH>
   void col(dim3 grid, size_t smem, ColParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_col<TH>(p); });
