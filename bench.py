@@ -271,7 +271,9 @@ def run_native(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_iteration")
+            per_elem = json.load(open(prof)).get("dram_bytes_per_element_per_iteration")
+            roof["traffic"] = None if per_elem is None else per_elem * N      # DRAM bytes per iteration of this batch (ncu)
+            roof["traffic_source"] = "profiles/traffic.json (ncu --set full, fused engine)"
         except Exception:
             pass
     cpu = None
