@@ -23,6 +23,7 @@ class FftEngine {
     (void)fb_std; (void)dq_std; (void)dq_batch; (void)s;
     return DPX_OK;
   }
+  virtual void reset_constants() {}
   // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true
   virtual bool fused() const { return false; }
   virtual int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2* fb, const float* dq,

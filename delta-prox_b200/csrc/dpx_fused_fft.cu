@@ -100,6 +100,7 @@ class FusedEngine final : public FftEngine {
     delete this;
   }
   bool fused() const override { return true; }
+  void reset_constants() override { dq_packed_ = false; }
 
   int set_constants(const float2* fb_std, const float* dq_std, int dq_batch, cudaStream_t s) override {
     const int Cd = dq_batch > 1 ? g_.P : g_.C;
@@ -111,7 +112,8 @@ class FusedEngine final : public FftEngine {
       dqp_cap_ = nd;
     }
     dq_batch_ = dq_batch;
-    if (!dq_std) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));
+    if (!dq_std && !dq_packed_) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));   // nullptr = keep what is packed
+    if (dq_std) dq_packed_ = true;
     if (!fb_std) DPX_CUDA(cudaMemsetAsync(fbp_, 0, s_elems(g_.P, g_.H, g_.W) * sizeof(float2), s));
     CudaBackend be{s};
     Driver<CudaBackend> drv(be);
@@ -144,6 +146,7 @@ class FusedEngine final : public FftEngine {
   size_t dqp_cap_ = 0, bytes_ = 0;
   int dq_batch_ = 1;
   int persist_ctas_ = 0;
+  bool dq_packed_ = false;
 };
 
 }  // namespace

@@ -37,6 +37,7 @@ struct dpx_plan {
   float2* fb = nullptr;      // F(sum_q A_q^T b_q)           [P,H,Wc]
   float* dq = nullptr;       // sum_q |OTF_q|^2  /  spatial diag
   int dq_batch = 1;
+  size_t dq_bytes = 0;
   float* dpsi = nullptr;     // non-identity psi diag [C,H,Wc]
   float* ktb_sp = nullptr;   // spatial-diag numerator [P,H,W]
   float* psi_off[DPX_MAX_PSI] = {nullptr};
@@ -199,27 +200,62 @@ int dpx_plan_set_freq_constants(dpx_plan* p, const float* ktb, const float* dq, 
   } else {
     DPX_CUDA(cudaMemsetAsync(p->fb, 0, sizeof(float2) * g.P * g.splane, s));
   }
-  cudaFree(p->dq); p->dq = nullptr;
-  cudaFree(p->dpsi); p->dpsi = nullptr;
+  // (re)allocate only when the size changes: cudaFree synchronises the device, which would serialise callers that
+  // refresh the constants of several plans on different streams
   if (dq) {
     const size_t n = sizeof(float) * (size_t)dq_batch * g.C * g.splane;
-    int rc = dev_alloc(p, (void**)&p->dq, n);
-    if (rc) return rc;
+    if (!p->dq || p->dq_bytes != n) {
+      cudaFree(p->dq); p->dq = nullptr;
+      int rc = dev_alloc(p, (void**)&p->dq, n);
+      if (rc) return rc;
+      p->dq_bytes = n;
+    }
     DPX_CUDA(cudaMemcpyAsync(p->dq, dq, n, cudaMemcpyDeviceToDevice, s));
     p->dq_batch = dq_batch;
+  } else if (p->dq) {
+    cudaFree(p->dq); p->dq = nullptr; p->dq_bytes = 0;
   }
   if (dpsi) {
     const size_t n = sizeof(float) * (size_t)g.C * g.splane;
-    int rc = dev_alloc(p, (void**)&p->dpsi, n);
-    if (rc) return rc;
+    if (!p->dpsi) {
+      int rc = dev_alloc(p, (void**)&p->dpsi, n);
+      if (rc) return rc;
+    }
     DPX_CUDA(cudaMemcpyAsync(p->dpsi, dpsi, n, cudaMemcpyDeviceToDevice, s));
+  } else if (p->dpsi) {
+    cudaFree(p->dpsi); p->dpsi = nullptr;
   }
   {
+    if (!p->dq) p->fft->reset_constants();
     int rc = p->fft->set_constants(p->fb, p->dq, p->dq ? p->dq_batch : 1, s);
     if (rc) return rc;
   }
   p->consts_set = true;
   return DPX_OK;
+}
+
+int dpx_plan_set_rhs(dpx_plan* p, const float* ktb, void* stream) {
+  DPX_REQUIRE(p, "null plan");
+  DPX_REQUIRE(p->consts_set, "constants not set yet (call dpx_plan_set_*_constants first)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Geom& g = p->g;
+  if (p->d.xupdate == DPX_X_SPATIAL_DIAG) {
+    const size_t n = sizeof(float) * g.P * g.plane;
+    if (ktb) {
+      if (!p->ktb_sp) { int rc = dev_alloc(p, (void**)&p->ktb_sp, n); if (rc) return rc; }
+      DPX_CUDA(cudaMemcpyAsync(p->ktb_sp, ktb, n, cudaMemcpyDeviceToDevice, s));
+    } else if (p->ktb_sp) {
+      DPX_CUDA(cudaMemsetAsync(p->ktb_sp, 0, n, s));
+    }
+    return DPX_OK;
+  }
+  if (ktb) {
+    int rc = p->fft->r2c(ktb, p->fb, s);
+    if (rc) return rc;
+  } else {
+    DPX_CUDA(cudaMemsetAsync(p->fb, 0, sizeof(float2) * g.P * g.splane, s));
+  }
+  return p->fft->set_constants(p->fb, nullptr, p->dq_batch, s);      // engines re-pack F(K^T b) only
 }
 
 int dpx_plan_set_spatial_constants(dpx_plan* p, const float* ktb, const float* dq, int dq_batch, void* stream) {

@@ -101,8 +101,12 @@ class Algorithm(nn.Module):
         ckey = _placeholder_versions(list(self.psi_fns) + list(self.omega_fns))
         if self._engine is not None and self._engine.key == key and self._engine.const_key != ckey \
                 and isinstance(self._engine, NativeEngine):
-            # only Placeholder values changed (a new batch of measurements): keep the plan, re-hoist the constants
-            self._engine._set_constants(x0)
+            # only Placeholder values changed: keep the plan.  A new batch of measurements (additive constants) only
+            # moves K^T b; a new operator parameter (PSF / weight) also moves the diagonals.
+            if self._engine.const_key[1] == ckey[1]:
+                self._engine.update_rhs(x0)
+            else:
+                self._engine._set_constants(x0)
             self._engine.const_key = ckey
         if self._engine is None or self._engine.key != key or self._engine.const_key != ckey:
             if not x0.is_cuda:

@@ -144,19 +144,25 @@ def _sched(t: torch.Tensor, B: int, device) -> tuple:
 
 
 def _placeholder_versions(fns):
-    out = []
+    """(constants, parameters): versions of the Placeholders that enter the objective as additive constants / explicit
+    `b` (a change only moves the right-hand side K^T b and psi offsets) and of those that parametrise an operator
+    (`conv_doe` PSF, `mul_elementwise` weight: a change also moves the diagonals)."""
+    consts, params = [], []
     for fn in fns:
         stack = [fn.linop] if fn.linop is not None else []
         while stack:
             n = stack.pop()
             if isinstance(n, Placeholder):
-                out.append((id(n), n.version))
+                consts.append((id(n), n.version))
+            for attr in ("_psf", "_w"):
+                q = getattr(n, attr, None)
+                if isinstance(q, Placeholder):
+                    params.append((id(q), q.version))
             stack += list(n.input_nodes)
-        for attr in ("_b",):
-            b = getattr(fn, attr, None)
-            if isinstance(b, Placeholder):
-                out.append((id(b), b.version))
-    return tuple(out)
+        b = getattr(fn, "_b", None)
+        if isinstance(b, Placeholder):
+            consts.append((id(b), b.version))
+    return tuple(consts), tuple(params)
 
 
 def _quad_rhs(quad: List[TermSpec], like: torch.Tensor) -> Optional[torch.Tensor]:
@@ -281,6 +287,26 @@ class NativeEngine(_EngineBase):
                     off = ops.axpby(-1.0, self._v(c).contiguous())
                     cabi.check(lib.dpx_plan_set_psi_offset(self.plan.handle, i, cabi.ptr(off), s), "dpx_plan_set_psi_offset")
         self._keep = (ktb, dq)
+
+    def update_rhs(self, x0):
+        """A Placeholder-fed measurement changed: re-hoist K^T b (and psi offsets) only; diagonals and plan stay."""
+        spec, dev = self.spec, self.device
+        like = torch.zeros(self.shape, device=dev, dtype=torch.float32)
+        for t in spec.psi + spec.quad:
+            for v in t.fn.linop.variables:
+                if v._value is None or tuple(v._value.shape) != self.shape or v._value.device != dev:
+                    v._value = like
+        ktb = _quad_rhs(spec.quad, like)
+        ktb4 = None if ktb is None else self._v(ktb).contiguous()
+        s, lib = cabi.stream_ptr(dev), cabi.lib()
+        with torch.cuda.device(dev):
+            cabi.check(lib.dpx_plan_set_rhs(self.plan.handle, cabi.ptr(ktb4), s), "dpx_plan_set_rhs")
+            for i, t in enumerate(spec.psi):
+                c = t.low.const_tensor(like)
+                if c is not None:
+                    off = ops.axpby(-1.0, self._v(c).contiguous())
+                    cabi.check(lib.dpx_plan_set_psi_offset(self.plan.handle, i, cabi.ptr(off), s), "dpx_plan_set_psi_offset")
+        self._keep = (ktb, self._keep[1])
 
     # state ---------------------------------------------------------------------------------------
     def initialize(self, x0):

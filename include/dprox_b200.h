@@ -119,6 +119,9 @@ size_t dpx_plan_workspace_bytes(const dpx_plan* plan);
  * The library transforms ktb once (R2C) and keeps F(ktb); the arrays are copied. */
 int dpx_plan_set_freq_constants(dpx_plan* plan, const float* ktb, const float* dq, int dq_batch,
                                 const float* dpsi, void* stream);
+/* Replace only the right-hand side K^T b (a new batch of measurements through the same operators): re-transforms
+ * ktb, keeps the diagonals.  ktb real [B,C,H,W] or NULL (= 0).  Valid for both x-update kinds. */
+int dpx_plan_set_rhs(dpx_plan* plan, const float* ktb, void* stream);
 /* SPATIAL_DIAG. ktb real [B,C,H,W]; dq real [dq_batch,C,H,W] (mask diagonal). */
 int dpx_plan_set_spatial_constants(dpx_plan* plan, const float* ktb, const float* dq, int dq_batch,
                                    void* stream);
