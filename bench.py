@@ -60,6 +60,17 @@ def make_measurements(B, C, H, W, seed, device):
     return img, noise
 
 
+def workload_config(args, world):
+    """Identical for both arms: the reference arm runs a bounded SAMPLE of this workload (see cpu_baseline.sample)."""
+    B, H, W, T = args.batch, args.size, args.size, args.iters
+    N = B * 3 * H * W
+    return {"workload": f"admm deconv+nonneg, {B} problems/GPU [3,{H},{W}] fp32, psf gaussian 15/5, rho=1, lam=0.02, "
+                        f"{T} iterations per step", "batch_per_gpu": B, "iters_per_step": T,
+            "l2_policy": f"state arrays are {N * 4 / 2**20:.0f} MiB each (> 126 MB L2) and every iteration streams all of them",
+            "fft_backend": {0: "auto", 1: "cufft", 2: "fused"}[args.fft_backend],
+            "parallelism": f"dp{world} (problem shards, no collective)"}
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -154,7 +165,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"admm deconv+nonneg [3,{H},{W}], psf gaussian 15/5, rho=1, lam=0.02 (CPU sample)"},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -312,10 +323,7 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"admm deconv+nonneg, {B} problems/GPU [3,{H},{W}] fp32, psf gaussian 15/5, rho=1, lam=0.02, "
-                               f"{T} iterations per step", "batch_per_gpu": B, "iters_per_step": T,
-                   "l2_policy": f"state arrays are {N * 4 / 2**20:.0f} MiB each (> 126 MB L2) and every iteration streams all of them",
-                   "fft_backend": {0: "auto", 1: "cufft", 2: "fused"}[args.fft_backend], "parallelism": f"dp{world} (problem shards, no collective)"},
+        "config": workload_config(args, world),
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4),
                 "steps": e_steps, "pipeline": f"{n_chunks} sub-batches of {Bc} problems on {n_chunks} CUDA streams "
