@@ -171,10 +171,13 @@ def _quad_rhs(quad: List[TermSpec], like: torch.Tensor) -> Optional[torch.Tensor
     acc = None
     for t in quad:
         fn = t.fn
-        b = fn.offset
-        b = torch.as_tensor(b).to(like.device, torch.float32)
-        if b.shape != like.shape:
-            b = torch.broadcast_to(b, like.shape).contiguous()
+        b = torch.as_tensor(fn.offset).to(like.device)
+        if b.is_complex():                                   # complex measurements (k-space) go straight to the plugin's adjoint
+            b = b.to(torch.complex64)
+        else:
+            b = b.to(torch.float32)
+            if b.shape != like.shape:
+                b = torch.broadcast_to(b, like.shape).contiguous()
         grads = {}
         evaluate_adjoint(fn.linop, b, grads)
         g = next(iter(grads.values())) if grads else None

@@ -23,7 +23,11 @@ def _new_like(x):
 
 
 def axpby(a: float, x: torch.Tensor, b: float = 0.0, y: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
-    """out = a*x + b*y  (scale / sum / subtraction glue; linop/scale.py, linop/sum.py)."""
+    """out = a*x + b*y  (scale / sum / subtraction glue; linop/scale.py, linop/sum.py).
+    complex64 operands (k-space data of plugin operators) are processed as interleaved float pairs."""
+    if isinstance(x, torch.Tensor) and x.is_complex():
+        yr = None if y is None else torch.view_as_real(y.to(torch.complex64).expand_as(x).contiguous())
+        return torch.view_as_complex(axpby(a, torch.view_as_real(x.to(torch.complex64).contiguous()), b, yr))
     x = cabi.require_cuda_f32(x, "x")
     if y is not None:
         y = cabi.require_cuda_f32(y, "y")

@@ -384,7 +384,7 @@ class Term:
         """ProxFn.offset = -linop.offset (proxfn/base.py:43-45); sum_squares with an explicit
         `b` returns b instead (sum_square.py:19-23)."""
         if self.kind == "sum_squares" and self.b is not None:
-            return self.b.to(like.dtype)
+            return self.b if self.b.is_complex() else self.b.to(like.dtype)      # complex k-space data stay complex
         return -self.linop_offset(like)
 
     # -- prox with the wrapper chain -------------------------------------------------------

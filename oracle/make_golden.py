@@ -290,6 +290,50 @@ def admm_pcg_mosaic_conv():
 
 
 @case
+def ladmm_tv_3it():
+    """LinearizedADMM with grad psi linops: the reference's self-inconsistent update, 3 iterations."""
+    img, psf, b = _deconv_inputs(1, 3, 32, 48, lo=0.0)
+    x = dp.Variable()
+    f1, f2 = dp.norm1(dp.grad(x, dim=0)), dp.norm1(dp.grad(x, dim=1))
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, "ladmm", b, 3, rhos=2.0, lams=0.01)
+    return dict(psf=psf, b=_np(b), T=3, rho=2.0, lam=0.01, **out)
+
+
+def _csmri_ops(mask):
+    def fwd(x, step=0):
+        return mask * torch.fft.fft2(x, norm="ortho")
+    def adj(y, step=0):
+        return torch.real(torch.fft.ifft2(mask * y, norm="ortho"))
+    return fwd, adj
+
+
+@case
+def admm_csmri_blackbox():
+    """cfg3: subsampled-FFT BlackBox data term (complex k-space) + anisotropic TV, ADMM, (P)CG inner solve."""
+    g = torch.Generator().manual_seed(31)
+    H = W = 32
+    img = torch.zeros(1, 1, H, W)
+    img[..., 8:24, 10:20] = 1.0
+    img[..., 12:18, 4:28] += 0.5
+    mask = (torch.rand(1, 1, H, W, generator=g) < 0.3).float()
+    mask[..., :4, :4] = 1; mask[..., -4:, :4] = 1; mask[..., :4, -4:] = 1; mask[..., -4:, -4:] = 1
+    fwd, adj = _csmri_ops(mask)
+    y0 = fwd(img)
+    x0 = adj(y0)
+    out = {}
+    for solver in ("cg", "pcg"):
+        x = dp.Variable()
+        A = dp.LinOpFactory(fwd, adj)
+        fns = dp.sum_squares(A(x), y0) + dp.norm1(dp.grad(x, dim=0)) + dp.norm1(dp.grad(x, dim=1))
+        cfg = LinearSolveConfig(rtol=1e-6, max_iters=20, solver_type=solver)
+        res = _run(fns, "admm", x0, 5, rhos=1.0, lams=0.05, linear_solve_config=cfg)
+        for k, v in res.items():
+            out[f"{solver}_{k}"] = v
+    return dict(mask=_np(mask), y0_re=_np(y0.real), y0_im=_np(y0.imag), x0=_np(x0), img=_np(img), T=5, rho=1.0, lam=0.05,
+                cg_iters=20, **out)
+
+
+@case
 def linear_solvers():
     """tests/linalg/test_linear_solver.py:57-111 style: SPD systems, fp64, plus a batched conv system."""
     rs = np.random.RandomState(0)

@@ -152,6 +152,32 @@ def test_cg_fallback(case, solver):
     check_state(st, g, 1e-5)
 
 
+def test_ladmm_with_grad_terms_reference_semantics():
+    g = load("ladmm_tv_3it")
+    psi = [orc.Term("norm1", orc.Grad(0, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))]
+    s = orc.Solver(deconv_terms(g, psi), "ladmm")
+    st = s.solve(T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 3e-6)
+
+
+def csmri_ops(mask):
+    fwd = lambda x, step=0: mask * torch.fft.fft2(x, norm="ortho")
+    adj = lambda y, step=0: torch.real(torch.fft.ifft2(mask * y, norm="ortho"))
+    return fwd, adj
+
+
+@pytest.mark.parametrize("solver", ["cg", "pcg"])
+def test_csmri_blackbox_cg(solver):
+    g = load("admm_csmri_blackbox")
+    fwd, adj = csmri_ops(T(g["mask"]))
+    y0 = torch.complex(T(g["y0_re"]), T(g["y0_im"]))
+    data = orc.Term("sum_squares", orc.BlackBox(fwd, adj, orc.Identity()), b=y0)
+    psi = [orc.Term("norm1", orc.Grad(0, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))]
+    s = orc.Solver([data] + psi, "admm", solver_type=solver, rtol=1e-6, max_iters=int(g["cg_iters"]))
+    st = s.solve(T(g["x0"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, {k[len(solver) + 1:]: v for k, v in g.items() if k.startswith(solver + "_s")}, 1e-5)
+
+
 def test_linear_solvers_known_answers():
     g = load("linear_solvers")
     A, b = T(g["A"]), T(g["b"])

@@ -200,6 +200,35 @@ def test_cg_fallback(dp, case, solver):
     check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
 
 
+def test_ladmm_with_grad_terms_generic_engine(dp):
+    """LADMM with grad psi linops keeps the reference's exact (self-inconsistent, App. A-6) update via the generic engine."""
+    g = load("ladmm_tv_3it")
+    x = dp.Variable()
+    b = T(g["b"])
+    fns = dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(dp.grad(x, dim=0)) + dp.norm1(dp.grad(x, dim=1))
+    s, st = run(dp, fns, "ladmm", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert s.spec.tier == "generic" and s.spec.xupdate == "freq"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+
+
+@pytest.mark.parametrize("solver", ["cg", "pcg"])
+def test_csmri_blackbox_generic_engine(dp, solver):
+    """cfg3: user BlackBox (subsampled FFT, complex k-space) + TV, ADMM with the fused-kernel (P)CG inner solve."""
+    g = load("admm_csmri_blackbox")
+    mask = T(g["mask"])
+    fwd = lambda x, step=0: mask * torch.fft.fft2(x, norm="ortho")
+    adj = lambda y, step=0: torch.real(torch.fft.ifft2(mask * y, norm="ortho")).contiguous()
+    y0 = torch.complex(T(g["y0_re"]), T(g["y0_im"]))
+    x = dp.Variable()
+    A = dp.LinOpFactory(fwd, adj)
+    fns = dp.sum_squares(A(x), y0) + dp.norm1(dp.grad(x, dim=0)) + dp.norm1(dp.grad(x, dim=1))
+    cfg = dp.LinearSolveConfig(rtol=1e-6, max_iters=int(g["cg_iters"]), solver_type=solver)
+    s, st = run(dp, fns, "admm", T(g["x0"]), int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]), linear_solve_config=cfg)
+    assert s.spec.tier == "generic" and s.spec.xupdate == "cg"
+    check_state(st, {k[len(solver) + 1:]: v for k, v in g.items() if k.startswith(solver + "_s")}, tol_x=3e-5, tol_aux=2e-4)
+    assert rel(st[0], g["img"]) < 0.2        # it actually reconstructs the phantom
+
+
 def test_linear_solvers_known_answers(dp):
     g = load("linear_solvers")
     x = dp.Variable()
