@@ -108,6 +108,29 @@ __global__ void __launch_bounds__(kThreads) k_rhs(Geom g, PsiPack psi, bool hqs,
   for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
   for (int i = 0; i < psi.n; ++i) {
     const PsiTerm& tm = psi.t[i];
+    if (tm.linop == DPX_LINOP_GRAD_HW) {            // stacked [grad_H; grad_W] term: state is [B,2C,H,W]
+      const int b = p / g.C, c = p - b * g.C;
+#pragma unroll
+      for (int comp = 0; comp < 2; ++comp) {
+        const size_t cb = ((size_t)b * 2 * g.C + (size_t)comp * g.C + c) * g.plane;
+        const float* vp2 = tm.v + cb;
+        const float* up2 = hqs ? nullptr : tm.u + cb;
+        auto loadd2 = [&](int hh, int ww, float(&d)[VEC]) {
+          loadv<VEC>(d, vp2 + (size_t)hh * g.W + ww);
+          if (up2) {
+            float uu[VEC];
+            loadv<VEC>(uu, up2 + (size_t)hh * g.W + ww);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) d[k] -= uu[k];
+          }
+        };
+        float o[VEC];
+        apply_adjoint<VEC>(comp == 0 ? DPX_LINOP_GRAD_H : DPX_LINOP_GRAD_W, tm.scale, loadd2, h, w0, g.H, g.W, o);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += o[k];
+      }
+      continue;
+    }
     const float* vp = tm.v + base;
     const float* up = hqs ? nullptr : tm.u + base;
     auto loadd = [&](int hh, int ww, float(&d)[VEC]) {
@@ -229,6 +252,57 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = 0; i < psi.n; ++i) {
       const PsiTerm& tm = psi.t[i];
       float kx[VEC], w[VEC], offv[VEC], vn[VEC], un[VEC];
+      if (tm.linop == DPX_LINOP_GRAD_HW) {
+        // K x = [grad_H x ; grad_W x] stacked on the channel axis; DPX_PROX_ISO_TV couples the two components
+        // (group soft-threshold, v = max(1 - lam/|w|_2, 0) w), any other native prox acts element-wise on both.
+        const int c = p - b * g.C;
+        const size_t cb0 = ((size_t)b * 2 * g.C + c) * g.plane + e, cb1 = cb0 + (size_t)g.C * g.plane;
+        float kh[VEC], kw[VEC], wh[VEC], ww[VEC], vh[VEC], vw[VEC];
+        apply_linop<VEC>(DPX_LINOP_GRAD_H, tm.scale, xp, xv, h, w0, g.H, g.W, kh);
+        apply_linop<VEC>(DPX_LINOP_GRAD_W, tm.scale, xp, xv, h, w0, g.H, g.W, kw);
+        if (!hqs) {
+          float u0[VEC], u1[VEC];
+          loadv<VEC>(u0, tm.u + cb0); loadv<VEC>(u1, tm.u + cb1);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { wh[k] = kh[k] + u0[k]; ww[k] = kw[k] + u1[k]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { wh[k] = kh[k]; ww[k] = kw[k]; }
+        }
+        const float lam = tm.lam[(size_t)b * tm.lam_stride + it];
+        const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
+        float v0o[VEC], v1o[VEC];
+        if (RESID) { loadv<VEC>(v0o, tm.v + cb0); loadv<VEC>(v1o, tm.v + cb1); }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          if (tm.prox == DPX_PROX_ISO_TV) {
+            const float lam_eff = tm.beta * tm.beta * lam * tm.alpha;
+            const float a0 = tm.beta * wh[k], a1 = tm.beta * ww[k];
+            const float nrm = sqrtf(a0 * a0 + a1 * a1);
+            const float f = nrm > lam_eff ? (1.f - lam_eff / nrm) * tm.inv_beta : 0.f;
+            vh[k] = f * a0; vw[k] = f * a1;
+          } else {
+            vh[k] = prox_wrapped(ps, wh[k], lam, 0.f); vw[k] = prox_wrapped(ps, ww[k], lam, 0.f);
+          }
+        }
+        storev<VEC>(tm.v + cb0, vh); storev<VEC>(tm.v + cb1, vw);
+        if (!hqs) {
+          float u0[VEC], u1[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { u0[k] = wh[k] - vh[k]; u1[k] = ww[k] - vw[k]; }
+          storev<VEC>(tm.u + cb0, u0); storev<VEC>(tm.u + cb1, u1);
+        }
+        if (RESID) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float r0 = kh[k] - vh[k], r1 = kw[k] - vw[k];
+            const float s0 = r * tm.scale * (vh[k] - v0o[k]), s1 = r * tm.scale * (vw[k] - v1o[k]);
+            racc[0] += r0 * r0 + r1 * r1; racc[1] += s0 * s0 + s1 * s1;
+            racc[2] += kh[k] * kh[k] + kw[k] * kw[k]; racc[3] += vh[k] * vh[k] + vw[k] * vw[k];
+          }
+        }
+        continue;
+      }
       apply_linop<VEC>(tm.linop, tm.scale, xp, xv, h, w0, g.H, g.W, kx);
       if (tm.off) {
         loadv<VEC>(offv, tm.off + base + e);
@@ -413,6 +487,16 @@ __global__ void __launch_bounds__(kThreads) k_init_state(Geom g, PsiPack psi, co
   for (int i = 0; i < psi.n; ++i) {
     const PsiTerm& tm = psi.t[i];
     float kx[VEC];
+    if (tm.linop == DPX_LINOP_GRAD_HW) {
+      const int b = p / g.C, c = p - b * g.C;
+      const size_t cb0 = ((size_t)b * 2 * g.C + c) * g.plane + e, cb1 = cb0 + (size_t)g.C * g.plane;
+      apply_linop<VEC>(DPX_LINOP_GRAD_H, tm.scale, xp, xv, h, w0, g.H, g.W, kx);
+      storev<VEC>(tm.v + cb0, kx);
+      apply_linop<VEC>(DPX_LINOP_GRAD_W, tm.scale, xp, xv, h, w0, g.H, g.W, kx);
+      storev<VEC>(tm.v + cb1, kx);
+      if (with_u) { storev<VEC>(tm.u + cb0, zero); storev<VEC>(tm.u + cb1, zero); }
+      continue;
+    }
     apply_linop<VEC>(tm.linop, tm.scale, xp, xv, h, w0, g.H, g.W, kx);
     if (tm.off) {
       float offv[VEC];
@@ -446,6 +530,30 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int k = 0; k < VEC; ++k) vv[k] = prox_wrapped(ps, vv[k], l, ov[k]);
   storev<VEC>(out + base, vv);
+}
+
+// isotropic (group) shrink of a stacked [B,2C,H,W] tensor: elements e and e + half of a sample form one group
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_prox_iso(ProxSpec ps, const float* __restrict__ v, const float* __restrict__ lam, int lam_stride, int it,
+               float* __restrict__ out, size_t half) {
+  const int b = blockIdx.y;
+  const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (e >= half) return;
+  const size_t base = (size_t)b * 2 * half + e;
+  const float lam_eff = ps.beta * ps.beta * lam[(size_t)b * lam_stride + it] * ps.alpha;
+  float a0[VEC], a1[VEC];
+  loadv<VEC>(a0, v + base);
+  loadv<VEC>(a1, v + base + half);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float x0 = ps.beta * a0[k], x1 = ps.beta * a1[k];
+    const float nrm = sqrtf(x0 * x0 + x1 * x1);
+    const float f = nrm > lam_eff ? (1.f - lam_eff / nrm) * ps.inv_beta : 0.f;
+    a0[k] = f * x0; a1[k] = f * x1;
+  }
+  storev<VEC>(out + base, a0);
+  storev<VEC>(out + base + half, a1);
 }
 
 template <int VEC>
@@ -770,6 +878,14 @@ static inline int flat_vec(size_t per_sample, std::initializer_list<const void*>
 
 int launch_prox_apply(const ProxSpec& ps, const float* v, const float* lam, int lam_stride, int it, const float* off,
                       float* out, int batch, size_t per_sample, cudaStream_t s) {
+  if (ps.kind == DPX_PROX_ISO_TV) {
+    DPX_REQUIRE(per_sample % 2 == 0 && off == nullptr, "iso-TV prox needs a stacked [B,2C,H,W] tensor and no offset");
+    const size_t half = per_sample / 2;
+    const int v2 = flat_vec(half, {v, out});
+    DPX_DISPATCH_VEC(v2, k_prox_iso<VEC><<<plane_grid(half, VEC, batch), kThreads, 0, s>>>(ps, v, lam, lam_stride, it, out, half));
+    DPX_LAUNCH_CHECK();
+    return DPX_OK;
+  }
   const int vec = flat_vec(per_sample, {v, off, out});
   DPX_DISPATCH_VEC(vec, k_prox_apply<VEC><<<plane_grid(per_sample, VEC, batch), kThreads, 0, s>>>(ps, v, lam, lam_stride, it,
                                                                                                  off, out, per_sample));

@@ -143,8 +143,10 @@ int dpx_plan_create(const dpx_problem_desc* d, dpx_plan** out) {
   float wid = 0.f;
   for (int i = 0; i < d->n_psi; ++i) {
     const dpx_psi_desc& s = d->psi[i];
-    DPX_REQUIRE(s.prox >= DPX_PROX_NONNEG && s.prox <= DPX_PROX_EXTERNAL, "psi[%d]: unknown prox %d", i, s.prox);
-    DPX_REQUIRE(s.linop >= DPX_LINOP_IDENTITY && s.linop <= DPX_LINOP_GRAD_W, "psi[%d]: unknown linop %d", i, s.linop);
+    DPX_REQUIRE(s.prox >= DPX_PROX_NONNEG && s.prox <= DPX_PROX_ISO_TV, "psi[%d]: unknown prox %d", i, s.prox);
+    DPX_REQUIRE(s.linop >= DPX_LINOP_IDENTITY && s.linop <= DPX_LINOP_GRAD_HW, "psi[%d]: unknown linop %d", i, s.linop);
+    DPX_REQUIRE(s.prox != DPX_PROX_ISO_TV || s.linop == DPX_LINOP_GRAD_HW, "psi[%d]: iso-TV needs the stacked gradient", i);
+    DPX_REQUIRE(!(s.linop == DPX_LINOP_GRAD_HW && s.prox == DPX_PROX_EXTERNAL), "psi[%d]: external prox on a stacked gradient", i);
     DPX_REQUIRE(s.beta != 0.f, "psi[%d]: beta must be non-zero", i);
     if (s.linop != DPX_LINOP_IDENTITY) all_id = false; else wid += s.scale * s.scale;
     if (s.prox == DPX_PROX_EXTERNAL) has_ext = true;
@@ -287,6 +289,7 @@ int dpx_plan_set_spatial_constants(dpx_plan* p, const float* ktb, const float* d
 int dpx_plan_set_psi_offset(dpx_plan* p, int i, const float* c, void* stream) {
   DPX_REQUIRE(p, "null plan");
   DPX_REQUIRE(i >= 0 && i < p->d.n_psi, "psi index %d out of range", i);
+  DPX_REQUIRE(!c || p->d.psi[i].linop != DPX_LINOP_GRAD_HW, "psi[%d]: offsets are not supported on a stacked gradient", i);
   cudaStream_t s = (cudaStream_t)stream;
   if (!c) { cudaFree(p->psi_off[i]); p->psi_off[i] = nullptr; return DPX_OK; }
   const size_t n = sizeof(float) * p->g.P * p->g.plane;
@@ -490,7 +493,8 @@ int dpx_prox_apply(int prox_kind, const float* v, const float* lam, int lam_per_
                    float box_lo, float box_hi, const float* offset, float* out, int batch, size_t per_sample,
                    void* stream) {
   DPX_REQUIRE(v && lam && out, "null argument");
-  DPX_REQUIRE(prox_kind >= DPX_PROX_NONNEG && prox_kind <= DPX_PROX_BOX, "prox kind %d has no native kernel", prox_kind);
+  DPX_REQUIRE((prox_kind >= DPX_PROX_NONNEG && prox_kind <= DPX_PROX_BOX) || prox_kind == DPX_PROX_ISO_TV,
+              "prox kind %d has no native kernel", prox_kind);
   DPX_REQUIRE(beta != 0.f, "beta must be non-zero");
   const ProxSpec ps{prox_kind, alpha, beta, 1.0f / beta, box_lo, box_hi};
   return launch_prox_apply(ps, v, lam, lam_per_sample ? 1 : 0, 0, offset, out, batch, per_sample, (cudaStream_t)stream);

@@ -8,8 +8,8 @@ from .algo import (ADMM, ADMM_vxu, HQS, Algorithm, LinearizedADMM, Problem, Prox
                    SOLVERS, compile, log_descent, specialize)
 from .linalg import LinearSolveConfig, linear_solve
 from .linop import (BlackBox, CompGraph, Constant, LinOp, LinOpFactory, Placeholder, Variable, adjoint, conv, conv_doe,
-                    copy, eval, grad, gram, mosaic, mul_elementwise, scale, split, sum, validate, vstack)
-from .proxfn import (Denoiser, ProxFn, box, deep_prior, ext_sum_squares, nonneg, norm1, norm2, sum_squares)
+                    copy, eval, grad, grad2d, gram, mosaic, mul_elementwise, scale, split, sum, validate, vstack)
+from .proxfn import (Denoiser, ProxFn, box, deep_prior, ext_sum_squares, iso_tv, nonneg, norm1, norm2, sum_squares)
 from .tensors import array, tensor
 
 __version__ = "0.1.0"
@@ -18,7 +18,7 @@ __all__ = [
     "ADMM", "ADMM_vxu", "HQS", "Algorithm", "LinearizedADMM", "Problem", "ProximalGradientDescent", "ResidualStop",
     "SOLVERS", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg",
     "BlackBox", "CompGraph", "Constant", "LinOp", "LinOpFactory", "Placeholder", "Variable", "adjoint", "conv", "conv_doe",
-    "copy", "eval", "grad", "gram", "mosaic", "mul_elementwise", "scale", "split", "sum", "validate", "vstack",
-    "Denoiser", "ProxFn", "box", "deep_prior", "ext_sum_squares", "nonneg", "norm1", "norm2", "sum_squares",
+    "copy", "eval", "grad", "grad2d", "gram", "mosaic", "mul_elementwise", "scale", "split", "sum", "validate", "vstack",
+    "Denoiser", "ProxFn", "box", "deep_prior", "ext_sum_squares", "iso_tv", "nonneg", "norm1", "norm2", "sum_squares",
     "array", "tensor",
 ]

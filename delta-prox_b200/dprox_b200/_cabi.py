@@ -17,8 +17,8 @@ MAX_PSI = 8
 # enums (keep in sync with include/dprox_b200.h)
 ALGO_ADMM, ALGO_HQS, ALGO_ADMM_VXU, ALGO_PGD, ALGO_LADMM = 0, 1, 2, 3, 4
 X_FREQ_DIAG, X_SPATIAL_DIAG = 0, 1
-PROX_NONNEG, PROX_L1, PROX_L2SQ, PROX_BOX, PROX_EXTERNAL = 0, 1, 2, 3, 4
-LINOP_IDENTITY, LINOP_GRAD_H, LINOP_GRAD_W = 0, 1, 2
+PROX_NONNEG, PROX_L1, PROX_L2SQ, PROX_BOX, PROX_EXTERNAL, PROX_ISO_TV = 0, 1, 2, 3, 4, 5
+LINOP_IDENTITY, LINOP_GRAD_H, LINOP_GRAD_W, LINOP_GRAD_HW = 0, 1, 2, 3
 FFT_AUTO, FFT_CUFFT, FFT_FUSED = 0, 1, 2
 
 

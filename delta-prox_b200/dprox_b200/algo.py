@@ -59,6 +59,16 @@ class ResidualStop:
         return r <= eps_abs + self.reltol * max(kx, v) and s <= eps_abs + self.reltol * v
 
 
+def _flat_tensors(*objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            yield o
+        elif isinstance(o, dict):
+            yield from _flat_tensors(*o.values())
+        elif isinstance(o, (list, tuple)):
+            yield from _flat_tensors(*o)
+
+
 class Algorithm(nn.Module):
     """Base class of the proximal solvers (dprox/algo/base.py:58-275)."""
 
@@ -94,6 +104,18 @@ class Algorithm(nn.Module):
     @property
     def device(self):
         return self._dev_anchor.device
+
+    def _check_no_grad(self, *objs):
+        """Autograd contract: the native loop is forward-only.  Rather than silently returning tensors
+        without a graph, refuse loudly when a gradient could be expected; wrap the call in `torch.no_grad()` for
+        inference, keep the reference path for unrolled training."""
+        if not torch.is_grad_enabled():
+            return
+        needs = [t for t in _flat_tensors(*objs) if t.requires_grad] + [p for p in self.parameters() if p.requires_grad]
+        if needs:
+            raise NotImplementedError(
+                "dprox_b200: the native proximal loop does not propagate gradients yet (inputs/parameters require grad). "
+                "Call it under torch.no_grad() for inference; differentiable unrolling is not part of this backend.")
 
     # -- engine management ---------------------------------------------------------------------------
     def engine(self, x0: torch.Tensor):
@@ -145,6 +167,7 @@ class Algorithm(nn.Module):
         x0 = _to_tensor(x0, batch=True)
         x0, rhos, lams, max_iter = self.defaults(x0, rhos, lams, max_iter)
         x0 = x0.to(self.device, torch.float32)
+        self._check_no_grad(x0, rhos, lams)
         state = self.initialize(x0, **kwargs)
         state = self.iters(state, rhos, lams, max_iter, pbar, callback=callback, stop=stop)
         return state if return_full_states else state[0]
@@ -200,6 +223,7 @@ class Algorithm(nn.Module):
 
     def iter(self, state, rho, lam):
         """One iteration with explicit (rho, lam) values (base.py:174-178); used by unrolled / DEQ callers."""
+        self._check_no_grad(state, rho, lam)
         eng = self.engine(state[0])
         rho = torch.as_tensor(rho, dtype=torch.float32)
         lam = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in lam.items()}

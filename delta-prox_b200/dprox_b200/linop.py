@@ -616,6 +616,40 @@ class grad(conv):
         return conv.lower(self)
 
 
+class grad2d(LinOp):
+    """[grad_H x ; grad_W x] stacked on the channel axis ([B,C,H,W] -> [B,2C,H,W]): the operator of isotropic TV
+    (`iso_tv`).  Not in the reference (which only has per-axis `grad`); named by the north star."""
+
+    def __init__(self, arg):
+        super().__init__([arg])
+        self._gh, self._gw = grad(Variable(), dim=0), grad(Variable(), dim=1)
+
+    def forward(self, input, **kw):
+        return torch.cat([ops.grad(input, 0), ops.grad(input, 1)], dim=1)
+
+    def adjoint(self, input, **kw):
+        C = input.shape[1] // 2
+        a = ops.grad(input[:, :C].contiguous(), 0, adjoint=True)
+        b = ops.grad(input[:, C:].contiguous(), 1, adjoint=True)
+        return ops.axpby(1.0, a, 1.0, b)
+
+    def is_diag(self, freq=False):
+        return freq and self.input_nodes[0].is_diag(freq)
+
+    def _gram_half(self, shape):
+        return self._gh._gram_half(shape) + self._gw._gram_half(shape)
+
+    def get_diag(self, x, freq=False):
+        assert freq
+        return self._gh.get_diag(x, True) + self._gw.get_diag(x, True)
+
+    def lower(self):
+        child = self.input_nodes[0].lower()
+        if child is None or child.const or child.kind != "identity":
+            return None
+        return Lowered("grad2d", child.scale, gram_fn=self._gram_half)
+
+
 class conv_doe(LinOp):
     """Circular convolution with a (learnable / Placeholder-fed) PSF [1,C,h,w]  (linop/conv.py:83-156).
     Only `circular=True` is lowered; gradients w.r.t. the PSF are not propagated by this backend."""

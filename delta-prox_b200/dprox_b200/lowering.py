@@ -78,7 +78,10 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
         raise NotImplementedError("objectives over more than one Variable are not supported "
                                   "(neither are they by the reference's iteration, SURVEY App. A-18)")
     kinds = [t.kind for t in terms]
-    freq_ok = all(k in ("identity", "spectral", "grad") for k in kinds)
+    freq_ok = all(k in ("identity", "spectral", "grad", "grad2d") for k in kinds)
+    for t in psi:
+        if t.prox_kind == cabi.PROX_ISO_TV and t.kind != "grad2d":
+            raise ValueError("iso_tv needs the stacked gradient operator grad2d(x) as its linop")
     spat_ok = all(k in ("identity", "mask") for k in kinds)
     # generic nodes may still be diagonalisable through the plugin protocol (BlackBox with diag=...)
     diagonalizable = (spat_ok or all(t.fn.linop.is_gram_diag(False) for t in terms)) and try_diagonalize
@@ -117,7 +120,8 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
     for t in psi:
         if t.kind == "identity":
             continue
-        if t.kind == "grad" and spec.xupdate == "freq" and method in ("admm", "hqs"):
+        if t.kind in ("grad", "grad2d") and spec.xupdate == "freq" and method in ("admm", "hqs") \
+                and (t.kind == "grad" or t.prox_kind != cabi.PROX_EXTERNAL):
             continue
         spec.reason = f"psi linop of kind {t.kind!r} under {method}: composed node by node"
         return spec
@@ -251,7 +255,7 @@ class NativeEngine(_EngineBase):
         for i, t in enumerate(spec.psi):
             p = d.psi[i]
             p.prox = t.prox_kind
-            p.linop = {"identity": cabi.LINOP_IDENTITY, "grad": cabi.LINOP_GRAD_H}[t.kind]
+            p.linop = {"identity": cabi.LINOP_IDENTITY, "grad": cabi.LINOP_GRAD_H, "grad2d": cabi.LINOP_GRAD_HW}[t.kind]
             if t.kind == "grad":
                 p.linop = cabi.LINOP_GRAD_H if t.low.axis == 0 else cabi.LINOP_GRAD_W
             p.scale, p.alpha, p.beta = float(t.scale), float(t.fn.alpha), float(t.fn.beta)
@@ -317,8 +321,13 @@ class NativeEngine(_EngineBase):
         m, method = len(self.spec.psi), self.spec.method
         if method == "pgd":
             return [x]
-        v = [torch.empty_like(x) for _ in range(m)]
-        u = [torch.empty_like(x) for _ in range(m)] if method != "hqs" else None
+        def term_like(t):                               # a stacked-gradient term carries [B,2C,H,W] state
+            if t.kind != "grad2d":
+                return torch.empty_like(x)
+            B, Cc, H, W = self.shape4
+            return torch.empty(B, 2 * Cc, H, W, device=x.device, dtype=x.dtype)
+        v = [term_like(t) for t in self.spec.psi]
+        u = [term_like(t) for t in self.spec.psi] if method != "hqs" else None
         with torch.cuda.device(self.device):
             cabi.check(cabi.lib().dpx_init_state(self.plan.handle, cabi.ptr(x), cabi.ptr_array(v), cabi.ptr_array(u),
                                                  cabi.stream_ptr(self.device)), "dpx_init_state")

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import _cabi as cabi
 from . import ops
-from .linop import CompGraph, LinOp, Placeholder, Variable, adjoint as linop_adjoint, eval as linop_eval
+from .linop import CompGraph, LinOp, Placeholder, Variable, adjoint as linop_adjoint, eval as linop_eval  # noqa: F401
 from .tensors import to_torch_tensor
 
 
@@ -150,6 +150,16 @@ class box(ProxFn):
     def __init__(self, linop=None, lo=0.0, hi=1.0):
         super().__init__(linop)
         self.box = (float(lo), float(hi))
+
+
+class iso_tv(ProxFn):
+    """Isotropic total variation  sum_pixels |(grad_H x, grad_W x)|_2 ; prox = group soft-threshold of the gradient
+    pair.  New (north star); the reference only offers the anisotropic `norm1(grad(x, dim))` per axis."""
+    native_kind = cabi.PROX_ISO_TV
+
+    def __init__(self, arg):
+        from .linop import grad2d
+        super().__init__(arg if isinstance(arg, grad2d) else grad2d(arg))
 
 
 class sum_squares(ProxFn):

@@ -61,14 +61,17 @@ typedef enum {
   DPX_PROX_L1 = 1,          /* sign(v) max(|v|-lam,0)      proxfn/norm.py:6-19    */
   DPX_PROX_L2SQ = 2,        /* v/(1+2 lam)                 proxfn/norm.py:22-27   */
   DPX_PROX_BOX = 3,         /* clamp(v, lo, hi)            (new; north_star)      */
-  DPX_PROX_EXTERNAL = 4     /* caller evaluates it (deep_prior: proxfn/pnp/prior.py:73-86) */
+  DPX_PROX_EXTERNAL = 4,    /* caller evaluates it (deep_prior: proxfn/pnp/prior.py:73-86) */
+  DPX_PROX_ISO_TV = 5       /* isotropic TV: group shrink max(1 - lam/|w|_2, 0) w over the (grad_H, grad_W) pair;
+                             * only with DPX_LINOP_GRAD_HW (new; north_star — the reference has no isotropic TV)  */
 } dpx_prox_kind;
 
 /* linop of a psi term, applied to the single variable x */
 typedef enum {
   DPX_LINOP_IDENTITY = 0,   /* Variable / scale            linop/variable.py, linop/scale.py */
   DPX_LINOP_GRAD_H = 1,     /* grad(x, dim=0): x[i+1]-x[i] along H, circular  linop/grad.py:8-23 */
-  DPX_LINOP_GRAD_W = 2      /* grad(x, dim=1): along W                                             */
+  DPX_LINOP_GRAD_W = 2,     /* grad(x, dim=1): along W                                             */
+  DPX_LINOP_GRAD_HW = 3     /* [grad_H x ; grad_W x] stacked on the channel axis: state v,u are [B,2C,H,W] */
 } dpx_linop_kind;
 
 typedef struct {

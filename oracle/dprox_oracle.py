@@ -244,6 +244,37 @@ class Grad(Conv):
         self.dim = dim
 
 
+class Grad2D(Op):
+    """[grad_H x ; grad_W x] stacked on the channel axis — NOT in the reference (it has no isotropic TV, SURVEY
+    App. A-12).  Built from the reference's own `grad` so that the only new arithmetic is the group shrink below;
+    parity for this operator/prox pair is therefore *unpinned* (checked against an fp64 run of the same formula)."""
+
+    def __init__(self, inner: Op):
+        self.inner, self.gh, self.gw = inner, Grad(0, Identity()), Grad(1, Identity())
+
+    def _fwd(self, x):
+        return torch.cat([self.gh._fwd(x), self.gw._fwd(x)], dim=1)
+
+    def _adj(self, y):
+        C = y.shape[1] // 2
+        return self.gh._adj(y[:, :C]) + self.gw._adj(y[:, C:])
+
+    def freq_diag_ok(self):
+        return self.inner.freq_diag_ok()
+
+    def diag(self, ref, freq):
+        assert freq
+        return self.gh.diag(ref, True) + self.gw.diag(ref, True)
+
+
+def prox_iso_tv(v, lam):
+    """group soft-threshold over the (grad_H, grad_W) pair of every pixel/channel"""
+    C = v.shape[1] // 2
+    nrm = torch.sqrt(v[:, :C] ** 2 + v[:, C:] ** 2)
+    f = torch.where(nrm > lam, 1 - lam / nrm.clamp_min(1e-30), torch.zeros_like(nrm))
+    return torch.cat([f * v[:, :C], f * v[:, C:]], dim=1)
+
+
 class ConvDOE(Op):
     """conv_doe, circular mode (linop/conv.py:83-156); OTF rebuilt on every call."""
 
@@ -401,6 +432,8 @@ class Term:
                 v = v.clamp(0, 1)
             out = self.denoiser(v, sigma.reshape(-1, 1, 1, 1))
             return out.to(v.dtype).reshape(v.shape)
+        if self.kind == "iso_tv":
+            return prox_iso_tv(v, lam)
         if self.kind == "custom":
             return self.custom_prox(v, lam)
         raise ValueError(self.kind)
@@ -410,7 +443,9 @@ class Term:
         translated(affine(scaled(_prox, alpha), beta), offset)."""
         if lam.ndim == 1:
             lam = lam.view(lam.shape[0], 1, 1, 1)
-        off = self.offset(v)
+        # (the stacked-gradient operator changes the channel count, so its - always zero - offset cannot be
+        #  evaluated on v's shape the way the reference does for shape-preserving linops)
+        off = self.offset(v) if self.kind != "iso_tv" else torch.zeros_like(v)
         w = self.beta * (v - off)
         return 1.0 / self.beta * self._prox(w, self.beta * self.beta * lam * self.alpha) + off
 

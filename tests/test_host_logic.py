@@ -96,6 +96,17 @@ def test_no_cpu_fallback():
         dp.conv(x, np.ones((3, 3, 1), "float32")).forward(torch.rand(1, 3, 8, 8))
 
 
+def test_autograd_contract_fails_loudly():
+    """The native loop is forward-only: inputs that require grad must not be silently detached."""
+    x = dp.Variable()
+    s = dp.compile(objective(x, "conv"), device="cpu")
+    rhos = torch.ones(4, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="gradients"):
+        s.solve(x0=torch.rand(2, 3, 32, 48), rhos=rhos, max_iter=4)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):      # under no_grad it proceeds (and then needs a GPU)
+        s.solve(x0=torch.rand(2, 3, 32, 48), rhos=rhos, max_iter=4)
+
+
 def test_kernel_otf_matches_reference_construction():
     g = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "linops.npz"))
     for name, k in (("conv", g["psf"]), ("conv2", g["k2"])):

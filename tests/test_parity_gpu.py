@@ -412,3 +412,34 @@ def test_fused_engine_headline_size_vs_cufft(dp):
         res[backend] = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=5, return_full_states=True)
     assert rel(res[2][0], res[1][0]) < 5e-6
     assert rel(res[2][1][0], res[1][1][0]) < 5e-5 and rel(res[2][2][0], res[1][2][0]) < 5e-5
+
+
+# ---- isotropic TV (new prox named by the north star; no reference counterpart: oracle restatement + fp64) -----
+
+@pytest.mark.parametrize("method", ["admm", "hqs"])
+def test_iso_tv_group_shrink(dp, method):
+    g = torch.Generator().manual_seed(17)
+    B, Cc, H, W, T_ = 2, 3, 32, 48, 8
+    img = torch.zeros(B, Cc, H, W)
+    img[..., 8:24, 12:36] = 1.0
+    img += 0.05 * torch.randn(B, Cc, H, W, generator=g)
+    psf = orc.point_spread_function(5, 1.5)
+    b = orc.Conv(psf, orc.Identity()).fwd(img)
+    lam = 0.01 + 0.04 * torch.rand(B, T_, generator=g)
+    data = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b)
+    o1, o2 = orc.Term("iso_tv", orc.Grad2D(orc.Identity()), alpha=0.7), orc.Term("nonneg")
+    want = orc.Solver([data, o1, o2], method).solve(b.clone(), rhos=1.5, lams={o1: lam, o2: 0.02}, max_iter=T_,
+                                                    return_full_states=True)
+    want64 = orc.Solver([data, o1, o2], method, dtype=torch.float64).solve(b.double(), rhos=1.5, lams={o1: lam, o2: 0.02},
+                                                                          max_iter=T_)
+    x = dp.Variable()
+    bd = b.cuda()
+    f1, f2 = 0.7 * dp.iso_tv(x), dp.nonneg(x)
+    s, st = run(dp, dp.sum_squares(dp.conv(x, psf) - bd) + f1 + f2, method, bd, T_, rhos=1.5, lams={f1: lam, f2: 0.02})
+    assert s.spec.tier == "native" and st[1][0].shape == (B, 2 * Cc, H, W)
+    assert rel(st[0], want[0]) < TOL_X and rel(st[0], want64) < TOL_X
+    assert rel(st[1][0], want[1][0]) < 1e-4 and rel(st[1][1], want[1][1]) < TOL_AUX
+    # stand-alone prox and operator adjointness
+    v = torch.randn(B, 2 * Cc, H, W, generator=g)
+    assert rel(f1.prox(v.cuda(), torch.tensor(0.3)), orc.prox_iso_tv(v, torch.tensor(0.3 * 0.7))) < 1e-6
+    assert dp.CompGraph(dp.grad2d(x)).sanity_check(shape=(1, 3, 32, 48))
