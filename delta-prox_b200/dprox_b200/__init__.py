@@ -4,7 +4,7 @@
 the reference it deliberately shadows the builtins `sum`, `eval`, `compile` and `copy`.
 """
 from . import linalg  # noqa: F401
-from .algo import (ADMM, ADMM_vxu, HQS, Algorithm, LinearizedADMM, Problem, ProximalGradientDescent, ResidualStop,
+from .algo import (ADMM, ADMM_vxu, HQS, Algorithm, LinearizedADMM, PockChambolle, Problem, ProximalGradientDescent, ResidualStop,
                    SOLVERS, compile, log_descent, specialize)
 from .linalg import LinearSolveConfig, linear_solve
 from .linop import (BlackBox, CompGraph, Constant, LinOp, LinOpFactory, Placeholder, Variable, adjoint, conv, conv_doe,
@@ -15,7 +15,7 @@ from .tensors import array, tensor
 __version__ = "0.1.0"
 
 __all__ = [
-    "ADMM", "ADMM_vxu", "HQS", "Algorithm", "LinearizedADMM", "Problem", "ProximalGradientDescent", "ResidualStop",
+    "ADMM", "ADMM_vxu", "HQS", "Algorithm", "LinearizedADMM", "PockChambolle", "Problem", "ProximalGradientDescent", "ResidualStop",
     "SOLVERS", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg",
     "BlackBox", "CompGraph", "Constant", "LinOp", "LinOpFactory", "Placeholder", "Variable", "adjoint", "conv", "conv_doe",
     "copy", "eval", "grad", "grad2d", "gram", "mosaic", "mul_elementwise", "scale", "split", "sum", "validate", "vstack",

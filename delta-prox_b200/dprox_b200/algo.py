@@ -325,6 +325,15 @@ class HQS(ADMM):
         return [1, [len(self.psi_fns)]]
 
 
+class PockChambolle(ADMM):
+    """algo/pc.py — primal-dual iteration; state (x, [z_i], xbar)."""
+    method = "pc"
+
+    @property
+    def state_split(self):
+        return [1, [len(self.psi_fns)], 1]
+
+
 class ProximalGradientDescent(Algorithm):
     """algo/pgd.py."""
     method = "pgd"
@@ -344,7 +353,8 @@ class ProximalGradientDescent(Algorithm):
         return [1]
 
 
-SOLVERS = {"admm": ADMM, "admm_vxu": ADMM_vxu, "ladmm": LinearizedADMM, "hqs": HQS, "pgd": ProximalGradientDescent}
+SOLVERS = {"admm": ADMM, "admm_vxu": ADMM_vxu, "ladmm": LinearizedADMM, "hqs": HQS, "pc": PockChambolle,
+           "pgd": ProximalGradientDescent}
 
 
 def compile(prox_fns: List[ProxFn], method: str = "admm", device: Union[str, torch.device] = "cuda", **kwargs):  # noqa: A001

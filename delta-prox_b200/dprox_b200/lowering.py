@@ -29,7 +29,7 @@ from .linop import Lowered, Placeholder, Variable, evaluate, evaluate_adjoint
 from .tensors import as_bchw
 
 ALGO_IDS = {"admm": cabi.ALGO_ADMM, "ladmm": cabi.ALGO_LADMM, "admm_vxu": cabi.ALGO_ADMM_VXU, "hqs": cabi.ALGO_HQS,
-            "pgd": cabi.ALGO_PGD}
+            "pgd": cabi.ALGO_PGD, "pc": -1}       # PockChambolle has no fused plan: always composed by the generic engine
 
 
 @dataclass
@@ -116,6 +116,9 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
         spec.xupdate, spec.reason = "cg", "Gram matrix is not diagonal(isable): CG fallback"
         return spec
 
+    if method == "pc":
+        spec.reason = "PockChambolle is composed node by node (closed-form x-update where diagonalisable)"
+        return spec
     # can the psi side be fused?
     for t in psi:
         if t.kind == "identity":
@@ -510,6 +513,8 @@ class GenericEngine(_EngineBase):
         v = [self._K(t.fn, x) for t in self.spec.psi]
         if self.spec.method == "hqs":
             return x, v
+        if self.spec.method == "pc":
+            return x, v, x.clone()
         return x, v, [torch.zeros_like(e) for e in v]
 
     def step(self, state, rho, lam: Dict, it: int):
@@ -547,6 +552,20 @@ class GenericEngine(_EngineBase):
             for i in range(len(spec.psi)):
                 u[i] = ops.lincomb(u[i], None, xs[i], None, z, _const(-1.0, z))
             return z, xs, u
+        if m == "pc":          # PockChambolle._iter (algo/pc.py:13-36)
+            x, z, xbar = state
+            for i, t in enumerate(spec.psi):
+                r = self._rho4(lam[t.fn])
+                zi = ops.lincomb(z[i], None, self._K(t.fn, xbar), r)
+                z[i] = ops.lincomb(zi, None, t.fn.prox(zi, r), -r)
+            xn = [ops.axpby(1.0, x, -1.0, self._Kt(t.fn, z[i])) for i, t in enumerate(spec.psi)]
+            if spec.quad:
+                x_next = self.solve_x(xn, rho, x)
+            else:
+                x_next = xn[0]
+                for e in xn[1:]:
+                    x_next = ops.axpby(1.0, x_next, 1.0, e)
+            return x_next, z, ops.axpby(2.0, x_next, -1.0, x)
         if m == "pgd":
             x = state[0]
             g = spec.quad[0].fn.grad(x)

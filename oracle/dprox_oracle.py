@@ -628,6 +628,8 @@ class Solver:
         v = [t.K(x) for t in self.psi]
         if self.method == "hqs":
             return x, v
+        if self.method == "pc":                          # pc.py:7-11
+            return x, v, x.clone()
         return x, v, [torch.zeros_like(e) for e in v]
 
     # -- one iteration -------------------------------------------------------------------------
@@ -669,6 +671,15 @@ class Solver:
             for i in range(len(self.psi)):
                 u[i] = u[i] + x[i] - z
             return z, x, u
+        if m == "pc":                                    # PockChambolle._iter, pc.py:13-36
+            x, z, xbar = state
+            for i, t in enumerate(self.psi):
+                r = lam[t].view(lam[t].shape[0], 1, 1, 1) if lam[t].ndim == 1 else lam[t]
+                z[i] = z[i] + r * t.K(xbar)
+                z[i] = z[i] - r * t.prox(z[i], r)
+            xn = [x - t.op.adj(z[i]) for i, t in enumerate(self.psi)]
+            x_next = self.ls.solve(xn, rho, x) if self.omega else sum(xn)
+            return x_next, z, x_next + x_next - x
         if m == "pgd":                                   # pgd.py:39-43
             x = state[0]
             r = rho.view(rho.shape[0], 1, 1, 1) if rho.ndim == 1 else rho

@@ -120,6 +120,15 @@ def vxu_conv_nonneg_b1():
 
 
 @case
+def pc_conv_nonneg():
+    """PockChambolle (algo/pc.py:13-36) on the headline objective."""
+    img, psf, b = _deconv_inputs(2, 3, 32, 48)
+    x = dp.Variable()
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x) + dp.norm1(x), "pc", b, 8, rhos=0.7, lams=0.4)
+    return dict(psf=psf, b=_np(b), T=8, rho=0.7, lam=0.4, **out)
+
+
+@case
 def pgd_conv_nonneg():
     img, psf, b = _deconv_inputs(2, 3, 32, 48)
     x = dp.Variable()

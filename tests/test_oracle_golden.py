@@ -51,6 +51,13 @@ def test_headline_objective(case, method):
     check_state(st, g, 2e-6)
 
 
+def test_pock_chambolle():
+    g = load("pc_conv_nonneg")
+    s = orc.Solver(deconv_terms(g, [orc.Term("nonneg"), orc.Term("norm1")]), "pc")
+    st = s.solve(T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 2e-6)
+
+
 def test_admm_50_iterations():
     g = load("admm_conv_nonneg_50it")
     s = orc.Solver(deconv_terms(g, [orc.Term("nonneg")]), "admm")

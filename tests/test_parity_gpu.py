@@ -200,6 +200,16 @@ def test_cg_fallback(dp, case, solver):
     check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
 
 
+def test_pock_chambolle_generic_engine(dp):
+    g = load("pc_conv_nonneg")
+    x = dp.Variable()
+    b = T(g["b"])
+    s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x) + dp.norm1(x), "pc", b, int(g["T"]),
+                rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert s.spec.tier == "generic" and isinstance(s, dp.PockChambolle)
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+
+
 def test_ladmm_with_grad_terms_generic_engine(dp):
     """LADMM with grad psi linops keeps the reference's exact (self-inconsistent, App. A-6) update via the generic engine."""
     g = load("ladmm_tv_3it")
