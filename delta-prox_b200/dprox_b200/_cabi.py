@@ -72,6 +72,11 @@ SIGNATURES = {
     "dpx_cg_update": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _SZ, _VP]),
     "dpx_cg_direction": (_I, [_VP, _VP, _VP, _VP, _I, _SZ, _VP]),
     "dpx_absmax": (_I, [_VP, _VP, _I, _SZ, _VP]),
+    "dpx_ffdnet_available": (_I, []),
+    "dpx_ffdnet_create": (_I, [_I, _I, C.POINTER(_VP)]),
+    "dpx_ffdnet_destroy": (None, [_VP]),
+    "dpx_ffdnet_set_layer": (_I, [_VP, _I, _VP, _VP, _I, _I, _VP]),
+    "dpx_ffdnet_forward": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),
     "dpx_solve_host": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dpx_resid_reduce": (_I, [_VP, _VP, _I, _I, _VP]),
 }

@@ -206,6 +206,19 @@ int dpx_cg_update(float* x, float* r, const float* p, const float* q, const floa
 int dpx_cg_direction(float* p, const float* r, const float* gamma_new, const float* gamma_old, int batch,
                      size_t per_sample, void* stream);
 
+/* ---- native deep-denoiser (FFDNet-color) on tcgen05 tensor cores ---------------------------------------------
+ * deep_prior -> FFDNetColorDenoiser -> FFDNet.forward (proxfn/pnp/prior.py:73-86, denoisers/wrapper.py:38-48,
+ * models/network_ffdnet.py:44-68).  bf16 operands, fp32 accumulation: the opt-in fast denoiser (~1e-2 relative). */
+typedef struct dpx_ffdnet dpx_ffdnet;
+int dpx_ffdnet_available(void);                       /* 0 when built without the CUTLASS header tree */
+int dpx_ffdnet_create(int nb, int nc, dpx_ffdnet** out);          /* nb conv layers, nc = 96 channels */
+void dpx_ffdnet_destroy(dpx_ffdnet* net);
+/* layer 0 = head [nc,13,3,3], 1..nb-2 = body [nc,nc,3,3], nb-1 = tail [12,nc,3,3]; w/bias: device fp32, nn.Conv2d layout */
+int dpx_ffdnet_set_layer(dpx_ffdnet* net, int layer, const float* w, const float* bias, int cout, int cin, void* stream);
+/* y = FFDNet(x, sigma); x, y device fp32 [B,3,H,W]; sigma device [B] (sigma_per_sample=1) or [1] */
+int dpx_ffdnet_forward(dpx_ffdnet* net, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H,
+                       int W, void* stream);
+
 /* ---- end-to-end host-buffer entry point (the e2e leg of bench.py) -------------------------- */
 /* Copies x0 (HOST, pinned or pageable, [B,C,H,W]) to the device, initialises (v = K x0, u = 0),
  * runs n_iters iterations with HOST schedules rho_host [T] / lam_host [n_psi][T] (scalars per

@@ -453,3 +453,28 @@ def test_iso_tv_group_shrink(dp, method):
     v = torch.randn(B, 2 * Cc, H, W, generator=g)
     assert rel(f1.prox(v.cuda(), torch.tensor(0.3)), orc.prox_iso_tv(v, torch.tensor(0.3 * 0.7))) < 1e-6
     assert dp.CompGraph(dp.grad2d(x)).sanity_check(shape=(1, 3, 32, 48))
+
+
+# ---- native FFDNet-color on tcgen05 tensor cores (bf16 fast mode) -----------------------------------------------
+
+def test_native_ffdnet_tcgen05_matches_fp32_network(dp):
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    g = torch.Generator().manual_seed(8)
+    ref = FFDNetColorDenoiser(seed=4).cuda()
+    fast = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
+    for shape in ((2, 3, 64, 96), (1, 3, 45, 70)):                       # even sizes and odd sizes (replicate pad + crop)
+        x = torch.rand(*shape, generator=g).cuda()
+        sig = (0.02 + 0.1 * torch.rand(shape[0], generator=g)).cuda()
+        y_ref = ref.denoise(x, sig)
+        y = fast.denoise(x, sig)
+        assert y.shape == x.shape and torch.isfinite(y).all()
+        r = rel(y, y_ref)
+        assert r < 2e-2, (shape, r)                                      # bf16 operands, fp32 accumulation
+    # inside the ADMM loop as an external prox
+    gold = load("admm_deep_prior_wellcond")
+    xv = dp.Variable()
+    b = T(gold["b"])
+    prior, nn_ = dp.deep_prior(xv, denoiser=fast), dp.nonneg(xv)
+    _, st = run(dp, dp.sum_squares(dp.conv(xv, gold["psf"]) - b) + prior + nn_, "admm", b, int(gold["T"]), rhos=float(gold["rho"]),
+                lams={prior: T(gold["sigmas"], "cpu"), nn_: 0.02})
+    assert rel(st[0], gold["s0"]) < 3e-2
