@@ -26,8 +26,9 @@ namespace conv {
 
 using namespace cute;
 
-// TILE_N = output channels per MMA tile, TILE_K = input channels per k-block, RELU = fuse max(.,0)
-template <int TILE_N, int TILE_K, bool RELU>
+// TILE_N = output channels per MMA tile, TILE_K = input channels per k-block, RELU = fuse max(.,0),
+// TWO_SM = pair two SMs on one 256-row tile (tcgen05 cta_group::2): the filter tile is fetched once per pair
+template <int TILE_N, int TILE_K, bool RELU, bool TWO_SM = false>
 struct Conv3x3 {
   using ElementAct = cutlass::bfloat16_t;
   using ElementFlt = cutlass::bfloat16_t;
@@ -37,10 +38,11 @@ struct Conv3x3 {
   using ElementBias = float;
   static constexpr int Align = 8;                                  // 16-byte TMA alignment of the channel axis
   static constexpr cutlass::conv::Operator ConvOp = cutlass::conv::Operator::kFprop;
-  using MmaTileShape = Shape<_128, Int<TILE_N>, Shape<Int<TILE_K>>>;
-  using ClusterShape = Shape<_1, _1, _1>;
-  using KernelSchedule = cutlass::conv::KernelImplicitTmaWarpSpecialized1SmSm100;
-  using EpilogueSchedule = cutlass::epilogue::TmaWarpSpecialized1Sm;
+  using MmaTileShape = Shape<Int<TWO_SM ? 256 : 128>, Int<TILE_N>, Shape<Int<TILE_K>>>;
+  using ClusterShape = cute::conditional_t<TWO_SM, Shape<_2, _1, _1>, Shape<_1, _1, _1>>;
+  using KernelSchedule = cute::conditional_t<TWO_SM, cutlass::conv::KernelImplicitTmaWarpSpecialized2SmSm100,
+                                             cutlass::conv::KernelImplicitTmaWarpSpecialized1SmSm100>;
+  using EpilogueSchedule = cute::conditional_t<TWO_SM, cutlass::epilogue::TmaWarpSpecialized2Sm, cutlass::epilogue::TmaWarpSpecialized1Sm>;
   template <class T> using Act = cute::conditional_t<RELU, cutlass::epilogue::thread::ReLu<T>, cutlass::epilogue::thread::Identity<T>>;
   using FusionOp = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Act, ElementOut, ElementCompute, ElementBias>;
 
