@@ -478,3 +478,40 @@ def test_native_ffdnet_tcgen05_matches_fp32_network(dp):
     _, st = run(dp, dp.sum_squares(dp.conv(xv, gold["psf"]) - b) + prior + nn_, "admm", b, int(gold["T"]), rhos=float(gold["rho"]),
                 lams={prior: T(gold["sigmas"], "cpu"), nn_: 0.02})
     assert rel(st[0], gold["s0"]) < 3e-2
+
+
+# ---- more fused-engine coverage: single-term fast paths (persistent row kernel), HQS, largest size, per-iteration calls ----
+
+@pytest.mark.parametrize("method,H,W,Cc", [("hqs", 128, 256, 3), ("ladmm", 256, 128, 1), ("admm", 1024, 64, 1)])
+def test_fused_single_term_paths(dp, method, H, W, Cc):
+    g = torch.Generator().manual_seed(H + 3 * W)
+    B, T_ = 3, 7
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(9, 2.5)
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)
+    rhos = 0.6 + torch.rand(B, T_, generator=g)
+    data, o1 = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")
+    want = orc.Solver([data, o1], method).solve(b.clone(), rhos=rhos, lams=0.02, max_iter=T_, return_full_states=True)
+    x = dp.Variable()
+    bd = b.cuda()
+    s, st = run(dp, dp.sum_squares(dp.conv(x, psf) - bd) + dp.nonneg(x), method, bd, T_, rhos=rhos, lams=0.02, fft_backend=2)
+    assert rel(st[0], want[0]) < TOL_X and rel(st[1][0], want[1][0]) < TOL_AUX
+    if method != "hqs":
+        assert rel(st[2][0], want[2][0]) < TOL_AUX
+    # the same solve driven one iteration per call (callback mode: FIRST + col + LAST kernels every iteration)
+    seen = []
+    out = s.solve(x0=bd, rhos=rhos, lams=0.02, max_iter=T_, callback=lambda **kw: seen.append(kw["iter"]))
+    assert seen == list(range(T_)) and rel(out, want[0]) < TOL_X
+
+
+def test_fused_engine_4096(dp):
+    """largest supported side: [1,1,4096,4096] (radix 16x16x16 tiles), fused vs cuFFT engine, 3 iterations."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b = torch.rand(1, 1, 4096, 4096, device="cuda", generator=g)
+    psf = orc.point_spread_function(15, 5)
+    res = {}
+    for backend in (2, 1):
+        x = dp.Variable()
+        s = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), method="admm", device="cuda", fft_backend=backend)
+        res[backend] = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=3)
+    assert rel(res[2], res[1]) < 5e-6
