@@ -247,6 +247,14 @@ def run_native(args):
     # The batch is fed as `n_chunks` sub-batches, each with its own compiled solver (public API) on its own CUDA
     # stream, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the iterations of chunk k.
     del state
+    if args.skip_e2e:                                        # experiment mode only: prints the resident-input line and stops
+        if rank == 0:
+            it_ms = ms_max / (T * args.steps)
+            print(json.dumps({"experiment": True, "value": value, "ms_per_iteration": it_ms, "gpu_launches": int(launches),
+                              "frac": ALG_BYTES_PER_ELEM * N / (it_ms * 1e-3) / 1e9 / load_peaks()[0], "clocks": clk.summary()}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n_chunks = max(1, min(args.e2e_chunks, B))
     while B % n_chunks:
         n_chunks -= 1
@@ -346,6 +354,7 @@ def main():
     ap.add_argument("--fft-backend", type=int, default=0)
     ap.add_argument("--ref-iters", type=int, default=6, help="CPU-arm iterations per sample")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="experiments: resident-input number only (not a bench line)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -102,7 +102,7 @@ struct Driver {
         cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
-        const dim3 rgrid(H / ROWS, P), cgrid(G + 1, P);
+        const dim3 rgrid(H / ROWS, P), cgrid(B, G + 1, C);
         const size_t rsm = RowSmem<TW>::BYTES, csm = TH::SMEM_FLOAT2 * sizeof(float2);
         auto row = [&](auto mode) {
           constexpr int MODE = decltype(mode)::value;

@@ -66,12 +66,14 @@ DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
 // streaming global loads: data touched once per kernel must not evict the twiddle records from the small L1
 // that is left next to ~220 KB of shared memory
 #ifdef DPX_EMU
+DPX_HD float fast_div(float a, float b) { return a / b; }
 DPX_HD float2 ld_stream2(const float2* p) { return *p; }
 DPX_HD float4 ld_stream4(const float4* p) { return *p; }
 DPX_HD void prefetch_l2(const void*) {}
 #else
 // pull one 128-byte line into L2 ahead of the CTA that will stream it (software pipelining across CTAs)
 DPX_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+DPX_HD float fast_div(float a, float b) { return __fdividef(a, b); }
 DPX_HD float2 ld_stream2(const float2* p) {
   float2 r;
   asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
@@ -359,6 +361,21 @@ DPX_HD void row_stage_u(const RowParams& P, int tile, float* stU, int tid) {
   }
 }
 
+// prox + dual + next-rhs for the 2*RA elements a thread holds, bare `_prox` body of kind KIND (see `simple` below)
+template <int KIND, int RA, int MA>
+DPX_HD void mid_simple(float2 (&a)[RA], const float* ua_s, const float* ub_s, float* __restrict__ up, size_t ea, size_t eb,
+                       int hqs, float lam_eff, float lo, float hi) {
+#pragma unroll
+  for (int m = 0; m < RA; ++m) {
+    float wa = a[m].x, wb = a[m].y;
+    if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
+    const float va = prox_body(KIND, wa, lam_eff, lo, hi), vb = prox_body(KIND, wb, lam_eff, lo, hi);
+    const float ua = wa - va, ub = wb - vb;
+    if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
+    a[m] = make_float2(hqs ? va : va - ua, hqs ? vb : vb - ub);
+  }
+}
+
 template <class TW>
 __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, int n_tiles) {
   constexpr int W = TW::N, NPAIR = TW::COLS, G = W / 2 / CG;
@@ -423,6 +440,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
       const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
       float* __restrict__ up = tm.u;
       const float* __restrict__ op = tm.off;
+      const bool simple = scale == 1.f && tm.beta == 1.f && op == nullptr &&
+                          (ps.kind == DPX_PROX_NONNEG || ps.kind == DPX_PROX_L1 || ps.kind == DPX_PROX_L2SQ || ps.kind == DPX_PROX_BOX);
+      const float lam_eff = lam * tm.alpha;            // beta*beta*lam*alpha with beta = 1 (bit-identical: x*1 = x)
       for (int t = tid; t < NPAIR * MA; t += kThreads) {
         const int c = t % NPAIR, j = t / NPAIR;
         const int p0 = TW::phys(j, c);
@@ -436,15 +456,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
         const size_t ea = ((size_t)p * H + r0 + 2 * c) * W + j, eb = ea + W;
         const float* ua_s = stU + (2 * c) * RSU + j;
         const float* ub_s = ua_s + RSU;
+        if (simple) {
+          // common case (scale = beta = 1, no offset): the ProxFn wrapper chain collapses to the bare `_prox` body and the
+          // switch on the prox kind is hoisted out of the element loop (it was 14 % of the kernel's instructions)
+          switch (ps.kind) {
+            case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            case DPX_PROX_L2SQ: mid_simple<DPX_PROX_L2SQ, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            default: mid_simple<DPX_PROX_BOX, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+          }
+        } else {
 #pragma unroll
-        for (int m = 0; m < RA; ++m) {
-          const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
-          float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
-          if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
-          const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
-          const float ua = wa - va, ub = wb - vb;
-          if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
-          a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
+          for (int m = 0; m < RA; ++m) {
+            const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
+            float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
+            if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
+            const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
+            const float ua = wa - va, ub = wb - vb;
+            if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
+            a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
+          }
         }
         fft::Dft<RA, false>::run(a);
 #pragma unroll
@@ -500,9 +531,11 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   constexpr int H = TH::N, RA = TH::RA, RC = TH::RC, MA = TH::MA;
   DPX_DYN_SMEM(float2, sm);
   const int tid = threadIdx.x;
-  const int g = blockIdx.x, p = blockIdx.y;
+  // grid = (B, G+1, C): the problems of the batch are adjacent in launch order, so the sum|OTF|^2 records of
+  // tile (g, channel) -- shared by the batch -- are fetched from DRAM once and hit in L2 for the other problems
+  const int b = blockIdx.x, g = blockIdx.y;
+  const int p = b * P.C + blockIdx.z;
   const int G = P.W / 2 / CG;
-  const int b = p / P.C;
   float2* tile = P.S + s_index(p, g, 0, 0, H, G);
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
@@ -559,8 +592,10 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     }
 #pragma unroll
     for (int m = 0; m < RC; ++m) {
-      const float den = d[m] + den0;
-      a[m] = make_float2((f[m].x + rho * a[m].x + P.eps) / den * P.inv_n, (f[m].y + rho * a[m].y) / den * P.inv_n);
+      // one reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions: the divisions were 19 % of the kernel's
+      // instructions (profiles/README.md, v6); 1/(H W) of the unnormalised inverse transform is folded in
+      const float r = fast_div(P.inv_n, d[m] + den0);
+      a[m] = make_float2((f[m].x + rho * a[m].x + P.eps) * r, (f[m].y + rho * a[m].y) * r);
     }
     fft::Dft<RC, true>::run(a);
 #pragma unroll

@@ -32,9 +32,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
   std::vector<std::thread> th;
   for (unsigned t = 0; t < block.x; ++t) {
     th.emplace_back([&, t]() {
+      for (unsigned bz = 0; bz < grid.z; ++bz)
       for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
-          t_threadIdx = dim3(t); t_blockIdx = dim3(bx, by);
+          t_threadIdx = dim3(t); t_blockIdx = dim3(bx, by, bz);
           kernel();
           g_barrier->arrive_and_wait();      // block boundary: shared memory is reused by the next block
         }
