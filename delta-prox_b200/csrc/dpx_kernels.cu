@@ -686,6 +686,91 @@ __global__ void k_resid_reduce(const float* __restrict__ resid, float* __restric
 }
 
 // ---- CG -------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+//  Backward kernels (autograd contract of Algorithm.iter/solve).  The reference gets these
+//  by plain autograd through solve_direct (sum_square.py:123-156) and the prox bodies; here they are closed forms.
+// ------------------------------------------------------------------------------------------------
+// spec holds W = F(g) (unnormalised R2C of the upstream gradient), qspec holds Q = F(x) of the forward output.
+//   spec    <- W / Dn * inv_n                        (C2R gives dL/d(K^T b);  dL/dt = rho * that)
+//   g_rho_b += sum_k wgt_k Re( conj(W_k) (Q_k (dq_k + eps) - fb_k - eps) ) / (Dn_k * n * rho_b)
+// with Dn = dq + rho (dpsi + wid) + eps and wgt = 2 for the half-spectrum columns that stand for two bins.
+__global__ void __launch_bounds__(kThreads)
+    k_spec_solve_bwd(Geom g, float2* __restrict__ spec, const float2* __restrict__ qspec, const float2* __restrict__ fb,
+                     const float* __restrict__ dq, int dq_batch, const float* __restrict__ dpsi, float wid, float eps,
+                     float inv_n, RhoRef rho, float* __restrict__ g_rho, int g_rho_stride) {
+  __shared__ float red[32];
+  const int p = blockIdx.y;
+  const int b = p / g.C, c = p - b * g.C;
+  const float r = rho_of(rho, b);
+  float acc[1] = {0.f};
+  const size_t ci = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci < g.splane) {
+    const size_t off = (size_t)p * g.splane + ci;
+    const float q = dq ? dq[(size_t)(dq_batch > 1 ? p : c) * g.splane + ci] : 0.f;
+    const float ps = dpsi ? dpsi[(size_t)c * g.splane + ci] : 0.f;
+    const float inv = 1.0f / (q + r * (ps + wid) + eps);
+    const float2 w = spec[off];
+    if (g_rho) {
+      const float2 Q = qspec[off];
+      const float2 f = fb ? fb[off] : make_float2(0.f, 0.f);
+      const int k = (int)(ci % g.Wc);
+      const float wgt = (k == 0 || (g.W % 2 == 0 && k == g.Wc - 1)) ? 1.f : 2.f;
+      const float nr = Q.x * (q + eps) - f.x - eps, ni = Q.y * (q + eps) - f.y;
+      acc[0] = wgt * (w.x * nr + w.y * ni) * inv * inv_n / r;
+    }
+    spec[off] = make_float2(w.x * inv * inv_n, w.y * inv * inv_n);
+  }
+  if (g_rho) {
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(g_rho + (size_t)b * g_rho_stride, acc[0]);
+  }
+}
+
+// backward of ProxFn.prox (wrapper chain of proxfn/base.py:55-64 around the native `_prox` bodies):
+//   out = 1/beta P(beta (v - off), beta^2 alpha lam) + off   =>   g_v = P'_z g,   g_lam = beta alpha sum P'_lam g
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_prox_bwd(ProxSpec ps, const float* __restrict__ v, const float* __restrict__ lam, int lam_stride,
+               const float* __restrict__ off, const float* __restrict__ g, float* __restrict__ gv,
+               float* __restrict__ glam, size_t per_sample) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const float le = ps.beta * ps.beta * lam[(size_t)b * lam_stride] * ps.alpha;
+  float acc[1] = {0.f};
+  const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
+  for (size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; e < per_sample; e += stride) {
+    const size_t base = (size_t)b * per_sample + e;
+    float vv[VEC], ov[VEC], gg[VEC];
+    loadv<VEC>(vv, v + base);
+    loadv<VEC>(gg, g + base);
+    if (off) loadv<VEC>(ov, off + base);
+    else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) ov[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float z = ps.beta * (vv[k] - ov[k]);
+      float dz = 1.f, dl = 0.f;
+      switch (ps.kind) {
+        case DPX_PROX_NONNEG: dz = z > 0.f ? 1.f : 0.f; break;
+        case DPX_PROX_L1: { const float m = fabsf(z) > le ? 1.f : 0.f; dz = m; dl = -copysignf(m, z); break; }
+        case DPX_PROX_L2SQ: { const float d = 1.f / (1.f + 2.f * le); dz = d; dl = -2.f * z * d * d; break; }
+        case DPX_PROX_BOX: dz = (z > ps.lo && z < ps.hi) ? 1.f : 0.f; break;
+        default: break;
+      }
+      acc[0] += dl * gg[k];
+      gg[k] *= dz;
+    }
+    storev<VEC>(gv + base, gg);
+  }
+  if (glam) {
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(glam + (size_t)b * (lam_stride ? 1 : 0), acc[0] * ps.beta * ps.alpha);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     k_cg_dot(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ dots, size_t per_sample) {
@@ -960,6 +1045,26 @@ int launch_cg_dot(const float* x, const float* y, float* dots, int batch, size_t
   DPX_CUDA(cudaMemsetAsync(dots, 0, sizeof(float) * batch, s));
   const int vec = flat_vec(per_sample, {x, y});
   DPX_DISPATCH_VEC(vec, k_cg_dot<VEC><<<reduce_grid(per_sample, VEC, batch), kThreads, 0, s>>>(x, y, dots, per_sample));
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_spec_solve_bwd(const Geom& g, float2* spec, const float2* qspec, const float2* fb, const float* dq, int dq_batch,
+                          const float* dpsi, float wid, float eps, float inv_n, RhoRef rho, float* g_rho, int g_rho_stride,
+                          cudaStream_t s) {
+  if (g_rho) DPX_CUDA(cudaMemsetAsync(g_rho, 0, sizeof(float) * (g_rho_stride ? g.B : 1), s));
+  k_spec_solve_bwd<<<plane_grid(g.splane, 1, g.P), kThreads, 0, s>>>(g, spec, qspec, fb, dq, dq_batch, dpsi, wid, eps, inv_n,
+                                                                      rho, g_rho, g_rho_stride);
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_prox_bwd(const ProxSpec& ps, const float* v, const float* lam, int lam_stride, const float* off, const float* g,
+                    float* gv, float* glam, int batch, size_t per_sample, cudaStream_t s) {
+  if (glam) DPX_CUDA(cudaMemsetAsync(glam, 0, sizeof(float) * (lam_stride ? batch : 1), s));
+  const int vec = flat_vec(per_sample, {v, off, g, gv});
+  DPX_DISPATCH_VEC(vec, k_prox_bwd<VEC><<<reduce_grid(per_sample, VEC, batch), kThreads, 0, s>>>(ps, v, lam, lam_stride, off, g,
+                                                                                                gv, glam, per_sample));
   DPX_LAUNCH_CHECK();
   return DPX_OK;
 }

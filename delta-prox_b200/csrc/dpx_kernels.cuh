@@ -53,6 +53,13 @@ int launch_mul(float* out, const float* x, const float* w, int w_batch, int batc
 int launch_absmax(const float* x, float* out, int batch, size_t per_sample, cudaStream_t s);
 int launch_resid_reduce(const float* resid, float* out, int n, int batch, cudaStream_t s);
 
+// backward of the Fourier-diagonal x-update and of the native prox bodies (autograd contract)
+int launch_spec_solve_bwd(const Geom& g, float2* spec, const float2* qspec, const float2* fb, const float* dq, int dq_batch,
+                          const float* dpsi, float wid, float eps, float inv_n, RhoRef rho, float* g_rho, int g_rho_stride,
+                          cudaStream_t s);
+int launch_prox_bwd(const ProxSpec& ps, const float* v, const float* lam, int lam_stride, const float* off, const float* g,
+                    float* gv, float* glam, int batch, size_t per_sample, cudaStream_t s);
+
 // CG
 int launch_cg_dot(const float* x, const float* y, float* dots, int batch, size_t per_sample, cudaStream_t s);
 int launch_cg_update(float* x, float* r, const float* p, const float* q, const float* gamma, const float* pq,

@@ -48,6 +48,7 @@ struct dpx_plan {
   // scratch
   float2* spec = nullptr;    // [P,H,Wc]
   float* t = nullptr;        // [P,H,W]
+  float2* spec2 = nullptr;   // [P,H,Wc], second spectrum of the backward pass (allocated on first use)
   // host-entry state (dpx_solve_host)
   float* hx = nullptr;
   float* hv[DPX_MAX_PSI] = {nullptr};
@@ -179,7 +180,7 @@ int dpx_plan_create(const dpx_problem_desc* d, dpx_plan** out) {
 void dpx_plan_destroy(dpx_plan* p) {
   if (!p) return;
   if (p->fft) { p->fft->destroy(); }
-  cudaFree(p->fb); cudaFree(p->dq); cudaFree(p->dpsi); cudaFree(p->ktb_sp); cudaFree(p->spec); cudaFree(p->t);
+  cudaFree(p->fb); cudaFree(p->dq); cudaFree(p->dpsi); cudaFree(p->ktb_sp); cudaFree(p->spec); cudaFree(p->spec2); cudaFree(p->t);
   cudaFree(p->hx); cudaFree(p->hsched);
   for (int i = 0; i < DPX_MAX_PSI; ++i) { cudaFree(p->psi_off[i]); cudaFree(p->hv[i]); cudaFree(p->hu[i]); }
   delete p;
@@ -365,6 +366,35 @@ int dpx_xsolve(dpx_plan* p, const float* t, const float* rho, int rho_stride, in
                                   1.0f / (float)((double)g.H * g.W), rr, s);
   if (!rc) rc = p->fft->c2r(p->spec, x, s);
   return rc;
+}
+
+int dpx_xsolve_backward(dpx_plan* p, const float* g, const float* x, const float* rho, int rho_stride, int it, float* g_ktb,
+                        float* g_rho, void* stream) {
+  DPX_REQUIRE(p && g && x && rho && g_ktb, "null argument");
+  DPX_REQUIRE(p->consts_set, "constants not set (dpx_plan_set_*_constants)");
+  DPX_REQUIRE(p->d.xupdate == DPX_X_FREQ_DIAG && p->fft, "dpx_xsolve_backward needs a FREQ_DIAG plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Geom& gm = p->g;
+  if (!p->spec2) {
+    int rc = dev_alloc(p, (void**)&p->spec2, sizeof(float2) * gm.P * gm.splane);
+    if (rc) return rc;
+  }
+  int rc = p->fft->r2c(g, p->spec, s);
+  if (!rc && g_rho) rc = p->fft->r2c(x, p->spec2, s);
+  if (!rc) rc = launch_spec_solve_bwd(gm, p->spec, p->spec2, p->fb, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps,
+                                      1.0f / (float)((double)gm.H * gm.W), RhoRef{rho, rho_stride, it}, g_rho, rho_stride ? 1 : 0, s);
+  if (!rc) rc = p->fft->c2r(p->spec, g_ktb, s);
+  return rc;
+}
+
+int dpx_prox_backward(int prox_kind, const float* v, const float* lam, int lam_per_sample, float alpha, float beta,
+                      float box_lo, float box_hi, const float* offset, const float* g, float* g_v, float* g_lam, int batch,
+                      size_t per_sample, void* stream) {
+  DPX_REQUIRE(v && lam && g && g_v, "null argument");
+  DPX_REQUIRE(prox_kind >= DPX_PROX_NONNEG && prox_kind <= DPX_PROX_BOX, "prox kind %d has no native backward", prox_kind);
+  DPX_REQUIRE(beta != 0.f, "beta must be non-zero");
+  const ProxSpec ps{prox_kind, alpha, beta, 1.0f / beta, box_lo, box_hi};
+  return launch_prox_bwd(ps, v, lam, lam_per_sample ? 1 : 0, offset, g, g_v, g_lam, batch, per_sample, (cudaStream_t)stream);
 }
 
 int dpx_stage_prox(dpx_plan* p, float* x, float* const* v, float* const* u, const float* const* lam,

@@ -61,9 +61,11 @@ SIGNATURES = {
     "dpx_stage_prox": (_I, [_VP, _VP, _PP, _PP, _PP, _IP, _I, _VP]),
     "dpx_stage_dual_external": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "dpx_xsolve": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
+    "dpx_xsolve_backward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
     "dpx_init_state": (_I, [_VP, _VP, _PP, _PP, _VP]),
     "dpx_spectral_filter": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
     "dpx_prox_apply": (_I, [_I, _VP, _VP, _I, _F, _F, _F, _F, _VP, _VP, _I, _SZ, _VP]),
+    "dpx_prox_backward": (_I, [_I, _VP, _VP, _I, _F, _F, _F, _F, _VP, _VP, _VP, _VP, _I, _SZ, _VP]),
     "dpx_lincomb": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _SZ, _VP]),
     "dpx_axpby": (_I, [_VP, _F, _VP, _F, _VP, _SZ, _VP]),
     "dpx_grad_apply": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _F, _VP]),

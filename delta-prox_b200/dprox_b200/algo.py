@@ -105,30 +105,46 @@ class Algorithm(nn.Module):
     def device(self):
         return self._dev_anchor.device
 
-    def _check_no_grad(self, *objs):
-        """Autograd contract: the native loop is forward-only.  Rather than silently returning tensors
-        without a graph, refuse loudly when a gradient could be expected; wrap the call in `torch.no_grad()` for
-        inference, keep the reference path for unrolled training."""
+    def _wants_grad(self, *objs) -> bool:
+        """Autograd contract: `solve/iters/iter` are differentiable w.r.t. the state, the measurements, `rhos`,
+        `lams` and trainable parameters whenever grad mode is on and one of them requires grad (unrolled training,
+        specialization/unroll.py:42-58).  Such calls run on the differentiable engine, whose forward AND backward are
+        native kernels (dprox_b200.autograd); everything else takes the fused forward-only loop."""
         if not torch.is_grad_enabled():
-            return
-        needs = [t for t in _flat_tensors(*objs) if t.requires_grad] + [p for p in self.parameters() if p.requires_grad]
-        if needs:
-            raise NotImplementedError(
-                "dprox_b200: the native proximal loop does not propagate gradients yet (inputs/parameters require grad). "
-                "Call it under torch.no_grad() for inference; differentiable unrolling is not part of this backend.")
+            return False
+        if any(t.requires_grad for t in _flat_tensors(*objs)) or any(p.requires_grad for p in self.parameters()):
+            return True
+        for fn in list(self.psi_fns) + list(self.omega_fns):            # Placeholder-fed measurements carrying a tape
+            stack = [fn.linop] if fn.linop is not None else []
+            while stack:
+                n = stack.pop()
+                val = getattr(n, "_value", None)
+                if isinstance(val, torch.Tensor) and val.requires_grad:
+                    return True
+                stack += list(n.input_nodes)
+            b = getattr(fn, "_b", None)
+            val = getattr(b, "_value", None) if b is not None else None
+            if isinstance(val, torch.Tensor) and val.requires_grad:
+                return True
+        return False
 
     # -- engine management ---------------------------------------------------------------------------
-    def engine(self, x0: torch.Tensor):
+    def engine(self, x0: torch.Tensor, diff: bool = False):
+        if diff:
+            return self._diff_engine(x0)
         key = (tuple(x0.shape), str(x0.device))
         ckey = _placeholder_versions(list(self.psi_fns) + list(self.omega_fns))
-        if self._engine is not None and self._engine.key == key and self._engine.const_key != ckey \
-                and isinstance(self._engine, NativeEngine):
+        if self._engine is not None and self._engine.key == key and self._engine.const_key != ckey:
             # only Placeholder values changed: keep the plan.  A new batch of measurements (additive constants) only
             # moves K^T b; a new operator parameter (PSF / weight) also moves the diagonals.
-            if self._engine.const_key[1] == ckey[1]:
-                self._engine.update_rhs(x0)
+            if isinstance(self._engine, NativeEngine):
+                if self._engine.const_key[1] == ckey[1]:
+                    self._engine.update_rhs(x0)
+                else:
+                    self._engine._set_constants(x0)
             else:
-                self._engine._set_constants(x0)
+                with torch.no_grad():
+                    self._engine.set_constants()
             self._engine.const_key = ckey
         if self._engine is None or self._engine.key != key or self._engine.const_key != ckey:
             if not x0.is_cuda:
@@ -137,10 +153,30 @@ class Algorithm(nn.Module):
             if self.spec.tier == "native":
                 eng = NativeEngine(self.spec, x0, fft_backend=self.fft_backend)
             else:
-                eng = GenericEngine(self.spec, x0, self.linear_solve_config)
+                with torch.no_grad():
+                    eng = GenericEngine(self.spec, x0, self.linear_solve_config)
             eng.key, eng.const_key = key, ckey
             self._engine = eng
         return self._engine
+
+    def _diff_engine(self, x0: torch.Tensor):
+        """The differentiable engine: the algorithm composed kernel by kernel, each with a native backward."""
+        if not x0.is_cuda:
+            raise RuntimeError(f"dprox_b200 computes on CUDA devices only; the solver lives on {x0.device}.")
+        if self.spec.xupdate == "cg":
+            raise NotImplementedError("dprox_b200: gradients through the CG x-update (LinearSolve's implicit differentiation, "
+                                      "linalg/custom.py:48-62) are not part of this backend yet")
+        key = (tuple(x0.shape), str(x0.device))
+        ckey = _placeholder_versions(list(self.psi_fns) + list(self.omega_fns))
+        eng = getattr(self, "_engine_d", None)
+        if eng is None or eng.key != key:
+            eng = GenericEngine(self.spec, x0, self.linear_solve_config)
+            eng.key = key
+            self._engine_d = eng
+        elif eng.const_key != ckey:
+            eng.set_constants()
+        eng.const_key = ckey
+        return eng
 
     # -- argument handling (base.py:20-45, 205-218) ---------------------------------------------------
     def defaults(self, x0=None, rhos=None, lams=None, max_iter=24):
@@ -167,18 +203,22 @@ class Algorithm(nn.Module):
         x0 = _to_tensor(x0, batch=True)
         x0, rhos, lams, max_iter = self.defaults(x0, rhos, lams, max_iter)
         x0 = x0.to(self.device, torch.float32)
-        self._check_no_grad(x0, rhos, lams)
-        state = self.initialize(x0, **kwargs)
-        state = self.iters(state, rhos, lams, max_iter, pbar, callback=callback, stop=stop)
+        diff = self._wants_grad(x0, rhos, lams)
+        if diff:
+            self._diff_engine(x0).set_constants()                    # fresh tape from the measurements to K^T b
+        state = self.initialize(x0, _diff=diff, **kwargs)
+        state = self.iters(state, rhos, lams, max_iter, pbar, callback=callback, stop=stop, _diff=diff)
         return state if return_full_states else state[0]
 
-    def initialize(self, x0, **kwargs):
+    def initialize(self, x0, _diff=None, **kwargs):
         x0 = torch.as_tensor(x0).to(self.device, torch.float32)      # already batched by solve() (base.py:20-33)
-        return self.engine(x0).initialize(x0)
+        diff = self._wants_grad(x0) if _diff is None else _diff
+        return self.engine(x0, diff).initialize(x0)
 
-    def iters(self, state, rhos, lams, max_iter, pbar=False, callback=None, stop: Optional[ResidualStop] = None):
+    def iters(self, state, rhos, lams, max_iter, pbar=False, callback=None, stop: Optional[ResidualStop] = None, _diff=None):
         """Algorithm.iters (base.py:128-156)."""
-        eng = self.engine(state[0])
+        diff = self._wants_grad(state, rhos, lams) if _diff is None else _diff
+        eng = self.engine(state[0], diff)
         if _isscalar(lams) or not isinstance(lams, dict):
             lams = {fn: lams for fn in self.psi_fns}
         dev = state[0].device
@@ -223,8 +263,7 @@ class Algorithm(nn.Module):
 
     def iter(self, state, rho, lam):
         """One iteration with explicit (rho, lam) values (base.py:174-178); used by unrolled / DEQ callers."""
-        self._check_no_grad(state, rho, lam)
-        eng = self.engine(state[0])
+        eng = self.engine(state[0], self._wants_grad(state, rho, lam))
         rho = torch.as_tensor(rho, dtype=torch.float32)
         lam = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in lam.items()}
         if isinstance(eng, NativeEngine):

@@ -111,6 +111,13 @@ class FFDNetColorDenoiser(Denoiser):
         return self
 
     def _denoise(self, x, sigma):
+        wants_grad = torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad
+                                                   or any(p.requires_grad for p in self.model.parameters()))
+        if self.precision == "bf16" and wants_grad:
+            # training (unrolled solver, BASELINE config 5): the tcgen05 forward has no backward yet, so the tape runs
+            # through the framework's convolutions with bf16 operands / fp32 accumulation
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.model(x, sigma).float()
         if self.precision == "bf16":
             if self._native is None or self._native.device != x.device:
                 self._native = NativeFFDNet(self.model, x.device)

@@ -413,41 +413,45 @@ class NativeEngine(_EngineBase):
 # ------------------------------------------------------------------------------------------------
 
 class GenericEngine(_EngineBase):
+    """Also the differentiable engine: every kernel it composes has an autograd Function (`dprox_b200.autograd`), so
+    under grad mode `step()` records a tape whose backward is native as well (SURVEY §8b autograd contract)."""
+
     def __init__(self, spec: PlanSpec, x0: torch.Tensor, linear_solve_config: LinearSolveConfig = LinearSolveConfig(), eps=1e-7):
         super().__init__(spec, x0.shape, x0.device, eps)
         self.cfg = linear_solve_config
         self.plan = None
-        like = torch.zeros(self.shape, device=self.device, dtype=torch.float32)
+        self.ktb = None
+        if spec.xupdate in ("freq", "spatial", "scalar"):
+            B, Cc, H, W = self.shape4
+            if spec.xupdate != "freq":
+                # spatial: dq + rho * dpsi has no slot in the spatial kernel unless dpsi is a constant -> fold as wid
+                raise NotImplementedError("generic engine with a spatial-diagonal closed form")
+            d = cabi.ProblemDesc()
+            d.abi_version = cabi.ABI_VERSION
+            d.batch, d.channels, d.height, d.width = B, Cc, H, W
+            d.algo, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, 0, self.eps, cabi.FFT_CUFFT
+            d.xupdate, d.eps_delta = cabi.X_FREQ_DIAG, 0
+            self.plan = cabi.NativePlan(d, self.device)
+        self.set_constants()
+
+    def set_constants(self):
+        """(Re-)hoist K^T b and the diagonals into the existing plan: called when a Placeholder changed and, under grad
+        mode, before every solve so that `ktb` carries a fresh tape to the measurements."""
+        spec, dev = self.spec, self.device
+        like = torch.zeros(self.shape, device=dev, dtype=torch.float32)
         for t in spec.psi + spec.quad:
             for v in t.fn.linop.variables:
-                if v._value is None or tuple(v._value.shape) != self.shape or v._value.device != self.device:
+                if v._value is None or tuple(v._value.shape) != self.shape or v._value.device != dev:
                     v._value = like
         self.ktb = _quad_rhs(spec.quad, like) if spec.xupdate not in ("ext",) else None
-        if spec.xupdate in ("freq", "spatial", "scalar"):
-            self._build_closed_form(like)
-
-    def _build_closed_form(self, like):
-        spec, dev = self.spec, self.device
-        B, Cc, H, W = self.shape4
-        d = cabi.ProblemDesc()
-        d.abi_version = cabi.ABI_VERSION
-        d.batch, d.channels, d.height, d.width = B, Cc, H, W
-        d.algo, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, 0, self.eps, cabi.FFT_CUFFT
-        freq = spec.xupdate == "freq"
-        d.xupdate = cabi.X_FREQ_DIAG if freq else cabi.X_SPATIAL_DIAG
-        d.eps_delta = 1 if spec.xupdate == "scalar" else 0
-        self.plan = cabi.NativePlan(d, dev)
-        ktb4 = None if self.ktb is None else self._v(self.ktb).contiguous()
-        dq = _gram_diag(spec.quad, self.shape4, dev, freq)
-        dpsi = _gram_diag(spec.psi, self.shape4, dev, freq)        # identity contributions folded in (plan has wid = 0)
-        s = cabi.stream_ptr(dev)
+        if self.plan is None:
+            return
+        ktb4 = None if self.ktb is None else self._v(self.ktb.detach()).contiguous()
+        dq = _gram_diag(spec.quad, self.shape4, dev, True)
+        dpsi = _gram_diag(spec.psi, self.shape4, dev, True)        # identity contributions folded in (plan has wid = 0)
         with torch.cuda.device(dev):
-            if freq:
-                cabi.check(cabi.lib().dpx_plan_set_freq_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0],
-                                                                  cabi.ptr(dpsi), s), "dpx_plan_set_freq_constants")
-            else:
-                # spatial: dq + rho * dpsi has no slot in the spatial kernel unless dpsi is a constant -> fold as wid
-                raise NotImplementedError("generic engine with a spatial-diagonal closed form and non-identity psi linops")
+            cabi.check(cabi.lib().dpx_plan_set_freq_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0],
+                                                              cabi.ptr(dpsi), cabi.stream_ptr(dev)), "dpx_plan_set_freq_constants")
         self._keep = (ktb4, dq, dpsi)
 
     # linop application through the tree -------------------------------------------------------------
@@ -482,11 +486,7 @@ class GenericEngine(_EngineBase):
             if t is None:
                 t = torch.zeros_like(like)
             rt, rs = _sched(rho.reshape(-1, 1) if rho.numel() > 1 else rho.reshape(1), B, self.device)
-            x = torch.empty_like(like)
-            with torch.cuda.device(self.device):
-                cabi.check(cabi.lib().dpx_xsolve(self.plan.handle, cabi.ptr(t.contiguous()), cabi.ptr(rt), rs, 0, cabi.ptr(x),
-                                                 cabi.stream_ptr(self.device)), "dpx_xsolve")
-            return x
+            return ops.xsolve(self.plan, t.contiguous(), rt, rs, self.ktb)
         # CG on the normal equations (solve_cg, sum_square.py:158-197)
         rhs = self.ktb if t is None else (ops.lincomb(t, rho) if self.ktb is None else ops.lincomb(self.ktb, None, t, rho))
 

@@ -9,6 +9,7 @@ from typing import Optional
 import torch
 
 from . import _cabi as cabi
+from . import autograd as ag
 from .tensors import as_bchw
 
 _fft_plans = {}
@@ -28,6 +29,8 @@ def axpby(a: float, x: torch.Tensor, b: float = 0.0, y: Optional[torch.Tensor] =
     if isinstance(x, torch.Tensor) and x.is_complex():
         yr = None if y is None else torch.view_as_real(y.to(torch.complex64).expand_as(x).contiguous())
         return torch.view_as_complex(axpby(a, torch.view_as_real(x.to(torch.complex64).contiguous()), b, yr))
+    if out is None and ag.needs_grad(x, y):
+        return ag.Axpby.apply(x, y, float(a), float(b))
     x = cabi.require_cuda_f32(x, "x")
     if y is not None:
         y = cabi.require_cuda_f32(y, "y")
@@ -42,6 +45,8 @@ def axpby(a: float, x: torch.Tensor, b: float = 0.0, y: Optional[torch.Tensor] =
 
 def lincomb(x, a=None, y=None, b=None, z=None, c=None, out=None) -> torch.Tensor:
     """out = a*x + b*y + c*z with per-sample ([B]) or shared ([1]) DEVICE coefficients (None = 1)."""
+    if out is None and ag.needs_grad(x, a, y, b, z, c):
+        return ag.Lincomb.apply(x, a, y, b, z, c)
     x = cabi.require_cuda_f32(x, "x")
     B = x.shape[0]
     per = x.numel() // B
@@ -60,6 +65,8 @@ def lincomb(x, a=None, y=None, b=None, z=None, c=None, out=None) -> torch.Tensor
 
 def mul(x: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
     """out = w * x with w of batch 1 or B (mosaic / mul_elementwise)."""
+    if out is None and ag.needs_grad(x):
+        return ag.Mul.apply(x, w.detach())
     x = cabi.require_cuda_f32(x, "x")
     w = cabi.require_cuda_f32(w.to(x.device), "w")
     B = x.shape[0]
@@ -79,6 +86,8 @@ def mul(x: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
 
 def grad(x: torch.Tensor, axis: int, adjoint: bool = False, scale: float = 1.0) -> torch.Tensor:
     """Circular forward difference along H (axis=0) or W (axis=1), or its adjoint (linop/grad.py:8-23)."""
+    if ag.needs_grad(x):
+        return ag.Grad.apply(x, int(axis), bool(adjoint), float(scale))
     x = cabi.require_cuda_f32(x, "x")
     x4 = as_bchw(x)
     out = _new_like(x)
@@ -90,6 +99,8 @@ def grad(x: torch.Tensor, axis: int, adjoint: bool = False, scale: float = 1.0) 
 
 def prox(kind: int, v: torch.Tensor, lam: torch.Tensor, alpha=1.0, beta=1.0, lo=0.0, hi=0.0, offset=None, out=None):
     """ProxFn.prox with the wrapper chain for a native `_prox` body (proxfn/base.py:55-64)."""
+    if out is None and ag.needs_grad(v, lam, offset):
+        return ag.Prox.apply(v, lam, offset, int(kind), float(alpha), float(beta), float(lo), float(hi))
     v = cabi.require_cuda_f32(v, "v")
     B = v.shape[0] if v.ndim > 0 else 1
     lam = cabi.require_cuda_f32(lam.to(v.device, torch.float32).reshape(-1), "lam")
@@ -120,6 +131,10 @@ def fft_plan(shape, device) -> cabi.NativePlan:
 def spectral_filter(x: torch.Tensor, otf: torch.Tensor, conj: bool = False, plan: Optional[cabi.NativePlan] = None):
     """y = Re F^-1(otf * F x) (or conj(otf)): conv.forward / conv.adjoint (linop/conv.py:31-41).
     `otf` is a complex64 half spectrum [1|B, C, H, W/2+1]."""
+    if ag.needs_grad(x):
+        x4 = as_bchw(x)
+        plan = plan or fft_plan(tuple(x4.shape), x.device)
+        return ag.SpectralFilter.apply(x, otf.detach(), bool(conj), plan)
     x = cabi.require_cuda_f32(x, "x")
     x4 = as_bchw(x)
     B, Cc, H, W = x4.shape
@@ -135,6 +150,20 @@ def spectral_filter(x: torch.Tensor, otf: torch.Tensor, conj: bool = False, plan
         cabi.check(cabi.lib().dpx_spectral_filter(plan.handle, cabi.ptr(x), C.c_void_p(otf.data_ptr()), ob, int(conj),
                                                   cabi.ptr(out), _s(x)), "dpx_spectral_filter")
     return out
+
+
+def xsolve(plan: cabi.NativePlan, t: torch.Tensor, rho: torch.Tensor, rho_stride: int, ktb: Optional[torch.Tensor] = None):
+    """least_squares.solve closed form through a plan whose constants are set (dpx_xsolve); differentiable w.r.t. the
+    psi part of the right-hand side `t`, `rho` and — through `ktb`, which the plan already holds as F(ktb) — the
+    measurements (autograd.XSolve)."""
+    t = cabi.require_cuda_f32(t, "t")
+    if ag.needs_grad(t, rho, ktb):
+        return ag.XSolve.apply(plan, t, rho, int(rho_stride), ktb)
+    x = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        cabi.check(cabi.lib().dpx_xsolve(plan.handle, cabi.ptr(t), cabi.ptr(rho), int(rho_stride), 0, cabi.ptr(x), _s(t)),
+                   "dpx_xsolve")
+    return x
 
 
 def dot(x: torch.Tensor, y: torch.Tensor, per_sample: bool = True) -> torch.Tensor:

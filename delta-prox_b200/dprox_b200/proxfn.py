@@ -251,8 +251,7 @@ class deep_prior(ProxFn):
             v = v.clamp(0, 1)
         inp = v.unsqueeze(1) if v.ndim == 3 else v
         den = self.denoisers[self.step] if self.unroll else self.denoiser
-        with torch.no_grad():
-            out = den.denoise(inp, sigma)
+        out = den.denoise(inp, sigma)          # under grad mode the tape runs through the denoiser (tests/test_grad.py:6-18)
         return out.type_as(v).reshape(v.shape).contiguous()
 
     def __repr__(self):

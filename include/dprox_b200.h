@@ -160,6 +160,14 @@ int dpx_stage_prox(dpx_plan* plan, float* x, float* const* v, float* const* u,
  * SPATIAL: (ktb + rho t)/(dq + rho wid + eps).  Lets the host compose LADMM / ADMM_vxu / external-prox
  * variants from the stand-alone kernels below.  (sum_square.py:123-156) */
 int dpx_xsolve(dpx_plan* plan, const float* t, const float* rho, int rho_stride, int it, float* x, void* stream);
+/* Backward of dpx_xsolve (FREQ_DIAG), the closed form of what the reference obtains by autograd through
+ * least_squares.solve_direct (sum_square.py:123-156; used by unrolled training, specialization/unroll.py:42-58):
+ * given g = dL/dx and the forward output x,
+ *   g_ktb = F^-1[F(g) / Dn]                 (= dL/d(sum_q A_q^T b_q);  dL/dt = rho * g_ktb)
+ *   g_rho = sum_k Re(conj(F g)_k (F(t) - (dpsi+wid) F(x))_k / Dn_k) / (H W)      [B] if rho_stride != 0, else [1]
+ * with Dn = dq + rho (dpsi + wid) + eps.  g_rho may be NULL.  x is only read when g_rho is requested. */
+int dpx_xsolve_backward(dpx_plan* plan, const float* g, const float* x, const float* rho, int rho_stride, int it,
+                        float* g_ktb, float* g_rho, void* stream);
 /* v_i <- K_i x0 (affine: scale * A_i x0 - c_i), u_i <- 0.   ADMM.initialize / HQS.initialize
  * (algo/admm.py:61-67, algo/hqs.py:5-8).  u may be NULL for HQS. */
 int dpx_init_state(dpx_plan* plan, const float* x, float* const* v, float* const* u, void* stream);
@@ -178,6 +186,11 @@ int dpx_spectral_filter(dpx_plan* plan, const float* x, const float* otf, int ot
 int dpx_prox_apply(int prox_kind, const float* v, const float* lam, int lam_per_sample, float alpha,
                    float beta, float box_lo, float box_hi, const float* offset, float* out, int batch,
                    size_t per_sample, void* stream);
+/* Backward of dpx_prox_apply for the native `_prox` bodies (nonneg / l1 / l2sq / box):
+ * g_v = dprox/dv * g;  g_lam (device [B] or [1], may be NULL) = sum dprox/dlam * g. */
+int dpx_prox_backward(int prox_kind, const float* v, const float* lam, int lam_per_sample, float alpha, float beta,
+                      float box_lo, float box_hi, const float* offset, const float* g, float* g_v, float* g_lam,
+                      int batch, size_t per_sample, void* stream);
 /* out = a*x + b*y (+ c*z); coefficient pointers are device [B] or [1] arrays or NULL (=1). y,z may be NULL. */
 int dpx_lincomb(float* out, const float* a, const float* x, const float* b, const float* y,
                 const float* c, const float* z, int coeff_per_sample, int batch, size_t per_sample,

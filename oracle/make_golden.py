@@ -484,6 +484,60 @@ def schedules():
     r2, s2 = dp.log_descent(49, 7.65, 10, sigma=7.65 / 255, sqrt=True)
     return dict(r1=_np(r1), s1=_np(s1), r2=_np(r2), s2=_np(s2))
 
+# ------------------------------------------------------------------------------------------------
+# a28 / §3.6: unrolled solver, gradients by the reference's plain autograd through the loop
+# ------------------------------------------------------------------------------------------------
+
+@case
+def unrolled_grads_native():
+    """ADMM with native proxes, 4 unrolled iterations: d loss / d (rhos [B,T], lam of the l1 term, measurements b, x0)."""
+    img, psf, b = _deconv_inputs(2, 3, 16, 24)
+    g = torch.Generator().manual_seed(77)
+    wgt = torch.rand(2, 3, 16, 24, generator=g)
+    b = b.clone().requires_grad_(True)
+    x0 = torch.rand(2, 3, 16, 24, generator=g).requires_grad_(True)
+    rhos = (0.5 + torch.rand(2, 4, generator=g)).requires_grad_(True)
+    lam1 = (0.02 + 0.05 * torch.rand(4, generator=g)).requires_grad_(True)
+    x = dp.Variable()
+    f1, f2 = 0.5 * dp.norm1(x), dp.nonneg(x)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, method="admm", device="cpu")
+    out = solver.solve(x0=x0, rhos=rhos, lams={f1: lam1, f2: torch.full((4,), 0.02)}, max_iter=4)
+    loss = (out * wgt).sum()
+    loss.backward()
+    return dict(psf=psf, b=_np(b), x0=_np(x0), wgt=_np(wgt), rhos=_np(rhos), lam1=_np(lam1), out=_np(out), loss=float(loss),
+                g_b=_np(b.grad), g_x0=_np(x0.grad), g_rhos=_np(rhos.grad), g_lam1=_np(lam1.grad), T=4)
+
+
+@case
+def unrolled_grads_doe():
+    """BASELINE config 5 in miniature: conv_doe (Placeholder PSF) + deep_prior(FFDNet, sqrt=True), `specialize('unroll')`,
+    mse loss; gradients w.r.t. rhos, sigmas and -- through the data formation inp = conv_doe(gt; psf) -- the PSF
+    (examples/papers/deltaprox_siggraph_2023/computional_optics/e2e_optics_dprox.py:46-58)."""
+    g = torch.Generator().manual_seed(31)
+    gt = torch.rand(2, 3, 16, 16, generator=g)
+    psf = torch.rand(1, 3, 16, 16, generator=g)
+    psf = (psf / psf.sum(dim=(-2, -1), keepdim=True)).requires_grad_(True)
+    noise = 0.03 * torch.randn(2, 3, 16, 16, generator=g)
+    den = _RandFFDNetColor(seed=9)
+    x, y, PSF = dp.Variable(), dp.Placeholder(), dp.Placeholder()
+    data_term = dp.sum_squares(dp.conv_doe(x, PSF, circular=True), y)
+    reg_term = dp.deep_prior(x, denoiser=den, sqrt=True)
+    solver = dp.compile(data_term + reg_term, method="admm", device="cpu")
+    solver = dp.specialize(solver, method="unroll", max_iter=3, device="cpu")
+    rhos, sigmas = dp.log_descent(49, 7.65, 3, sigma=7.65 / 255)
+    rhos, sigmas = rhos.clone().requires_grad_(True), sigmas.clone().requires_grad_(True)
+    psf_used = psf * 1.0
+    inp = dp.conv_doe(dp.Variable(), psf_used.detach(), circular=True).forward(gt)      # data formation (differentiable below)
+    otf = sys.modules['dprox.linop.conv'].psf2otf2(psf_used, gt.shape)
+    inp = torch.real(torch.fft.ifftn(otf * torch.fft.fftn(gt, dim=[-2, -1]), dim=[-2, -1])).float() + noise
+    y.value = inp
+    PSF.value = psf_used
+    out = solver.solve(x0=inp, rhos=rhos, lams={reg_term: sigmas})
+    loss = torch.nn.functional.mse_loss(gt, out)
+    loss.backward()
+    return dict(gt=_np(gt), psf=_np(psf), noise=_np(noise), inp=_np(inp), rhos=_np(rhos), sigmas=_np(sigmas), out=_np(out),
+                loss=float(loss), g_rhos=_np(rhos.grad), g_sigmas=_np(sigmas.grad), g_psf=_np(psf.grad), seed=9, T=3)
+
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -96,15 +96,22 @@ def test_no_cpu_fallback():
         dp.conv(x, np.ones((3, 3, 1), "float32")).forward(torch.rand(1, 3, 8, 8))
 
 
-def test_autograd_contract_fails_loudly():
-    """The native loop is forward-only: inputs that require grad must not be silently detached."""
+def test_autograd_contract_routes_to_the_differentiable_engine():
+    """Inputs that require grad are never silently detached: they select the differentiable engine (which,
+    like everything else, needs a CUDA device); the CG x-update has no backward yet and says so."""
     x = dp.Variable()
     s = dp.compile(objective(x, "conv"), device="cpu")
     rhos = torch.ones(4, requires_grad=True)
-    with pytest.raises(NotImplementedError, match="gradients"):
+    assert s._wants_grad(rhos) and not s._wants_grad(torch.ones(4))
+    with torch.no_grad():
+        assert not s._wants_grad(rhos)
+    with pytest.raises(RuntimeError, match="CUDA"):
         s.solve(x0=torch.rand(2, 3, 32, 48), rhos=rhos, max_iter=4)
-    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):      # under no_grad it proceeds (and then needs a GPU)
-        s.solve(x0=torch.rand(2, 3, 32, 48), rhos=rhos, max_iter=4)
+    s2 = dp.compile(dp.sum_squares(dp.mosaic(dp.conv(x, np.ones((3, 3, 1), "float32"))) - torch.rand(1, 3, 8, 8)) + dp.nonneg(x),
+                    device="cpu")
+    assert s2.spec.xupdate == "cg"
+    with pytest.raises((NotImplementedError, RuntimeError), match="CG|CUDA"):
+        s2.solve(x0=torch.rand(1, 3, 8, 8), rhos=rhos, max_iter=4)
 
 
 def test_kernel_otf_matches_reference_construction():
