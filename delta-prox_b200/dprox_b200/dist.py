@@ -71,3 +71,45 @@ def solve_sharded(make_solver, x0: torch.Tensor, rhos=None, lams=None, gather: b
     lams = local_lams if local_lams is not None else shard_schedule(lams, n)
     out = solver.solve(x0=x0[lo:hi], rhos=shard_schedule(rhos, n), lams=lams, **solve_kw)
     return gather_batch(out, n) if gather else out
+
+
+def allreduce_gradients(params, group=None, bucket_bytes: int = 32 << 20, average: bool = True) -> int:
+    """Data-parallel training of an unrolled solver (BASELINE config 5): every rank differentiates its own shard of the
+    batch; the gradients of the shared trainable parameters (rho / sigma schedules, the DOE height map, ...) are summed
+    over ranks in flat buckets — one all-reduce per `bucket_bytes` (NCCL over NVLink on the GPU box, gloo in the CPU
+    tests).  The reference has no distributed training at all; semantics follow DDP: parameters without a
+    gradient contribute zeros, the result is averaged.  Returns the number of collectives issued."""
+    params = [p for p in params if p.requires_grad]
+    if not params or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    w = dist.get_world_size(group)
+    calls, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal calls, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= w
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            gnew = flat[off:off + n].reshape(p.shape).to(p.dtype)
+            if p.grad is None:
+                p.grad = gnew.clone()
+            else:
+                p.grad.copy_(gnew)
+            off += n
+        calls += 1
+        bucket, size = [], 0
+
+    for p in params:
+        nb = p.numel() * 4
+        if bucket and size + nb > bucket_bytes:
+            flush()
+        bucket.append(p)
+        size += nb
+    flush()
+    return calls

@@ -56,7 +56,16 @@ def _worker(rank, world, port, q):
         per_sample = torch.arange(B, dtype=torch.float32).view(B, 1).repeat(1, 2)
         out = ddist.solve_sharded(lambda lo, hi: (Fake(), None), x, rhos=torch.ones(3), lams={"f": per_sample})
         ok_solve = torch.equal(out, x + 3.0 + 2 * torch.arange(B, dtype=torch.float32).view(B, 1, 1, 1))
-        q.put((rank, ok_gather, ok_stop, ok_solve))
+        # DDP-style gradient all-reduce of shared trainable parameters (unrolled training, config 5)
+        p1, p2, p3 = (torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2)),
+                      torch.nn.Parameter(torch.zeros(1), requires_grad=False))
+        p1.grad = torch.full((3,), float(rank + 1))
+        if rank == 0:
+            p2.grad = torch.ones(2, 2)                       # rank 1 has no gradient for p2: contributes zeros
+        ncalls = ddist.allreduce_gradients([p1, p2, p3], bucket_bytes=12)
+        ok_grad = (ncalls == 2 and torch.allclose(p1.grad, torch.full((3,), 1.5)) and torch.allclose(p2.grad, torch.full((2, 2), 0.5))
+                   and p3.grad is None)
+        q.put((rank, ok_gather, ok_stop, ok_solve, ok_grad))
     finally:
         dist.destroy_process_group()
 
