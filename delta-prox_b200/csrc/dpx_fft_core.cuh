@@ -158,15 +158,17 @@ struct Tile {
   }
 };
 
-// Twiddle records: for a pass of radix R over sub-blocks of length L, the factors of butterfly j are stored
-// contiguously, rec[j*R + q] = exp(-2 pi i j q / L), q = 0..R-1 (q = 0 is 1), so a thread fetches them with
-// R/2 128-bit loads.  (tables are built on the host in double precision, see make_twiddle_records)
-template <int R>
-DPX_HD void load_twiddles(const float2* __restrict__ rec, float2 (&w)[R]) {
-  const float4* r4 = reinterpret_cast<const float4*>(rec);
+// Twiddle records: for a pass of radix R over sub-blocks of length L (M = L/R butterflies j = 0..M-1), the factors
+// exp(-2 pi i j q / L), q = 0..R-1 (q = 0 is 1) are stored TRANSPOSED as float4 pairs, rec4[(q/2)*M + j] = (w^{j q}, w^{j (q+1)}):
+// the lanes of a warp work on consecutive j, so each of a thread's R/2 128-bit fetches reads one contiguous run of the
+// table -- one L1 wavefront per fetch instead of one per distinct j ([j][q] records cost 8 wavefronts per fetch, as much
+// LSU time as the data itself; profiles/README.md v6).  (tables are built on the host in double precision)
+template <int R, int M>
+DPX_HD void load_twiddles(const float2* __restrict__ rec, int j, float2 (&w)[R]) {
+  const float4* r4 = reinterpret_cast<const float4*>(rec) + j;
 #pragma unroll
   for (int q = 0; q < R / 2; ++q) {
-    const float4 v = r4[q];
+    const float4 v = r4[q * M];
     w[2 * q] = make_float2(v.x, v.y);
     w[2 * q + 1] = make_float2(v.z, v.w);
   }
@@ -193,7 +195,7 @@ DPX_HD void smem_pass(float2* sm, const float2* __restrict__ rec, int tid, int n
     for (int m = 0; m < R; ++m) a[m] = sm[LIN ? p0 + T::template delta<M>(m) * T::COLS : T::phys(base + m * M, c)];
     if (TWIDDLE) {
       float2 w[R];
-      load_twiddles<R>(rec + j * R, w);
+      load_twiddles<R, M>(rec, j, w);
       if (INV) {
 #pragma unroll
         for (int q = 1; q < R; ++q) a[q] = cmulc(a[q], w[q]);

@@ -56,12 +56,12 @@ inline std::vector<float2> make_twiddle_records() {
   for (int j = 0; j < T::MA; ++j)
     for (int q = 0; q < T::RA; ++q) {
       const double a = two_pi * (double)j * q / T::N;
-      t[L::A_OFF + j * T::RA + q] = make_float2((float)cos(a), (float)-sin(a));
+      t[L::A_OFF + ((q / 2) * T::MA + j) * 2 + (q % 2)] = make_float2((float)cos(a), (float)-sin(a));
     }
   for (int j = 0; j < T::MB; ++j)
     for (int q = 0; q < T::RB; ++q) {
       const double a = two_pi * (double)j * q / T::MA;
-      t[L::B_OFF + j * T::RB + q] = make_float2((float)cos(a), (float)-sin(a));
+      t[L::B_OFF + ((q / 2) * T::MB + j) * 2 + (q % 2)] = make_float2((float)cos(a), (float)-sin(a));
     }
   return t;
 }
@@ -99,7 +99,7 @@ struct Driver {
         RowParams rp;
         rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
         ColParams cp;
-        cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
+        cp.C = C; cp.W = W; cp.groups = G + 1; cp.bmul = 1; cp.eps_im = 0.f; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
         const dim3 rgrid(H / ROWS, P), cgrid(B, G + 1, C);
@@ -119,6 +119,62 @@ struct Driver {
               be.template row_persist<TW>(dim3(be.persistent_ctas()), RowPersistSmem<TW>::BYTES, rp, (H / ROWS) * P);
             else row(std::integral_constant<int, ROW_MID>{});
           }
+          else row(std::integral_constant<int, ROW_LAST>{});
+        }
+      });
+    });
+  }
+
+  // ---- plane-pair engine (k_rowz / k_col on Z = X_A + i X_B; see dpx_fused_kernels.cuh) ---------------------------------
+  // usable when the two planes of every pair share all solve coefficients: even batch, batch-shared diagonal, shared
+  // (not per-sample) rho and lam schedules
+  static bool pairs_ok(int B, int dq_batch, int rho_stride, const PsiPack& psi) {
+    if (B < 2 || B % 2 != 0 || dq_batch != 1 || rho_stride != 0) return false;
+    for (int i = 0; i < psi.n; ++i)
+      if (psi.t[i].lam_stride != 0) return false;
+    return true;
+  }
+  static size_t pair_elems(int planes, int H, int W) { return (size_t)planes * H * W; }   // float2 (fbz, S) / float (dqz) count
+
+  void pack_constants_pairs(int B, int C, int H, int W, const float2* fb_std, float2* fbz, const float* dq_std, float* dqz) {
+    dispatch_size(W, [&](auto wn) {
+      dispatch_size(H, [&](auto hn) {
+        using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
+        using TH = typename TileFor<decltype(hn)::value, CG>::type;
+        if (fb_std) be.template packz_fb<TH, TW>(fb_std, fbz, (B / 2) * C, C, H, W);
+        if (dq_std) be.template packz_dq<TH, TW>(dq_std, dqz, C, H, W);
+      });
+    });
+  }
+
+  void iterate_pairs(int B, int C, int H, int W, float2* S, const PsiPack& psi, int hqs, float* x, const float2* fbz,
+                     const float* dqz, float wid, float eps, const float* rho, int it0, int n_iters, const float2* tw_h,
+                     const float2* tw_w) {
+    if (n_iters <= 0) return;
+    const int PP = (B / 2) * C, G = W / CG;
+    dispatch_size(W, [&](auto wn) {
+      dispatch_size(H, [&](auto hn) {
+        using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
+        using TH = typename TileFor<decltype(hn)::value, CG>::type;
+        RowParams rp;
+        rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
+        ColParams cp;
+        cp.C = C; cp.W = W; cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.S = S; cp.fbp = fbz; cp.dqp = dqz; cp.dq_batch = 1;
+        cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
+        cp.rho.p = rho; cp.rho.stride = 0; cp.rho.it = it0; cp.tw = tw_h;
+        const dim3 rgrid(H / ROWS, PP), cgrid(B / 2, G, C);
+        const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2), csm = TH::SMEM_FLOAT2 * sizeof(float2);
+        auto row = [&](auto mode) {
+          constexpr int MODE = decltype(mode)::value;
+          if (psi.n == 1) be.template rowz<TW, MODE, true>(rgrid, rsm, rp);
+          else be.template rowz<TW, MODE, false>(rgrid, rsm, rp);
+        };
+        row(std::integral_constant<int, ROW_FIRST>{});
+        for (int k = 0; k < n_iters; ++k) {
+          cp.rho.it = it0 + k;
+          be.template col<TH>(cgrid, csm, cp);
+          rp.it = it0 + k;
+          if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
           else row(std::integral_constant<int, ROW_LAST>{});
         }
       });

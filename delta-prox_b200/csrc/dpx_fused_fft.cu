@@ -59,6 +59,27 @@ struct CudaBackend {
     k_col<TH><<<grid, kThreads, smem, s>>>(p);
     after();
   }
+  template <class TW, int MODE, bool SINGLE>
+  void rowz(dim3 grid, size_t smem, const RowParams& p) {
+    if (rc) return;
+    prep(k_rowz<TW, MODE, SINGLE>, smem);
+    k_rowz<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
+    after();
+  }
+  template <class TH, class TW>
+  void packz_fb(const float2* src, float2* dst, int pairs, int C, int H, int W) {
+    if (rc) return;
+    const size_t total = (size_t)pairs * H * W;
+    k_packz_fb<TH, TW><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, pairs, C, H, W);
+    after();
+  }
+  template <class TH, class TW>
+  void packz_dq(const float* src, float* dst, int C, int H, int W) {
+    if (rc) return;
+    const size_t total = (size_t)C * H * W;
+    k_packz_dq<TH, TW><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, C, H, W);
+    after();
+  }
   template <class TH, typename V>
   void pack(const V* src, V* dst, int planes, int H, int W, int G, V zero) {
     if (rc) return;
@@ -86,6 +107,8 @@ class FusedEngine final : public FftEngine {
       DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       const char* env = getenv("DPX_ROW_PERSIST");            // 0 disables the persistent row kernel (for A/B runs)
       persist_ctas_ = (env && env[0] == '0') ? 0 : 2 * sms;
+      const char* pe = getenv("DPX_PAIRS");                   // 1 selects the plane-pair engine where it applies
+      pairs_enabled_ = pe && pe[0] == '1';               // opt-in until its row kernel is software-pipelined too
     }
     rc = upload_twiddles(g.H, &tw_h_);
     if (!rc) rc = upload_twiddles(g.W, &tw_w_);
@@ -100,35 +123,44 @@ class FusedEngine final : public FftEngine {
     delete this;
   }
   bool fused() const override { return true; }
-  void reset_constants() override { dq_packed_ = false; }
+  void reset_constants() override { dq_set_ = false; dq_std_ = nullptr; dq_dirty_ = true; }
 
+  // Constants are packed lazily, in the layout of the engine variant the next fused_iters call selects (half-spectrum
+  // planes or plane pairs): set_constants only records which standard-layout arrays (owned by the plan) changed.
   int set_constants(const float2* fb_std, const float* dq_std, int dq_batch, cudaStream_t s) override {
-    const int Cd = dq_batch > 1 ? g_.P : g_.C;
-    const size_t nd = packed_elems(Cd, g_.H, g_.W);
+    fb_std_ = fb_std; fb_dirty_ = true;                 // nullptr = zero right-hand side
+    if (dq_std || !dq_set_) { dq_std_ = dq_std; dq_dirty_ = true; dq_set_ = dq_set_ || dq_std != nullptr; }
+    dq_batch_ = dq_batch;
+    (void)s;
+    return DPX_OK;
+  }
+
+  int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2*, const float*, int, float wid,
+                  float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
+    CudaBackend be{s};
+    be.n_persist = persist_ctas_;
+    Driver<CudaBackend> drv(be);
+    const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g.B, dq_batch_, rho_stride, psi);
+    if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = true; packed_pairs_ = pairs; }
+    const int Cd = dq_batch_ > 1 ? g_.P : g_.C;
+    const size_t nd = pairs ? Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W) : packed_elems(Cd, g_.H, g_.W);
     if (dqp_cap_ < nd) {
       cudaFree(dqp_); dqp_ = nullptr;
       DPX_CUDA(cudaMalloc(&dqp_, nd * sizeof(float)));
       bytes_ += (nd - dqp_cap_) * sizeof(float);
       dqp_cap_ = nd;
+      dq_dirty_ = true;
     }
-    dq_batch_ = dq_batch;
-    if (!dq_std && !dq_packed_) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));   // nullptr = keep what is packed
-    if (dq_std) dq_packed_ = true;
-    if (!fb_std) DPX_CUDA(cudaMemsetAsync(fbp_, 0, s_elems(g_.P, g_.H, g_.W) * sizeof(float2), s));
-    CudaBackend be{s};
-    Driver<CudaBackend> drv(be);
-    drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_std, fbp_, dq_std, dqp_);
-    return be.rc;
-  }
-
-  int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2*, const float*, int, float wid,
-                  float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
-    if (!dqp_) { set_error("fused engine: constants not packed"); return DPX_ERR_STATE; }
-    CudaBackend be{s};
-    be.n_persist = persist_ctas_;
-    Driver<CudaBackend> drv(be);
-    drv.iterate(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it0, n_iters,
-                tw_h_, tw_w_);
+    if (dq_dirty_ && !dq_std_) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));
+    if (fb_dirty_ && !fb_std_) DPX_CUDA(cudaMemsetAsync(fbp_, 0, s_elems(g_.P, g_.H, g_.W) * sizeof(float2), s));
+    if (pairs) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
+    else drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
+    fb_dirty_ = dq_dirty_ = false;
+    if (pairs)
+      drv.iterate_pairs(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, wid, eps, rho, it0, n_iters, tw_h_, tw_w_);
+    else
+      drv.iterate(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it0, n_iters,
+                  tw_h_, tw_w_);
     return be.rc;
   }
 
@@ -146,7 +178,10 @@ class FusedEngine final : public FftEngine {
   size_t dqp_cap_ = 0, bytes_ = 0;
   int dq_batch_ = 1;
   int persist_ctas_ = 0;
-  bool dq_packed_ = false;
+  const float2* fb_std_ = nullptr;
+  const float* dq_std_ = nullptr;
+  bool fb_dirty_ = true, dq_dirty_ = true, dq_set_ = false;
+  bool packed_pairs_ = false, pairs_enabled_ = false;
 };
 
 }  // namespace

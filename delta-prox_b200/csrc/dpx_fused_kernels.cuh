@@ -50,6 +50,9 @@ struct RowParams {
 
 struct ColParams {
   int C, W;
+  int groups;                    // column groups per (pair-)plane: W/2/CG + 1 (half spectrum) or W/CG (plane pairs)
+  int bmul;                      // sample index of plane index p is bmul * (p / C): 1, or 2 for plane pairs
+  float eps_im;                  // eps added to the imaginary numerator: 0, or eps when the imaginary part carries a plane
   float2* S;
   const float2* fbp;             // packed F(K^T b)      [(P*(G+1)), H/RC, CG, RC]
   const float* dqp;              // packed sum|OTF|^2    [(Cd*(G+1)), H/RC, CG, RC]
@@ -201,12 +204,12 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
   const int b = p / P.C;
   const int H = P.H;
 
-  // ---- 0. twiddle records -> shared memory, transposed to [q/2][j] ---------------------------------------------
+  // ---- 0. twiddle records ([q/2][j], fft::load_twiddles) -> shared memory ------------------------------------------
   {
-    const float4* gA = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::A_OFF);   // [j][q/2]
-    for (int t = tid; t < RowSmem<TW>::TWA_F4; t += kThreads) twA_s[(t % (RA / 2)) * MA + t / (RA / 2)] = gA[t];
+    const float4* gA = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::A_OFF);
+    for (int t = tid; t < RowSmem<TW>::TWA_F4; t += kThreads) twA_s[t] = gA[t];
     const float4* gB = reinterpret_cast<const float4*>(P.tw + fft::TwiddleLayout<TW>::B_OFF);
-    for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[(t % (RB / 2)) * MB + t / (RB / 2)] = gB[t];
+    for (int t = tid; t < RowSmem<TW>::TWB_F4; t += kThreads) twB_s[t] = gB[t];
   }
 
   {  // pull this CTA's own dual rows into L2 now; they are consumed two FFT passes later (step 3)
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
         float2 a[RA], w[RA];
 #pragma unroll
         for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NPAIR];
-        fft::load_twiddles<RA>(twA + j * RA, w);
+        fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
         for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
         fft::Dft<RA, true>::run(a);
@@ -533,14 +536,15 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   const int tid = threadIdx.x;
   // grid = (B, G+1, C): the problems of the batch are adjacent in launch order, so the sum|OTF|^2 records of
   // tile (g, channel) -- shared by the batch -- are fetched from DRAM once and hit in L2 for the other problems
-  const int b = blockIdx.x, g = blockIdx.y;
-  const int p = b * P.C + blockIdx.z;
-  const int G = P.W / 2 / CG;
-  float2* tile = P.S + s_index(p, g, 0, 0, H, G);
+  const int g = blockIdx.y;
+  const int p = blockIdx.x * P.C + blockIdx.z;
+  const int b = blockIdx.x * P.bmul;
+  const int NG = P.groups;
+  float2* tile = P.S + ((size_t)p * NG + g) * H * CG;
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
   {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
-    const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * (G + 1) + g) * H * CG);
+    const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * NG + g) * H * CG);
     for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) prefetch_l2(nf + o);
   }
 
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
 #pragma unroll
     for (int m = 0; m < RA; ++m) a[m] = tile[(size_t)(j + m * MA) * CG + c];
     fft::Dft<RA, false>::run(a);
-    fft::load_twiddles<RA>(twA + j * RA, w);
+    fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
     for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
 #pragma unroll
@@ -576,8 +580,8 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     // constants of this block: record [m/2][task] (float4 = two spectrum values) / [m/4][task] (four diagonals), so
     // consecutive threads read consecutive 16-byte words
     constexpr int NT = CG * (H / RC);
-    const float4* fb4 = reinterpret_cast<const float4*>(P.fbp) + ((size_t)p * (G + 1) + g) * (H * CG / 2) + t;
-    const float4* dq4 = reinterpret_cast<const float4*>(P.dqp) + ((size_t)pd * (G + 1) + g) * (H * CG / 4) + t;
+    const float4* fb4 = reinterpret_cast<const float4*>(P.fbp) + ((size_t)p * NG + g) * (H * CG / 2) + t;
+    const float4* dq4 = reinterpret_cast<const float4*>(P.dqp) + ((size_t)pd * NG + g) * (H * CG / 4) + t;
     float2 f[RC];
     float d[RC];
 #pragma unroll
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
       // one reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions: the divisions were 19 % of the kernel's
       // instructions (profiles/README.md, v6); 1/(H W) of the unnormalised inverse transform is folded in
       const float r = fast_div(P.inv_n, d[m] + den0);
-      a[m] = make_float2((f[m].x + rho * a[m].x + P.eps) * r, (f[m].y + rho * a[m].y) * r);
+      a[m] = make_float2((f[m].x + rho * a[m].x + P.eps) * r, (f[m].y + rho * a[m].y + P.eps_im) * r);
     }
     fft::Dft<RC, true>::run(a);
 #pragma unroll
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     float2 a[RA], w[RA];
 #pragma unroll
     for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TH::template delta<MA>(m) * CG];
-    fft::load_twiddles<RA>(twA + j * RA, w);
+    fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
     for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
     fft::Dft<RA, true>::run(a);
@@ -643,6 +647,187 @@ __global__ void k_pack(const V* __restrict__ src, V* __restrict__ dst, int plane
   const int h = TH::freq_of_pos(blk * RC + m);
   const int k = g < G ? g * CG + c : (c == 0 ? W / 2 : -1);
   dst[i] = k >= 0 ? src[((size_t)p * H + h) * (W / 2 + 1) + k] : zero;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Plane-pair engine.  Two real planes that share every coefficient of the spectral solve (same channel of two
+//  problems of the batch, shared rho / lam schedules) ride ONE complex 2-D transform: z = x_A + i x_B.  The solve
+//  (F(K^T b) + rho T + eps)/(D + rho wid + eps) is linear with REAL coefficients, so it acts on Z = X_A + i X_B directly
+//  and the Hermitian split / merge of the real-input trick (steps 1 and 5 of k_row: digit-reversed scatter with mirrored
+//  indices, ~40 % of that kernel's instructions and a third of its shared-memory traffic) disappears: the first pass of
+//  the row transform is fed from global memory, the last one stores to global memory, and the spectrum is a plain
+//  [W/CG groups][H][CG] array of the full W columns (in the digit-reversed order the row DIF leaves them in; constants
+//  are pre-permuted to match, k_packz_*).  Same DRAM traffic as the half-spectrum engine, one third fewer instructions.
+//     S[((pp*G + g)*H + h)*CG + c],  G = W/CG,  pair pp = (b/2)*C + ch  holds planes (b, ch) + i (b+1, ch), b even;
+//     column s = g*CG + c holds digit-reversed position (s % (W/RC))*RC + s / (W/RC)  (coalescing, see step 1).
+// ------------------------------------------------------------------------------------------------
+template <class TW, int MODE, bool SINGLE>
+__global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowParams P) {
+  static_assert(TW::COLS == ROWS, "row tile of the pair engine holds one complex sequence per image row");
+  constexpr int W = TW::N, NSEQ = TW::COLS, G = W / CG;
+  constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA;
+  static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass must fall into the same column of different groups");
+  DPX_DYN_SMEM(float2, sm);
+  const int tid = threadIdx.x;
+  const int pp = blockIdx.y, h0 = blockIdx.x * ROWS;
+  const int H = P.H;
+  const int bq = pp / P.C;
+  const int pA = 2 * bq * P.C + (pp - bq * P.C), pB = pA + P.C;
+  const int b = 2 * bq;
+  const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
+  const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
+  constexpr int NT1 = NSEQ * (W / RC);
+
+  {  // pull this CTA's dual rows into L2 now; they are consumed two FFT passes later
+    const size_t eA = ((size_t)pA * H + h0) * W, eB = ((size_t)pB * H + h0) * W;
+    for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
+      const float* base = P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u;
+      if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) { prefetch_l2(base + eA + o); prefetch_l2(base + eB + o); }
+    }
+  }
+
+  if (MODE != ROW_FIRST) {
+    // ---- 1. inverse pass C fed straight from global memory.  Column storage order: position pos of the digit-reversed
+    //         spectrum lives at column s = (pos % RC) * (W/RC) + pos / RC, so the RC inputs of a butterfly are W/RC columns
+    //         apart and the lanes of a warp (4 columns x 4 rows, then the next group) read whole 128-byte lines.
+    for (int t = tid; t < NT1; t += kThreads) {
+      const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
+      const int blk = gq * CG + cc;
+      const float2* src = P.S + (((size_t)pp * G + gq) * H + h0 + r) * CG + cc;
+      float2 a[RC];
+#pragma unroll
+      for (int m = 0; m < RC; ++m) a[m] = ld_stream2(src + (size_t)m * (W / RC / CG) * H * CG);
+      fft::Dft<RC, true>::run(a);
+      const int p0 = TW::phys(blk * RC, r);
+#pragma unroll
+      for (int m = 0; m < RC; ++m) sm[p0 + TW::template delta<1>(m) * NSEQ] = a[m];
+    }
+    __syncthreads();
+    fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
+  }
+  __syncthreads();
+
+  // ---- 2. fused in registers: last inverse pass -> (x_A, x_B);  prox / dual / next rhs;  first forward pass -------------
+  {
+    const PsiTerm& tm = P.psi.t[0];
+    const bool simple = SINGLE && MODE == ROW_MID && tm.scale == 1.f && tm.beta == 1.f && tm.off == nullptr &&
+                        (tm.prox == DPX_PROX_NONNEG || tm.prox == DPX_PROX_L1 || tm.prox == DPX_PROX_L2SQ || tm.prox == DPX_PROX_BOX);
+    const float lam_eff = (MODE == ROW_FIRST) ? 0.f : tm.lam[(size_t)b * tm.lam_stride + P.it] * tm.alpha;
+    for (int t = tid; t < NSEQ * MA; t += kThreads) {
+      const int c = t % NSEQ, j = t / NSEQ;
+      const int p0 = TW::phys(j, c);
+      float2 a[RA], w[RA];
+      if (MODE != ROW_FIRST) {
+#pragma unroll
+        for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NSEQ];
+        fft::load_twiddles<RA, MA>(twA, j, w);
+#pragma unroll
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
+        fft::Dft<RA, true>::run(a);                     // a[m] = (x_A[h0+c][j + m MA], x_B[h0+c][j + m MA])
+      }
+      const size_t ea = ((size_t)pA * H + h0 + c) * W + j, eb = ((size_t)pB * H + h0 + c) * W + j;
+      if (MODE == ROW_LAST) {
+#pragma unroll
+        for (int m = 0; m < RA; ++m) { P.x[ea + m * MA] = a[m].x; P.x[eb + m * MA] = a[m].y; }
+      }
+      if (simple) {
+        float* __restrict__ up = tm.u;
+        switch (tm.prox) {
+          case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA>(a, up + ea, up + eb, up, ea, eb, P.hqs, lam_eff, tm.lo, tm.hi); break;
+          case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA>(a, up + ea, up + eb, up, ea, eb, P.hqs, lam_eff, tm.lo, tm.hi); break;
+          case DPX_PROX_L2SQ: mid_simple<DPX_PROX_L2SQ, RA, MA>(a, up + ea, up + eb, up, ea, eb, P.hqs, lam_eff, tm.lo, tm.hi); break;
+          default: mid_simple<DPX_PROX_BOX, RA, MA>(a, up + ea, up + eb, up, ea, eb, P.hqs, lam_eff, tm.lo, tm.hi); break;
+        }
+      } else if (SINGLE) {
+        row_term<MODE, false, RA, MA>(tm, P.hqs, b, P.it, ea, eb, a, a);
+      } else {
+        float2 acc[RA];
+#pragma unroll
+        for (int m = 0; m < RA; ++m) acc[m] = make_float2(0.f, 0.f);
+        for (int i = 0; i < P.psi.n; ++i) row_term<MODE, true, RA, MA>(P.psi.t[i], P.hqs, b, P.it, ea, eb, a, acc);
+#pragma unroll
+        for (int m = 0; m < RA; ++m) a[m] = acc[m];
+      }
+      if (MODE == ROW_LAST) continue;
+      fft::Dft<RA, false>::run(a);
+#ifndef DPX_EMU
+      asm volatile("" ::: "memory");                    // re-read the twiddle record (L1 hit) instead of keeping 32 registers live
+#endif
+      fft::load_twiddles<RA, MA>(twA, j, w);
+#pragma unroll
+      for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
+#pragma unroll
+      for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
+    }
+  }
+  if (MODE == ROW_LAST) return;
+  __syncthreads();
+
+  // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ----------------------------
+  fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
+  __syncthreads();
+  for (int t = tid; t < NT1; t += kThreads) {
+    const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
+    const int blk = gq * CG + cc;
+    const int p0 = TW::phys(blk * RC, r);
+    float2 a[RC];
+#pragma unroll
+    for (int m = 0; m < RC; ++m) a[m] = sm[p0 + TW::template delta<1>(m) * NSEQ];
+    fft::Dft<RC, false>::run(a);
+    float2* dst = P.S + (((size_t)pp * G + gq) * H + h0 + r) * CG + cc;
+#pragma unroll
+    for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
+  }
+}
+
+// Constant packing for the pair engine (cold path).  Standard R2C half spectra -> full-spectrum records of pair pp in
+// k_col's per-thread record order, columns in the row transform's digit-reversed order:
+//   fbz = F(K^T b)_A + i F(K^T b)_B   (bins k > W/2 by Hermitian symmetry),  dqz = sum|OTF|^2 (even symmetry).
+template <class TH, class TW>
+__global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, int H, int W) {
+  constexpr int RC = TH::RC;
+  const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
+  const size_t total = (size_t)pairs * G * H * CG;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int lane = (int)(i % 2);                     // dst[tile][m / 2][task][m % 2]
+  size_t r = i / 2;
+  const int task = (int)(r % NT); r /= NT;
+  const int mg = (int)(r % (RC / 2)); r /= (RC / 2);
+  const int g = (int)(r % G);
+  const int pp = (int)(r / G);
+  const int m = mg * 2 + lane, c = task % CG, blk = task / CG;
+  const int sc = g * CG + c;                          // storage column -> digit-reversed position -> frequency
+  const int h = TH::freq_of_pos(blk * RC + m), k = TW::freq_of_pos((sc % (W / TW::RC)) * TW::RC + sc / (W / TW::RC));
+  const int bq = pp / C, pA = 2 * bq * C + (pp - bq * C), pB = pA + C;
+  float2 fa, fb;
+  if (k < Wc) {
+    fa = src[((size_t)pA * H + h) * Wc + k];
+    fb = src[((size_t)pB * H + h) * Wc + k];
+  } else {
+    const int hm = (H - h) % H, km = W - k;
+    fa = src[((size_t)pA * H + hm) * Wc + km]; fa.y = -fa.y;
+    fb = src[((size_t)pB * H + hm) * Wc + km]; fb.y = -fb.y;
+  }
+  dst[i] = make_float2(fa.x - fb.y, fa.y + fb.x);
+}
+template <class TH, class TW>
+__global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
+  constexpr int RC = TH::RC;
+  const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
+  const size_t total = (size_t)C * G * H * CG;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int lane = (int)(i % 4);                     // dst[tile][m / 4][task][m % 4]
+  size_t r = i / 4;
+  const int task = (int)(r % NT); r /= NT;
+  const int mg = (int)(r % (RC / 4)); r /= (RC / 4);
+  const int g = (int)(r % G);
+  const int ch = (int)(r / G);
+  const int m = mg * 4 + lane, c = task % CG, blk = task / CG;
+  const int sc = g * CG + c;
+  const int h = TH::freq_of_pos(blk * RC + m), k = TW::freq_of_pos((sc % (W / TW::RC)) * TW::RC + sc / (W / TW::RC));
+  dst[i] = k < Wc ? src[((size_t)ch * H + h) * Wc + k] : src[((size_t)ch * H + (H - h) % H) * Wc + (W - k)];
 }
 
 }  // namespace fused

@@ -1,7 +1,9 @@
 // emu_fused.cpp — TEST INFRASTRUCTURE: runs the fused FFT engine's kernels (same source as the GPU build)
 // on the CPU through tests/emu/cuda_emu.h.  Built by tests/test_fused_emulator.py with g++ and driven via ctypes.
 #define DPX_EMU
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "dpx_fused_driver.cuh"
@@ -25,6 +27,20 @@ struct EmuBackend {
   void col(dim3 grid, size_t smem, ColParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_col<TH>(p); });
   }
+  template <class TW, int MODE, bool SINGLE>
+  void rowz(dim3 grid, size_t smem, RowParams p) {
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz<TW, MODE, SINGLE>(p); });
+  }
+  template <class TH, class TW>
+  void packz_fb(const float2* src, float2* dst, int pairs, int C, int H, int W) {
+    const size_t total = (size_t)pairs * H * W;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_fb<TH, TW>(src, dst, pairs, C, H, W); });
+  }
+  template <class TH, class TW>
+  void packz_dq(const float* src, float* dst, int C, int H, int W) {
+    const size_t total = (size_t)C * H * W;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_dq<TH, TW>(src, dst, C, H, W); });
+  }
   template <class TH, typename V>
   void pack(const V* src, V* dst, int planes, int H, int W, int G, V zero) {
     const size_t total = (size_t)planes * (G + 1) * H * CG;
@@ -45,11 +61,10 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C
   const int P = B * C, Cd = dq_batch > 1 ? P : C;
   std::vector<float2> S(s_elems(P, H, W), make_float2(0.f, 0.f));
   std::vector<float2> fbp(packed_elems(P, H, W));
-  std::vector<float> dqp(packed_elems(Cd, H, W));
+  std::vector<float> dqp(std::max(packed_elems(Cd, H, W), (size_t)C * H * W));     // the pair layout holds the full spectrum
   auto twh = twiddle_records_for(H), tww = twiddle_records_for(W);
   EmuBackend be;
   Driver<EmuBackend> drv(be);
-  drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
   PsiPack pk;
   pk.n = n_psi;
   for (int i = 0; i < n_psi; ++i) {
@@ -58,6 +73,13 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C
     t.lo = 0.f; t.hi = 1.f; t.v = v[i]; t.u = hqs ? nullptr : u[i]; t.off = off ? off[i] : nullptr;
     t.lam = lam + (size_t)i * T; t.lam_stride = 0;
   }
+  const bool pairs = !getenv("DPX_EMU_NO_PAIRS") && Driver<EmuBackend>::pairs_ok(B, dq_batch, 0, pk);
+  if (pairs) {      // plane-pair engine: what the CUDA engine selects for an even batch with shared schedules
+    drv.pack_constants_pairs(B, C, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
+    drv.iterate_pairs(B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), wid, eps, rho, 0, T, twh.data(), tww.data());
+    return 2;
+  }
+  drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
   drv.iterate(B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), dq_batch, wid, eps, rho, 0, 0, T, twh.data(), tww.data());
   return 0;
 }

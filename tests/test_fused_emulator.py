@@ -58,7 +58,8 @@ def run_emu(lib, b, psf, kinds, scales, alphas, rho, lams, T, hqs):
                            (C.c_float * m)(*([1.0] * m)), fptr(x), arr(v), arr(u), None,
                            fb.view(np.float32).ctypes.data_as(C.POINTER(C.c_float)), fptr(dq), 1,
                            C.c_float(float(sum(s * s for s in scales))), C.c_float(1e-7), fptr(rho_a), fptr(lam_a), T, int(hqs))
-    assert rc == 0
+    assert rc in (0, 2)                # 2 = the plane-pair engine ran (even batch, shared schedules)
+    run_emu.last_engine = "pairs" if rc == 2 else "planes"
     return x, v, u
 
 
@@ -100,3 +101,20 @@ def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     assert rel(x, want[0].numpy()) < 5e-6 and rel(v[0], want[1][0].numpy()) < 5e-5
     if method == "admm":
         assert rel(u[0], want[2][0].numpy()) < 5e-5
+
+
+def test_pair_engine_is_selected_and_matches_plane_engine(emu, monkeypatch):
+    """Even batch + shared schedules -> plane-pair engine (k_rowz, paired k_col); same answer as the half-spectrum engine
+    to fp32 round-off, on a non-square image with 3 channels and two prox terms."""
+    g = torch.Generator().manual_seed(17)
+    B, Cc, H, W, T = 4, 3, 64, 128, 3
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(5, 1.5)
+    b = (orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    monkeypatch.delenv("DPX_EMU_NO_PAIRS", raising=False)
+    got = run_emu(emu, b, psf, [1, 0], [1.0, 1.0], [0.5, 1.0], 0.7, [0.05, 0.02], T, False)
+    assert run_emu.last_engine == "pairs"
+    monkeypatch.setenv("DPX_EMU_NO_PAIRS", "1")
+    base = run_emu(emu, b, psf, [1, 0], [1.0, 1.0], [0.5, 1.0], 0.7, [0.05, 0.02], T, False)
+    assert run_emu.last_engine == "planes"
+    assert rel(got[0], base[0]) < 2e-6 and rel(got[2][0], base[2][0]) < 2e-5 and rel(got[1][1], base[1][1]) < 2e-5
