@@ -76,6 +76,20 @@ struct Driver {
   Backend& be;
   explicit Driver(Backend& b) : be(b) {}
 
+  // column kernel: the persistent TMA-pipelined variant where three padded tiles fit shared memory, else k_col
+  template <class TH>
+  void launch_col(const ColParams& cp, int nb, int groups, int C) {
+    if constexpr (TH::N == 1024 || TH::N == 2048) {
+      if (be.sm_count() > 0) {
+        const int n_tiles = nb * groups * C, per_sm = TH::N >= 2048 ? 1 : 2;
+        const int ctas = n_tiles < be.sm_count() * per_sm ? n_tiles : be.sm_count() * per_sm;
+        be.template col_tma<TH>(dim3(ctas), ColTmaCfg<TH>::BYTES, cp, n_tiles, nb);
+        return;
+      }
+    }
+    be.template col<TH>(dim3(nb, groups, C), TH::SMEM_FLOAT2 * sizeof(float2), cp);
+  }
+
   // packs F(K^T b) (complex, [P,H,Wc]) and sum|OTF|^2 (real, [Cd,H,Wc]) into k_col's record layout
   void pack_constants(int P, int Cd, int H, int W, const float2* fb_std, float2* fbp, const float* dq_std, float* dqp) {
     const int G = (W / 2) / CG;
@@ -102,8 +116,8 @@ struct Driver {
         cp.C = C; cp.W = W; cp.groups = G + 1; cp.bmul = 1; cp.eps_im = 0.f; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
-        const dim3 rgrid(H / ROWS, P), cgrid(B, G + 1, C);
-        const size_t rsm = RowSmem<TW>::BYTES, csm = TH::SMEM_FLOAT2 * sizeof(float2);
+        const dim3 rgrid(H / ROWS, P);
+        const size_t rsm = RowSmem<TW>::BYTES;
         auto row = [&](auto mode) {
           constexpr int MODE = decltype(mode)::value;
           if (psi.n == 1) be.template row<TW, MODE, true>(rgrid, rsm, rp);
@@ -112,7 +126,7 @@ struct Driver {
         row(std::integral_constant<int, ROW_FIRST>{});
         for (int k = 0; k < n_iters; ++k) {
           cp.rho.it = it0 + k;
-          be.template col<TH>(cgrid, csm, cp);
+          launch_col<TH>(cp, B, G + 1, C);
           rp.it = it0 + k;
           if (k + 1 < n_iters) {
             if (psi.n == 1 && be.persistent_ctas() > 0)
@@ -162,8 +176,8 @@ struct Driver {
         cp.C = C; cp.W = W; cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.S = S; cp.fbp = fbz; cp.dqp = dqz; cp.dq_batch = 1;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = 0; cp.rho.it = it0; cp.tw = tw_h;
-        const dim3 rgrid(H / ROWS, PP), cgrid(B / 2, G, C);
-        const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2), csm = TH::SMEM_FLOAT2 * sizeof(float2);
+        const dim3 rgrid(H / ROWS, PP);
+        const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2);
         auto row = [&](auto mode) {
           constexpr int MODE = decltype(mode)::value;
           if (psi.n == 1) be.template rowz<TW, MODE, true>(rgrid, rsm, rp);
@@ -172,9 +186,14 @@ struct Driver {
         row(std::integral_constant<int, ROW_FIRST>{});
         for (int k = 0; k < n_iters; ++k) {
           cp.rho.it = it0 + k;
-          be.template col<TH>(cgrid, csm, cp);
+          launch_col<TH>(cp, B / 2, G, C);
           rp.it = it0 + k;
-          if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
+          if (k + 1 < n_iters) {
+            if (psi.n == 1 && be.persistent_ctas() > 0) {
+              using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
+              be.template rowz_persist<TW2>(dim3(be.persistent_ctas()), RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);
+            } else row(std::integral_constant<int, ROW_MID>{});
+          }
           else row(std::integral_constant<int, ROW_LAST>{});
         }
       });

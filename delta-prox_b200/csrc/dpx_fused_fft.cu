@@ -52,6 +52,15 @@ struct CudaBackend {
     k_row_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
     after();
   }
+  int n_sm = 0;                                       // SMs for the persistent TMA column kernel; 0 disables it
+  int sm_count() const { return n_sm; }
+  template <class TH>
+  void col_tma(dim3 grid, size_t smem, const ColParams& p, int n_tiles, int nb) {
+    if (rc) return;
+    prep(k_col_tma<TH>, smem);
+    k_col_tma<TH><<<grid, ColTmaCfg<TH>::NT, smem, s>>>(p, n_tiles, nb);
+    after();
+  }
   template <class TH>
   void col(dim3 grid, size_t smem, const ColParams& p) {
     if (rc) return;
@@ -64,6 +73,13 @@ struct CudaBackend {
     if (rc) return;
     prep(k_rowz<TW, MODE, SINGLE>, smem);
     k_rowz<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
+    after();
+  }
+  template <class TW>
+  void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
+    if (rc) return;
+    prep(k_rowz_mid_persist<TW>, smem);
+    k_rowz_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
     after();
   }
   template <class TH, class TW>
@@ -107,8 +123,10 @@ class FusedEngine final : public FftEngine {
       DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       const char* env = getenv("DPX_ROW_PERSIST");            // 0 disables the persistent row kernel (for A/B runs)
       persist_ctas_ = (env && env[0] == '0') ? 0 : 2 * sms;
-      const char* pe = getenv("DPX_PAIRS");                   // 1 selects the plane-pair engine where it applies
-      pairs_enabled_ = pe && pe[0] == '1';               // opt-in until its row kernel is software-pipelined too
+      const char* te = getenv("DPX_COL_TMA");                 // 1 selects the persistent TMA column kernel
+      col_tma_sms_ = (te && te[0] == '1') ? sms : 0;          // opt-in: measured slower than 3 co-resident k_col CTAs (profiles/README.md)
+      const char* pe = getenv("DPX_PAIRS");                   // 0 disables the plane-pair engine (for A/B runs)
+      pairs_enabled_ = !(pe && pe[0] == '0');
     }
     rc = upload_twiddles(g.H, &tw_h_);
     if (!rc) rc = upload_twiddles(g.W, &tw_w_);
@@ -139,6 +157,7 @@ class FusedEngine final : public FftEngine {
                   float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
     CudaBackend be{s};
     be.n_persist = persist_ctas_;
+    be.n_sm = col_tma_sms_;
     Driver<CudaBackend> drv(be);
     const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g.B, dq_batch_, rho_stride, psi);
     if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = true; packed_pairs_ = pairs; }
@@ -178,10 +197,11 @@ class FusedEngine final : public FftEngine {
   size_t dqp_cap_ = 0, bytes_ = 0;
   int dq_batch_ = 1;
   int persist_ctas_ = 0;
+  int col_tma_sms_ = 0;
   const float2* fb_std_ = nullptr;
   const float* dq_std_ = nullptr;
   bool fb_dirty_ = true, dq_dirty_ = true, dq_set_ = false;
-  bool packed_pairs_ = false, pairs_enabled_ = false;
+  bool packed_pairs_ = false, pairs_enabled_ = true;
 };
 
 }  // namespace

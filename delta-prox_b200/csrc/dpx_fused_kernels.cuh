@@ -103,6 +103,54 @@ DPX_HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 DPX_HD void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
+// ---- bulk asynchronous copies (TMA engine, non-tensor form) + transaction barriers ---------------------------------------
+// cp.async.bulk moves whole 16-byte-aligned runs global<->shared without occupying registers, LSU issue slots or the L1
+// data stage; completion of loads is signalled on an mbarrier (expected-bytes transaction count), stores are tracked per
+// thread in bulk groups.  SASS: UBLKCP / SYNCS.  Under DPX_EMU they are plain memcpy calls between CTA barriers.
+#ifdef DPX_EMU
+typedef unsigned long long mbar_t;
+DPX_HD void mbar_init(mbar_t*, int) {}
+DPX_HD void mbar_fence_init() {}
+DPX_HD void mbar_expect_tx(mbar_t*, unsigned) {}
+DPX_HD void mbar_wait(mbar_t*, unsigned) { __syncthreads(); }
+DPX_HD void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t*) { memcpy(dst, src, bytes); }
+DPX_HD void bulk_store(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+DPX_HD void bulk_commit() {}
+DPX_HD void bulk_wait_read_all() {}
+DPX_HD void bulk_wait_all() {}
+DPX_HD void fence_async_smem() {}
+#else
+typedef unsigned long long mbar_t;
+DPX_HD unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DPX_HD void mbar_init(mbar_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+DPX_HD void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DPX_HD void mbar_expect_tx(mbar_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+DPX_HD void mbar_wait(mbar_t* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+DPX_HD void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+DPX_HD void bulk_store(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+DPX_HD void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DPX_HD void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DPX_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DPX_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 template <class TW>
 struct RowSmem {
   // tile (padded, pairs interleaved) + twiddle records re-laid out for conflict-free 128-bit shared loads:
@@ -626,6 +674,131 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+//  Persistent, TMA-pipelined column kernel.  One CTA per SM loops over column tiles with THREE tile buffers in shared
+//  memory: while tile i is transformed in place, tile i+1 / i+2 stream in through cp.async.bulk (256-byte runs of 8 rows
+//  x CG columns land directly at their padded positions, so the FFT passes stay bank-conflict free) and tile i-1 streams
+//  out, so ~128 KB per SM are in flight at all times and no global load/store of S goes through registers or the LSU.
+//  Same arithmetic as k_col (bit-identical results).  H in {1024, 2048}: three padded tiles must fit 227 KB.
+// ------------------------------------------------------------------------------------------------
+template <class TH>
+struct ColTmaCfg {
+  static constexpr int NT = TH::N >= 2048 ? 512 : 256;                      // threads per CTA
+  static constexpr int NBUF = 3;
+  static constexpr int NCHUNK = TH::N / 8;                                  // 8 rows x CG columns = 256 bytes per bulk copy
+  static constexpr unsigned CHUNK_BYTES = 8 * CG * sizeof(float2);
+  static constexpr unsigned TILE_BYTES = TH::N * CG * sizeof(float2);
+  static constexpr size_t BYTES = (size_t)NBUF * TH::SMEM_FLOAT2 * sizeof(float2) + NBUF * sizeof(mbar_t);
+  static_assert(NCHUNK <= NT, "one bulk copy per thread");
+};
+
+template <class TH>
+__global__ void __launch_bounds__(ColTmaCfg<TH>::NT, TH::N >= 2048 ? 1 : 2) k_col_tma(ColParams P, int n_tiles, int nb) {
+  using Cfg = ColTmaCfg<TH>;
+  constexpr int H = TH::N, RC = TH::RC, NT = Cfg::NT, NBUF = Cfg::NBUF;
+  DPX_DYN_SMEM(float2, sm);
+  mbar_t* full = reinterpret_cast<mbar_t*>(sm + (size_t)NBUF * TH::SMEM_FLOAT2);
+  const int tid = threadIdx.x;
+  const int NG = P.groups;
+  const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
+  const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
+  // tile t -> (sample/pair bx, group g, channel ch): problems adjacent so that the shared diagonal hits in L2
+  auto plane_of = [&](int t, int& g) { const int bx = t % nb; g = (t / nb) % NG; return bx * P.C + t / (nb * NG); };
+  auto tile_ptr = [&](int t) { int g; const int p = plane_of(t, g); return P.S + ((size_t)p * NG + g) * H * CG; };
+  auto issue_load = [&](int t, int k) {                                     // tid < NCHUNK; expect_tx already registered
+    bulk_load(sm + (size_t)k * TH::SMEM_FLOAT2 + TH::pn(8 * tid) * CG, tile_ptr(t) + (size_t)tid * 8 * CG, Cfg::CHUNK_BYTES, full + k);
+  };
+
+  if (tid == 0) {
+    for (int k = 0; k < NBUF; ++k) mbar_init(full + k, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0) {
+    if (n_my > 0) mbar_expect_tx(full + 0, Cfg::TILE_BYTES);
+    if (n_my > 1) mbar_expect_tx(full + 1, Cfg::TILE_BYTES);
+  }
+  __syncthreads();
+  if (tid < Cfg::NCHUNK) {
+    if (n_my > 0) issue_load(blockIdx.x, 0);
+    if (n_my > 1) issue_load(blockIdx.x + gridDim.x, 1);
+  }
+
+  for (int i = 0; i < n_my; ++i) {
+    const int k = i % NBUF;
+    const int tile = blockIdx.x + i * gridDim.x;
+    float2* buf = sm + (size_t)k * TH::SMEM_FLOAT2;
+    int g;
+    const int p = plane_of(tile, g);
+    const int b = (tile % nb) * P.bmul;
+    if (i + 1 < n_my) {            // constants of the next tile -> L2 (they are read in the middle of its processing)
+      int gn;
+      const int pn_ = plane_of(tile + gridDim.x, gn);
+      const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)pn_ * NG + gn) * H * CG);
+      for (int o = tid * 128; o < H * CG * 8; o += NT * 128) prefetch_l2(nf + o);
+    }
+    mbar_wait(full + k, (unsigned)((i / NBUF) & 1));
+
+    fft::smem_pass<TH, TH::RA, TH::N, false, true>(buf, twA, tid, NT);
+    if (i > 0 && tid < Cfg::NCHUNK) bulk_wait_read_all();          // tile i-1 has left its buffer (the one tile i+2 will use)
+    __syncthreads();
+    if (tid == 0 && i + 2 < n_my) mbar_expect_tx(full + (i + 2) % NBUF, Cfg::TILE_BYTES);
+    fft::smem_pass<TH, TH::RB, TH::MA, false, true>(buf, twB, tid, NT);
+    __syncthreads();
+    if (i + 2 < n_my && tid < Cfg::NCHUNK) issue_load(tile + 2 * gridDim.x, (i + 2) % NBUF);
+
+    // ---- pass C, spectral solve, inverse pass C on a thread-private block of RC positions (as k_col) -----------------
+    {
+      const float rho = P.rho.p[(size_t)b * P.rho.stride + P.rho.it];
+      const int pd = P.dq_batch > 1 ? p : p % P.C;
+      const float den0 = rho * P.wid + P.eps;
+      constexpr int NTASK = CG * (H / RC);
+      for (int t = tid; t < NTASK; t += NT) {
+        const int c = t % CG, blk = t / CG;
+        const int p0 = TH::phys(blk * RC, c);
+        float2 a[RC];
+#pragma unroll
+        for (int m = 0; m < RC; ++m) a[m] = buf[p0 + TH::template delta<1>(m) * CG];
+        fft::Dft<RC, false>::run(a);
+        const float4* fb4 = reinterpret_cast<const float4*>(P.fbp) + ((size_t)p * NG + g) * (H * CG / 2) + t;
+        const float4* dq4 = reinterpret_cast<const float4*>(P.dqp) + ((size_t)pd * NG + g) * (H * CG / 4) + t;
+        float2 f[RC];
+        float d[RC];
+#pragma unroll
+        for (int m = 0; m < RC / 2; ++m) {
+          const float4 v = fb4[m * NTASK];
+          f[2 * m] = make_float2(v.x, v.y); f[2 * m + 1] = make_float2(v.z, v.w);
+        }
+#pragma unroll
+        for (int m = 0; m < RC / 4; ++m) {
+          const float4 v = dq4[m * NTASK];
+          d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
+        }
+#pragma unroll
+        for (int m = 0; m < RC; ++m) {
+          const float r = fast_div(P.inv_n, d[m] + den0);
+          a[m] = make_float2((f[m].x + rho * a[m].x + P.eps) * r, (f[m].y + rho * a[m].y + P.eps_im) * r);
+        }
+        fft::Dft<RC, true>::run(a);
+#pragma unroll
+        for (int m = 0; m < RC; ++m) buf[p0 + TH::template delta<1>(m) * CG] = a[m];
+      }
+    }
+    __syncthreads();
+    fft::smem_pass<TH, TH::RB, TH::MA, true, true>(buf, twB, tid, NT);
+    __syncthreads();
+    fft::smem_pass<TH, TH::RA, TH::N, true, true>(buf, twA, tid, NT);
+    fence_async_smem();                                            // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (tid < Cfg::NCHUNK) {
+      bulk_store(tile_ptr(tile) + (size_t)tid * 8 * CG, buf + TH::pn(8 * tid) * CG, Cfg::CHUNK_BYTES);
+      bulk_commit();
+    }
+  }
+  if (tid < Cfg::NCHUNK) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
 //  Constant packing (cold path): standard R2C layout [planes, H, W/2+1] -> k_col's record layout
 // ------------------------------------------------------------------------------------------------
 template <class TH, typename V>
@@ -778,6 +951,178 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
 #pragma unroll
     for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Persistent middle row kernel of the plane-pair engine (one psi term).  Same arithmetic as k_rowz<.., ROW_MID, true>
+//  on tiles of ZR = 2 image rows; every CTA loops over tiles and the NEXT tile's spectrum rows and dual rows are staged
+//  into shared memory with cp.async while the current tile is transformed (2 CTAs/SM: padded tile 37 KB + 32 KB + 32 KB).
+// ------------------------------------------------------------------------------------------------
+constexpr int ZR = 2;
+template <class TW>
+struct RowZPersistSmem {
+  static constexpr int G = TW::N / CG;
+  static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
+  static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
+  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float);
+};
+
+template <class TW>
+DPX_HD void rowz_tile(const RowParams& P, int tile, int& pp, int& h0, int& pA, int& pB) {
+  const int tpp = P.H / ZR;
+  pp = tile / tpp; h0 = (tile % tpp) * ZR;
+  const int bq = pp / P.C;
+  pA = 2 * bq * P.C + (pp - bq * P.C); pB = pA + P.C;
+}
+template <class TW>
+DPX_HD void rowz_stage_S(const RowParams& P, int tile, float2* stS, int tid) {
+  constexpr int G = TW::N / CG, SEG16 = ZR * CG * 8 / 16;        // 16-byte chunks per 64-byte segment
+  int pp, h0, pA, pB;
+  rowz_tile<TW>(P, tile, pp, h0, pA, pB);
+  for (int t = tid; t < G * SEG16; t += kThreads) {
+    const int g = t / SEG16, ch = t % SEG16;
+    cp_async16(reinterpret_cast<char*>(stS + g * (ZR * CG)) + ch * 16,
+               reinterpret_cast<const char*>(P.S + (((size_t)pp * G + g) * P.H + h0) * CG) + ch * 16);
+  }
+}
+template <class TW>
+DPX_HD void rowz_stage_u(const RowParams& P, int tile, float* stU, int tid) {
+  constexpr int W = TW::N, RSU = RowZPersistSmem<TW>::RSU;
+  int pp, h0, pA, pB;
+  rowz_tile<TW>(P, tile, pp, h0, pA, pB);
+  const float* u = P.psi.t[0].u;
+  for (int t = tid; t < 2 * ZR * (W / 4); t += kThreads) {
+    const int row = t / (W / 4), i4 = (t % (W / 4)) * 4;         // row = plane * ZR + r
+    const int pl = row / ZR, r = row % ZR;
+    cp_async16(stU + row * RSU + i4, u + ((size_t)(pl ? pB : pA) * P.H + h0 + r) * W + i4);
+  }
+}
+
+template <class TW>
+__global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, int n_tiles) {
+  static_assert(TW::COLS == ZR, "tile holds one complex sequence per image row");
+  constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
+  constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
+  constexpr int NT1 = NSEQ * (W / RC);
+  static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass fall into the same column of different groups");
+  DPX_DYN_SMEM(float2, sm);
+  float2* stS = sm + TW::SMEM_FLOAT2;
+  float* stU = reinterpret_cast<float*>(stS + RowZPersistSmem<TW>::STS_F2);
+  const int tid = threadIdx.x;
+  const int H = P.H;
+  const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
+  const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
+  const PsiTerm& tm = P.psi.t[0];
+  const int hqs = P.hqs;
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) {
+    rowz_stage_S<TW>(P, tile, stS, tid);
+    if (!hqs) rowz_stage_u<TW>(P, tile, stU, tid);
+  }
+  cp_async_commit();
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    int pp, h0, pA, pB;
+    rowz_tile<TW>(P, tile, pp, h0, pA, pB);
+    const int b = 2 * (pp / P.C);
+    const int next = tile + gridDim.x;
+    cp_async_wait_all();
+    __syncthreads();                                   // staged inputs of `tile` are visible; tile buffer is free
+
+    // ---- 1. inverse pass C out of the staged spectrum rows (column storage order: see k_rowz) ----------------------------
+    for (int t = tid; t < NT1; t += kThreads) {
+      const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
+      const int blk = gq * CG + cc;
+      const float2* src = stS + gq * (ZR * CG) + r * CG + cc;
+      float2 a[RC];
+#pragma unroll
+      for (int m = 0; m < RC; ++m) a[m] = src[m * (W / RC / CG) * (ZR * CG)];
+      fft::Dft<RC, true>::run(a);
+      const int p0 = TW::phys(blk * RC, r);
+#pragma unroll
+      for (int m = 0; m < RC; ++m) sm[p0 + TW::template delta<1>(m) * NSEQ] = a[m];
+    }
+    __syncthreads();                                   // stS consumed
+    if (next < n_tiles) rowz_stage_S<TW>(P, next, stS, tid);
+    cp_async_commit();
+    fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
+    __syncthreads();
+
+    // ---- 2. last inverse pass -> (x_A, x_B);  prox / dual / next rhs in registers (dual rows from the stage);  first forward pass
+    {
+      const float scale = tm.scale;
+      const float lam = tm.lam[(size_t)b * tm.lam_stride + P.it];
+      const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
+      float* __restrict__ up = tm.u;
+      const float* __restrict__ op = tm.off;
+      const bool simple = scale == 1.f && tm.beta == 1.f && op == nullptr &&
+                          (ps.kind == DPX_PROX_NONNEG || ps.kind == DPX_PROX_L1 || ps.kind == DPX_PROX_L2SQ || ps.kind == DPX_PROX_BOX);
+      const float lam_eff = lam * tm.alpha;
+      for (int t = tid; t < NSEQ * MA; t += kThreads) {
+        const int c = t % NSEQ, j = t / NSEQ;
+        const int p0 = TW::phys(j, c);
+        float2 a[RA], w[RA];
+#pragma unroll
+        for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NSEQ];
+        fft::load_twiddles<RA, MA>(twA, j, w);
+#pragma unroll
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
+        fft::Dft<RA, true>::run(a);
+        const size_t ea = ((size_t)pA * H + h0 + c) * W + j, eb = ((size_t)pB * H + h0 + c) * W + j;
+        const float* ua_s = stU + c * RSU + j;
+        const float* ub_s = stU + (ZR + c) * RSU + j;
+        if (simple) {
+          switch (ps.kind) {
+            case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            case DPX_PROX_L2SQ: mid_simple<DPX_PROX_L2SQ, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            default: mid_simple<DPX_PROX_BOX, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < RA; ++m) {
+            const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
+            float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
+            if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
+            const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
+            const float ua = wa - va, ub = wb - vb;
+            if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
+            a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
+          }
+        }
+        fft::Dft<RA, false>::run(a);
+#ifndef DPX_EMU
+        asm volatile("" ::: "memory");
+#endif
+        fft::load_twiddles<RA, MA>(twA, j, w);
+#pragma unroll
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
+#pragma unroll
+        for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
+      }
+    }
+    __syncthreads();                                   // stU consumed, tile holds pass-A output
+    if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, next, stU, tid);
+    cp_async_commit();
+
+    // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
+    fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
+    __syncthreads();
+    for (int t = tid; t < NT1; t += kThreads) {
+      const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
+      const int blk = gq * CG + cc;
+      const int p0 = TW::phys(blk * RC, r);
+      float2 a[RC];
+#pragma unroll
+      for (int m = 0; m < RC; ++m) a[m] = sm[p0 + TW::template delta<1>(m) * NSEQ];
+      fft::Dft<RC, false>::run(a);
+      float2* dst = P.S + (((size_t)pp * G + gq) * H + h0 + r) * CG + cc;
+#pragma unroll
+      for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
+    }
+  }
+  cp_async_wait_all();
 }
 
 // Constant packing for the pair engine (cold path).  Standard R2C half spectra -> full-spectrum records of pair pp in

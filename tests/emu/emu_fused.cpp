@@ -23,6 +23,12 @@ struct EmuBackend {
   void row_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_row_mid_persist<TW>(p, n_tiles); });
   }
+  int sms = 3;                                        // emulated SM count of the persistent TMA column kernel
+  int sm_count() const { return sms; }
+  template <class TH>
+  void col_tma(dim3 grid, size_t smem, ColParams p, int n_tiles, int nb) {
+    emu::launch(grid, dim3(ColTmaCfg<TH>::NT), smem, [=]() { k_col_tma<TH>(p, n_tiles, nb); });
+  }
   template <class TH>
   void col(dim3 grid, size_t smem, ColParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_col<TH>(p); });
@@ -30,6 +36,10 @@ struct EmuBackend {
   template <class TW, int MODE, bool SINGLE>
   void rowz(dim3 grid, size_t smem, RowParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz<TW, MODE, SINGLE>(p); });
+  }
+  template <class TW>
+  void rowz_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz_mid_persist<TW>(p, n_tiles); });
   }
   template <class TH, class TW>
   void packz_fb(const float2* src, float2* dst, int pairs, int C, int H, int W) {

@@ -86,7 +86,7 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
         assert rel(u[0], want[2][0].numpy()) < 5e-5 and rel(u[1], want[2][1].numpy()) < 5e-5
 
 
-@pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs")])
+@pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm")])   # H = 1024: k_col_tma
 def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     """One psi term: the in-place register path of k_row (template SINGLE)."""
     g = torch.Generator().manual_seed(H * 3 + W)
@@ -118,3 +118,24 @@ def test_pair_engine_is_selected_and_matches_plane_engine(emu, monkeypatch):
     base = run_emu(emu, b, psf, [1, 0], [1.0, 1.0], [0.5, 1.0], 0.7, [0.05, 0.02], T, False)
     assert run_emu.last_engine == "planes"
     assert rel(got[0], base[0]) < 2e-6 and rel(got[2][0], base[2][0]) < 2e-5 and rel(got[1][1], base[1][1]) < 2e-5
+
+
+def test_tma_column_kernel_with_plane_pairs(emu, monkeypatch):
+    """H = 1024 selects the persistent bulk-copy (TMA) column kernel; B = 2 the plane-pair engine on top of it.  The emulated
+    grid has 3 'SMs' x 2 CTAs for 34 tiles, so every CTA walks its 3-buffer ring several times."""
+    g = torch.Generator().manual_seed(23)
+    B, Cc, H, W, T = 2, 1, 1024, 64, 3
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(5, 1.5)
+    b = (orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    f = orc.Term("nonneg")
+    data = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=torch.from_numpy(b))
+    want = orc.Solver([data, f], "admm").solve(torch.from_numpy(b), rhos=1.0, lams=0.02, max_iter=T, return_full_states=True)
+    for no_pairs in ("", "1"):
+        if no_pairs:
+            monkeypatch.setenv("DPX_EMU_NO_PAIRS", "1")
+        else:
+            monkeypatch.delenv("DPX_EMU_NO_PAIRS", raising=False)
+        x, v, u = run_emu(emu, b, psf, [0], [1.0], [1.0], 1.0, [0.02], T, False)
+        assert run_emu.last_engine == ("planes" if no_pairs else "pairs")
+        assert rel(x, want[0].numpy()) < 5e-6 and rel(u[0], want[2][0].numpy()) < 5e-5
