@@ -108,6 +108,7 @@ DPX_HD void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"
 // data stage; completion of loads is signalled on an mbarrier (expected-bytes transaction count), stores are tracked per
 // thread in bulk groups.  SASS: UBLKCP / SYNCS.  Under DPX_EMU they are plain memcpy calls between CTA barriers.
 #ifdef DPX_EMU
+#define DPX_MBAR_ALL_WAIT 1
 typedef unsigned long long mbar_t;
 DPX_HD void mbar_init(mbar_t*, int) {}
 DPX_HD void mbar_fence_init() {}
@@ -120,6 +121,7 @@ DPX_HD void bulk_wait_read_all() {}
 DPX_HD void bulk_wait_all() {}
 DPX_HD void fence_async_smem() {}
 #else
+#define DPX_MBAR_ALL_WAIT 0
 typedef unsigned long long mbar_t;
 DPX_HD unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 DPX_HD void mbar_init(mbar_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
@@ -956,7 +958,8 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
 // ------------------------------------------------------------------------------------------------
 //  Persistent middle row kernel of the plane-pair engine (one psi term).  Same arithmetic as k_rowz<.., ROW_MID, true>
 //  on tiles of ZR = 2 image rows; every CTA loops over tiles and the NEXT tile's spectrum rows and dual rows are staged
-//  into shared memory with cp.async while the current tile is transformed (2 CTAs/SM: padded tile 37 KB + 32 KB + 32 KB).
+//  into shared memory by the TMA engine (cp.async.bulk + transaction barriers: no registers, no LSU issue slots) while the
+//  current tile is transformed (2 CTAs/SM: padded tile 37 KB + 32 KB + 32 KB).
 // ------------------------------------------------------------------------------------------------
 constexpr int ZR = 2;
 template <class TW>
@@ -964,37 +967,36 @@ struct RowZPersistSmem {
   static constexpr int G = TW::N / CG;
   static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
   static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
-  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float);
+  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t);
 };
 
-template <class TW>
-DPX_HD void rowz_tile(const RowParams& P, int tile, int& pp, int& h0, int& pA, int& pB) {
-  const int tpp = P.H / ZR;
-  pp = tile / tpp; h0 = (tile % tpp) * ZR;
-  const int bq = pp / P.C;
-  pA = 2 * bq * P.C + (pp - bq * P.C); pB = pA + P.C;
+struct RowZTile { int pp, h0, pA, pB; };
+DPX_HD RowZTile rowz_tile(const RowParams& P, int tile, int tiles_per_pair) {
+  RowZTile t;
+  t.pp = tile / tiles_per_pair; t.h0 = (tile - t.pp * tiles_per_pair) * ZR;
+  const int bq = t.pp / P.C;
+  t.pA = 2 * bq * P.C + (t.pp - bq * P.C); t.pB = t.pA + P.C;
+  return t;
 }
+// staging of a tile's inputs: G spectrum segments of 64 bytes (rows h0, h0+1 of one column group; cp.async) and the
+// 2 x ZR dual rows of 4 W bytes (bulk copies by the TMA engine, completion counted on a transaction barrier)
 template <class TW>
-DPX_HD void rowz_stage_S(const RowParams& P, int tile, float2* stS, int tid) {
-  constexpr int G = TW::N / CG, SEG16 = ZR * CG * 8 / 16;        // 16-byte chunks per 64-byte segment
-  int pp, h0, pA, pB;
-  rowz_tile<TW>(P, tile, pp, h0, pA, pB);
-  for (int t = tid; t < G * SEG16; t += kThreads) {
-    const int g = t / SEG16, ch = t % SEG16;
-    cp_async16(reinterpret_cast<char*>(stS + g * (ZR * CG)) + ch * 16,
-               reinterpret_cast<const char*>(P.S + (((size_t)pp * G + g) * P.H + h0) * CG) + ch * 16);
+DPX_HD void rowz_stage_S(const RowParams& P, const RowZTile& t, float2* stS, int tid) {
+  // 64-byte segments: too small for the TMA engine to be efficient (measured: 512 bulk copies per tile were slower than
+  // LDGSTS), so the spectrum rows are staged with 16-byte cp.async; the 8 KB dual rows below go through the TMA engine
+  constexpr int G = TW::N / CG, SEG16 = ZR * CG * 8 / 16;
+  const char* base = reinterpret_cast<const char*>(P.S + ((size_t)t.pp * G * P.H + t.h0) * CG);
+  for (int i = tid; i < G * SEG16; i += kThreads) {
+    const int g = i / SEG16, ch = i % SEG16;
+    cp_async16(reinterpret_cast<char*>(stS + g * (ZR * CG)) + ch * 16, base + (size_t)g * P.H * CG * sizeof(float2) + ch * 16);
   }
 }
 template <class TW>
-DPX_HD void rowz_stage_u(const RowParams& P, int tile, float* stU, int tid) {
+DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar_t* bar, int tid) {
   constexpr int W = TW::N, RSU = RowZPersistSmem<TW>::RSU;
-  int pp, h0, pA, pB;
-  rowz_tile<TW>(P, tile, pp, h0, pA, pB);
-  const float* u = P.psi.t[0].u;
-  for (int t = tid; t < 2 * ZR * (W / 4); t += kThreads) {
-    const int row = t / (W / 4), i4 = (t % (W / 4)) * 4;         // row = plane * ZR + r
-    const int pl = row / ZR, r = row % ZR;
-    cp_async16(stU + row * RSU + i4, u + ((size_t)(pl ? pB : pA) * P.H + h0 + r) * W + i4);
+  if (tid < 2 * ZR) {
+    const int pl = tid / ZR, r = tid % ZR;                         // row = plane * ZR + r
+    bulk_load(stU + tid * RSU, P.psi.t[0].u + ((size_t)(pl ? t.pB : t.pA) * P.H + t.h0 + r) * W, W * sizeof(float), bar);
   }
 }
 
@@ -1004,31 +1006,45 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
   constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
   constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
   constexpr int NT1 = NSEQ * (W / RC);
+  constexpr unsigned U_BYTES = 2 * ZR * W * sizeof(float);
   static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass fall into the same column of different groups");
   DPX_DYN_SMEM(float2, sm);
   float2* stS = sm + TW::SMEM_FLOAT2;
   float* stU = reinterpret_cast<float*>(stS + RowZPersistSmem<TW>::STS_F2);
+  mbar_t* bars = reinterpret_cast<mbar_t*>(stU + 2 * ZR * RSU);    // [1]: dual stage
   const int tid = threadIdx.x;
-  const int H = P.H;
+  const int H = P.H, tpp = H / ZR;
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
   const PsiTerm& tm = P.psi.t[0];
   const int hqs = P.hqs;
 
+  if (tid == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   int tile = blockIdx.x;
+  RowZTile cur = rowz_tile(P, tile < n_tiles ? tile : 0, tpp);
   if (tile < n_tiles) {
-    rowz_stage_S<TW>(P, tile, stS, tid);
-    if (!hqs) rowz_stage_u<TW>(P, tile, stU, tid);
+    if (tid == 0 && !hqs) mbar_expect_tx(bars + 1, U_BYTES);
+    __syncthreads();
+    rowz_stage_S<TW>(P, cur, stS, tid);
+    if (!hqs) rowz_stage_u<TW>(P, cur, stU, bars + 1, tid);
   }
   cp_async_commit();
 
-  for (; tile < n_tiles; tile += gridDim.x) {
-    int pp, h0, pA, pB;
-    rowz_tile<TW>(P, tile, pp, h0, pA, pB);
+  unsigned phase = 0;
+  for (; tile < n_tiles; tile += gridDim.x, phase ^= 1u) {
+    const int pp = cur.pp, h0 = cur.h0, pA = cur.pA, pB = cur.pB;
     const int b = 2 * (pp / P.C);
     const int next = tile + gridDim.x;
+    const RowZTile nxt = rowz_tile(P, next < n_tiles ? next : tile, tpp);
     cp_async_wait_all();
-    __syncthreads();                                   // staged inputs of `tile` are visible; tile buffer is free
+    if (DPX_MBAR_ALL_WAIT || tid == 0) { if (!hqs) mbar_wait(bars + 1, phase); }   // one poller; the barrier below publishes it
+    __syncthreads();                                   // staged inputs are visible; the tile buffer is free
+    if (tid == 0 && next < n_tiles && !hqs) mbar_expect_tx(bars + 1, U_BYTES);   // copies are issued behind later barriers
 
     // ---- 1. inverse pass C out of the staged spectrum rows (column storage order: see k_rowz) ----------------------------
     for (int t = tid; t < NT1; t += kThreads) {
@@ -1044,7 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
       for (int m = 0; m < RC; ++m) sm[p0 + TW::template delta<1>(m) * NSEQ] = a[m];
     }
     __syncthreads();                                   // stS consumed
-    if (next < n_tiles) rowz_stage_S<TW>(P, next, stS, tid);
+    if (next < n_tiles) rowz_stage_S<TW>(P, nxt, stS, tid);
     cp_async_commit();
     fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
     __syncthreads();
@@ -1103,8 +1119,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
       }
     }
     __syncthreads();                                   // stU consumed, tile holds pass-A output
-    if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, next, stU, tid);
-    cp_async_commit();
+    if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, nxt, stU, bars + 1, tid);
 
     // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
     fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
@@ -1121,6 +1136,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
 #pragma unroll
       for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
     }
+    cur = nxt;
   }
   cp_async_wait_all();
 }
