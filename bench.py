@@ -12,8 +12,9 @@ call).  `value` = problem-iterations / second over all GPUs with every input alr
 the constant hoisting (K^T b, its FFT), state init, T iterations and the D2H copy of x are inside the timing.
 
 N > 1: one process per GPU under torchrun, independent problem shards, no data-path collective ("weak").
-`--impl reference` times the CPU oracle port (oracle/dprox_oracle.py, the reference's op sequence) on the
-host cores of this box on a bounded sample of the same workload.
+`--impl reference` times the reference's own CPU implementation on the host cores of this box on a bounded sample
+of the same workload: the UNMODIFIED reference package when it is installed under baseline/_ref (`pip install --target
+baseline/_ref /root/reference`, git-ignored), else the oracle port of its op sequence (oracle/dprox_oracle.py).
 """
 import argparse
 import json
@@ -127,21 +128,48 @@ class ClockSampler:
 #  CPU arm: the oracle port timed on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def cpu_port_rate(H, W, iters, threads, seed=0):
-    """problem-iterations/s of the oracle (reference op sequence, torch CPU) on ONE [3,H,W] problem."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")        # `pip install --target baseline/_ref /root/reference` (git-ignored, ships to the box)
+
+
+def _reference_module():
+    """The UNMODIFIED reference package if it was installed next to the repo, else None."""
+    if not os.path.isdir(os.path.join(REF_DIR, "dprox")):
+        return None
+    os.environ["DPROX_REFERENCE_ROOT"] = REF_DIR
+    try:
+        import refshim                                   # stubs for import-time-only third-party modules (oracle/refshim.py)
+        refshim.REFERENCE_ROOT = REF_DIR
+        return refshim.import_reference()
+    except Exception as e:                               # noqa: BLE001
+        print(f"[bench] reference import failed ({type(e).__name__}: {e}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_rate(H, W, iters, threads, seed=0):
+    """problem-iterations/s of the reference path on the host cores, ONE [3,H,W] problem: the reference's own
+    `compile(...).solve(...)` (kind 'reference') when baseline/_ref holds it, else the oracle port of its op sequence."""
     import dprox_oracle as orc
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(seed)
     img = torch.rand(1, 3, H, W, generator=g) - 0.3
     psf = orc.point_spread_function(15, 5)
-    conv = orc.Conv(psf, orc.Identity())
-    b = conv.fwd(img) + 0.01 * torch.randn(1, 3, H, W, generator=g)
-    solver = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")], "admm")
-    solver.solve(b, rhos=1.0, lams=0.02, max_iter=2)                 # warm-up (FFT plans, OTF cache)
-    t0 = time.perf_counter()
-    solver.solve(b, rhos=1.0, lams=0.02, max_iter=iters)
-    dt = time.perf_counter() - t0
-    return iters / dt, dt
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(1, 3, H, W, generator=g)
+    ref = _reference_module()
+    if ref is not None:
+        x = ref.Variable()
+        solver = ref.compile(ref.sum_squares(ref.conv(x, psf) - b) + ref.nonneg(x), method="admm", device="cpu")
+        run = lambda n: solver.solve(x0=b, rhos=1.0, lams=0.02, max_iter=n)
+        kind = "reference"
+    else:
+        solver = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")], "admm")
+        run = lambda n: solver.solve(b, rhos=1.0, lams=0.02, max_iter=n)
+        kind = "port"
+    with torch.no_grad():
+        run(2)                                           # warm-up (FFT plans, OTF cache)
+        t0 = time.perf_counter()
+        run(iters)
+        dt = time.perf_counter() - t0
+    return iters / dt, dt, kind
 
 
 def run_reference(args):
@@ -152,21 +180,23 @@ def run_reference(args):
     H = W = args.size
     iters = args.ref_iters
     rates = []
+    kind = "port"
     for _ in range(args.warmup):
-        cpu_port_rate(H, W, 1, threads)
+        cpu_rate(H, W, 1, threads)
     t_all = 0.0
     for _ in range(args.steps):
-        r, dt = cpu_port_rate(H, W, iters, threads)
+        r, dt, kind = cpu_rate(H, W, iters, threads)
         rates.append(r)
         t_all += dt
     value = float(np.mean(rates))
-    sample = f"1 problem [3,{H},{W}] x {iters} ADMM iterations per step, {args.steps} steps, torch-CPU {threads} threads"
+    what = "the unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port of the reference's op sequence"
+    sample = f"1 problem [3,{H},{W}] x {iters} ADMM iterations per step, {args.steps} steps, {what}, torch-CPU {threads} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -324,9 +354,11 @@ def run_native(args):
     cpu = None
     if not args.skip_cpu:
         threads = os.cpu_count() or 1
-        r, dt = cpu_port_rate(H, W, args.ref_iters, threads)
-        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"1 problem [3,{H},{W}] x {args.ref_iters} ADMM iterations ({dt:.1f} s), oracle port, torch-CPU"}
+        n_cpu = max(args.ref_iters, 60)                       # ~10-20 s of CPU work
+        r, dt, kind = cpu_rate(H, W, n_cpu, threads)
+        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"1 problem [3,{H},{W}] x {n_cpu} ADMM iterations ({dt:.1f} s), "
+                         f"{'unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port'}, torch-CPU"}
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -352,7 +384,7 @@ def main():
     ap.add_argument("--iters", type=int, default=50, help="ADMM iterations per step")
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--fft-backend", type=int, default=0)
-    ap.add_argument("--ref-iters", type=int, default=6, help="CPU-arm iterations per sample")
+    ap.add_argument("--ref-iters", type=int, default=12, help="CPU-arm iterations per step (reference arm)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="experiments: resident-input number only (not a bench line)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")

@@ -604,8 +604,8 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     const int p0 = TH::phys(j, c);
     float2 a[RA], w[RA];
 #pragma unroll
-    for (int m = 0; m < RA; ++m) a[m] = tile[(size_t)(j + m * MA) * CG + c];
-    fft::Dft<RA, false>::run(a);
+    for (int m = 0; m < RA; ++m) a[m] = ld_stream2(tile + (size_t)(j + m * MA) * CG + c);   // streamed: the small L1 next to
+    fft::Dft<RA, false>::run(a);                                                              // 217 KB of tiles is kept for twiddles
     fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
     for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
@@ -636,12 +636,12 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     float d[RC];
 #pragma unroll
     for (int m = 0; m < RC / 2; ++m) {
-      const float4 v = fb4[m * NT];
+      const float4 v = ld_stream4(fb4 + m * NT);
       f[2 * m] = make_float2(v.x, v.y); f[2 * m + 1] = make_float2(v.z, v.w);
     }
 #pragma unroll
     for (int m = 0; m < RC / 4; ++m) {
-      const float4 v = dq4[m * NT];
+      const float4 v = ld_stream4(dq4 + m * NT);
       d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
     }
 #pragma unroll

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B helper (run under gpurun): fused-engine parity tests, then the resident-input number of the headline workload
 mkdir -p gpurun_out
-for v in "DPX_PAIRS=0" "DPX_PAIRS=1"; do
+for v in "DPX_PAIRS=1"; do
 env $v timeout 300 python -m pytest tests/test_parity_gpu.py -x -q -k "fused or fft_backend or engine or headline" 2>&1 | tail -2
 echo "== $v" | tee -a gpurun_out/exp_ab.log
 env $v timeout 200 python bench.py --batch 8 --steps 3 --warmup 3 --skip-cpu --skip-e2e 2>&1 | tail -1 | tee -a gpurun_out/exp_ab.log
