@@ -65,7 +65,7 @@ def workload_config(args, world):
     """Identical for both arms: the reference arm runs a bounded SAMPLE of this workload (see cpu_baseline.sample)."""
     B, H, W, T = args.batch, args.size, args.size, args.iters
     N = B * 3 * H * W
-    return {"workload": f"admm deconv+nonneg, {B} problems/GPU [3,{H},{W}] fp32, psf gaussian 15/5, rho=1, lam=0.02, "
+    return {"workload": f"{args.method} deconv+nonneg, {B} problems/GPU [3,{H},{W}] fp32, psf gaussian 15/5, rho=1, lam=0.02, "
                         f"{T} iterations per step", "batch_per_gpu": B, "iters_per_step": T,
             "l2_policy": f"state arrays are {N * 4 / 2**20:.0f} MiB each (> 126 MB L2) and every iteration streams all of them",
             "fft_backend": {0: "auto", 1: "cufft", 2: "fused"}[args.fft_backend],
@@ -229,7 +229,7 @@ def run_native(args):
     x = dp.Variable()
     y = dp.Placeholder()
     data_op = dp.conv(x, psf)
-    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method="admm", device=dev,
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method=args.method, device=dev,
                         fft_backend=args.fft_backend)
     img, noise = make_measurements(B, C, H, W, seed=1234 + rank, device=dev)
     b_dev = data_op.to(dev).forward(img)
@@ -281,7 +281,8 @@ def run_native(args):
         if rank == 0:
             it_ms = ms_max / (T * args.steps)
             print(json.dumps({"experiment": True, "value": value, "ms_per_iteration": it_ms, "gpu_launches": int(launches),
-                              "frac": ALG_BYTES_PER_ELEM * N / (it_ms * 1e-3) / 1e9 / load_peaks()[0], "clocks": clk.summary()}))
+                              "frac": (16.0 if args.method == "hqs" else ALG_BYTES_PER_ELEM) * N / (it_ms * 1e-3) / 1e9 / load_peaks()[0],
+                              "clocks": clk.summary()}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -295,7 +296,7 @@ def run_native(args):
     chunks = []
     for c in range(n_chunks):
         xc, yc = dp.Variable(), dp.Placeholder()
-        sc = solver if n_chunks == 1 else dp.compile(dp.sum_squares(dp.conv(xc, psf) - yc) + dp.nonneg(xc), method="admm",
+        sc = solver if n_chunks == 1 else dp.compile(dp.sum_squares(dp.conv(xc, psf) - yc) + dp.nonneg(xc), method=args.method,
                                                      device=dev, fft_backend=args.fft_backend)
         chunks.append((sc, y if n_chunks == 1 else yc, b_host[c * Bc:(c + 1) * Bc], out_host[c * Bc:(c + 1) * Bc],
                        torch.cuda.Stream(device=dev)))
@@ -338,10 +339,11 @@ def run_native(args):
     # ---- roofline of the fused iteration + CPU baseline (rank 0) ----------------------------------------
     peak, peak_src = load_peaks()
     it_ms = ms_max / (T * args.steps)                      # average duration of one iteration of the whole batch
-    achieved = ALG_BYTES_PER_ELEM * N / (it_ms * 1e-3) / 1e9
+    alg_bytes = 16.0 if args.method == "hqs" else ALG_BYTES_PER_ELEM      # HQS has no dual variable
+    achieved = alg_bytes * N / (it_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src,
-            "unit_of_work": f"one ADMM iteration of {B} problems = {ALG_BYTES_PER_ELEM:.0f} B x {N} elements",
+            "unit_of_work": f"one {args.method.upper()} iteration of {B} problems = {alg_bytes:.0f} B x {N} elements",
             "avg_iteration_ms": it_ms}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
@@ -385,6 +387,7 @@ def main():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--fft-backend", type=int, default=0)
     ap.add_argument("--ref-iters", type=int, default=12, help="CPU-arm iterations per step (reference arm)")
+    ap.add_argument("--method", default="admm", choices=["admm", "hqs"], help="hqs + --size 1024 --iters 24 = BASELINE config 4 per GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="experiments: resident-input number only (not a bench line)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")

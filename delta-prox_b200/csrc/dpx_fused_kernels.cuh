@@ -623,12 +623,8 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   for (int t = tid; t < CG * (H / RC); t += kThreads) {
     const int c = t % CG, blk = t / CG;
     const int p0 = TH::phys(blk * RC, c);
-    float2 a[RC];
-#pragma unroll
-    for (int m = 0; m < RC; ++m) a[m] = sm[p0 + TH::template delta<1>(m) * CG];
-    fft::Dft<RC, false>::run(a);
-    // constants of this block: record [m/2][task] (float4 = two spectrum values) / [m/4][task] (four diagonals), so
-    // consecutive threads read consecutive 16-byte words
+    // constants of this block first (their DRAM/L2 latency overlaps the forward butterfly below): record [m/2][task]
+    // (float4 = two spectrum values) / [m/4][task] (four diagonals), so consecutive threads read consecutive 16-byte words
     constexpr int NT = CG * (H / RC);
     const float4* fb4 = reinterpret_cast<const float4*>(P.fbp) + ((size_t)p * NG + g) * (H * CG / 2) + t;
     const float4* dq4 = reinterpret_cast<const float4*>(P.dqp) + ((size_t)pd * NG + g) * (H * CG / 4) + t;
@@ -644,6 +640,10 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
       const float4 v = ld_stream4(dq4 + m * NT);
       d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
     }
+    float2 a[RC];
+#pragma unroll
+    for (int m = 0; m < RC; ++m) a[m] = sm[p0 + TH::template delta<1>(m) * CG];
+    fft::Dft<RC, false>::run(a);
 #pragma unroll
     for (int m = 0; m < RC; ++m) {
       // one reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions: the divisions were 19 % of the kernel's

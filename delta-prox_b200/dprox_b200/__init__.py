@@ -9,16 +9,17 @@ from .algo import (ADMM, ADMM_vxu, HQS, Algorithm, LinearizedADMM, PockChambolle
 from .linalg import LinearSolveConfig, linear_solve
 from .linop import (BlackBox, CompGraph, Constant, LinOp, LinOpFactory, Placeholder, Variable, adjoint, conv, conv_doe,
                     copy, eval, grad, grad2d, gram, mosaic, mul_elementwise, scale, split, sum, validate, vstack)
-from .proxfn import (Denoiser, ProxFn, box, deep_prior, ext_sum_squares, iso_tv, nonneg, norm1, norm2, sum_squares)
+from . import contrib  # noqa: F401
+from .proxfn import (Denoiser, ProxFn, box, csmri, deep_prior, ext_sum_squares, iso_tv, nonneg, norm1, norm2, sum_squares)
 from .tensors import array, tensor
 
 __version__ = "0.1.0"
 
 __all__ = [
     "ADMM", "ADMM_vxu", "HQS", "Algorithm", "LinearizedADMM", "PockChambolle", "Problem", "ProximalGradientDescent", "ResidualStop",
-    "SOLVERS", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg",
+    "SOLVERS", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg", "contrib",
     "BlackBox", "CompGraph", "Constant", "LinOp", "LinOpFactory", "Placeholder", "Variable", "adjoint", "conv", "conv_doe",
     "copy", "eval", "grad", "grad2d", "gram", "mosaic", "mul_elementwise", "scale", "split", "sum", "validate", "vstack",
-    "Denoiser", "ProxFn", "box", "deep_prior", "ext_sum_squares", "iso_tv", "nonneg", "norm1", "norm2", "sum_squares",
+    "Denoiser", "ProxFn", "box", "csmri", "deep_prior", "ext_sum_squares", "iso_tv", "nonneg", "norm1", "norm2", "sum_squares",
     "array", "tensor",
 ]

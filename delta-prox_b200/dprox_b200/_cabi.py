@@ -79,6 +79,9 @@ SIGNATURES = {
     "dpx_ffdnet_destroy": (None, [_VP]),
     "dpx_ffdnet_set_layer": (_I, [_VP, _I, _VP, _VP, _I, _I, _VP]),
     "dpx_ffdnet_forward": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),
+    "dpx_csmri_prox": (_I, [_VP, _VP, _VP, _I, _VP, _I, _F, _VP, _I, _I, _I, _I, _VP]),
+    "dpx_real_to_complex": (_I, [_VP, _VP, _SZ, _VP]),
+    "dpx_complex_real": (_I, [_VP, _VP, _SZ, _VP]),
     "dpx_solve_host": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dpx_resid_reduce": (_I, [_VP, _VP, _I, _I, _VP]),
 }

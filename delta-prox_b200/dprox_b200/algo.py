@@ -202,7 +202,7 @@ class Algorithm(nn.Module):
         """Algorithm.solve (base.py:85-126): fixed `max_iter` iterations unless an opt-in `stop` rule is given."""
         x0 = _to_tensor(x0, batch=True)
         x0, rhos, lams, max_iter = self.defaults(x0, rhos, lams, max_iter)
-        x0 = x0.to(self.device, torch.float32)
+        x0 = x0.to(self.device, torch.complex64 if x0.is_complex() else torch.float32)
         diff = self._wants_grad(x0, rhos, lams)
         if diff:
             self._diff_engine(x0).set_constants()                    # fresh tape from the measurements to K^T b
@@ -211,7 +211,8 @@ class Algorithm(nn.Module):
         return state if return_full_states else state[0]
 
     def initialize(self, x0, _diff=None, **kwargs):
-        x0 = torch.as_tensor(x0).to(self.device, torch.float32)      # already batched by solve() (base.py:20-33)
+        x0 = torch.as_tensor(x0)                                     # already batched by solve() (base.py:20-33)
+        x0 = x0.to(self.device, torch.complex64 if x0.is_complex() else torch.float32)
         diff = self._wants_grad(x0) if _diff is None else _diff
         return self.engine(x0, diff).initialize(x0)
 

@@ -29,7 +29,8 @@ from .linop import Lowered, Placeholder, Variable, evaluate, evaluate_adjoint
 from .tensors import as_bchw
 
 ALGO_IDS = {"admm": cabi.ALGO_ADMM, "ladmm": cabi.ALGO_LADMM, "admm_vxu": cabi.ALGO_ADMM_VXU, "hqs": cabi.ALGO_HQS,
-            "pgd": cabi.ALGO_PGD, "pc": -1}       # PockChambolle has no fused plan: always composed by the generic engine
+            "pgd": cabi.ALGO_PGD, "pc": -1,       # PockChambolle has no fused plan: always composed by the generic engine
+            "custom_admm": -1}                    # contrib.CustomADMM (CS-MRI, prox first, complex iterates): generic engine
 
 
 @dataclass
@@ -116,8 +117,8 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
         spec.xupdate, spec.reason = "cg", "Gram matrix is not diagonal(isable): CG fallback"
         return spec
 
-    if method == "pc":
-        spec.reason = "PockChambolle is composed node by node (closed-form x-update where diagonalisable)"
+    if method in ("pc", "custom_admm"):
+        spec.reason = f"{method} is composed node by node (closed-form x-update where diagonalisable)"
         return spec
     # can the psi side be fused?
     for t in psi:
@@ -507,7 +508,12 @@ class GenericEngine(_EngineBase):
 
     # state + one iteration ----------------------------------------------------------------------------
     def initialize(self, x0):
-        x = cabi.require_cuda_f32(x0.to(self.device, torch.float32), "x0").clone()
+        if x0.is_complex():                                  # complex iterates (CS-MRI): glue kernels work on (re, im) pairs
+            if not x0.is_cuda:
+                raise RuntimeError("dprox_b200 computes on CUDA devices only (no CPU fallback)")
+            x = x0.to(self.device, torch.complex64).contiguous().clone()
+        else:
+            x = cabi.require_cuda_f32(x0.to(self.device, torch.float32), "x0").clone()
         if self.spec.method == "pgd":
             return [x]
         v = [self._K(t.fn, x) for t in self.spec.psi]
@@ -552,6 +558,16 @@ class GenericEngine(_EngineBase):
             for i in range(len(spec.psi)):
                 u[i] = ops.lincomb(u[i], None, xs[i], None, z, _const(-1.0, z))
             return z, xs, u
+        if m == "custom_admm":  # CustomADMM._iter (contrib/csmri.py:157-171): prox first, complex z / u, real x
+            x, zs, u = state
+            z = zs[0]
+            xs = [t.fn.prox(ops.axpby(1.0, z, -1.0, u[i]), lam[t.fn]) for i, t in enumerate(spec.psi)]
+            lift = ops.to_complex if z.is_complex() else (lambda e: e)
+            b = [ops.axpby(1.0, lift(xs[i]), 1.0, u[i]) for i in range(len(spec.psi))]
+            z = self.solve_x(b, rho, z)
+            for i in range(len(spec.psi)):
+                u[i] = ops.axpby(1.0, b[i], -1.0, z)           # u + x - z
+            return xs[0], [z], u
         if m == "pc":          # PockChambolle._iter (algo/pc.py:13-36)
             x, z, xbar = state
             for i, t in enumerate(spec.psi):

@@ -202,3 +202,50 @@ def cg_direction(p, r, gamma_new, gamma_old, per_sample=True):
         cabi.check(cabi.lib().dpx_cg_direction(cabi.ptr(p), cabi.ptr(r), cabi.ptr(gamma_new), cabi.ptr(gamma_old), B,
                                                p.numel() // B, _s(p)), "dpx_cg_direction")
     return p
+
+
+def to_complex(x: torch.Tensor) -> torch.Tensor:
+    """real fp32 -> complex64 with zero imaginary part (native copy kernel); complex input is returned as is."""
+    if x.is_complex():
+        return x
+    x = cabi.require_cuda_f32(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.complex64)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_real_to_complex(cabi.ptr(x), C.c_void_p(out.data_ptr()), x.numel(), _s(x)), "dpx_real_to_complex")
+    return out
+
+
+def real_part(z: torch.Tensor) -> torch.Tensor:
+    """real part of a complex64 CUDA tensor as a contiguous fp32 tensor (pnp/prior.py:79 `v = v.real`)."""
+    if not z.is_complex():
+        return z
+    if not z.is_cuda:
+        raise RuntimeError("dprox_b200: complex tensor lives on the CPU; this backend only computes on CUDA devices")
+    z = z.to(torch.complex64).contiguous()
+    out = torch.empty(z.shape, device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        cabi.check(cabi.lib().dpx_complex_real(C.c_void_p(z.data_ptr()), cabi.ptr(out), z.numel(), _s(z)), "dpx_complex_real")
+    return out
+
+
+def csmri_prox(v: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, rho: torch.Tensor, num_psi: float) -> torch.Tensor:
+    """csmri._prox (proxfn/fast/csmri.py:14-25): masked closed-form update in centred ortho k-space, complex64 in / out."""
+    if not v.is_cuda:
+        raise RuntimeError(f"dprox_b200: v lives on {v.device}; this backend only computes on CUDA devices (no CPU fallback)")
+    v = to_complex(v).to(torch.complex64).contiguous()
+    v4 = as_bchw(v)
+    B, Cc, H, W = v4.shape
+    y = y.to(v.device, torch.complex64).expand(v4.shape).contiguous()
+    m = cabi.require_cuda_f32(mask.to(v.device, torch.float32), "mask")
+    m4 = as_bchw(m)
+    if m4.shape[0] not in (1, B) or tuple(m4.shape[1:]) != (Cc, H, W):
+        m4 = m4.expand(B, Cc, H, W).contiguous()
+    rho = cabi.require_cuda_f32(torch.as_tensor(rho, dtype=torch.float32, device=v.device).reshape(-1), "rho")
+    if rho.numel() not in (1, B):
+        raise ValueError(f"rho must have 1 or B={B} entries")
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        cabi.check(cabi.lib().dpx_csmri_prox(C.c_void_p(v.data_ptr()), C.c_void_p(y.data_ptr()), cabi.ptr(m4.contiguous()), m4.shape[0],
+                                             cabi.ptr(rho), int(rho.numel() > 1), float(num_psi), C.c_void_p(out.data_ptr()),
+                                             B, Cc, H, W, _s(v)), "dpx_csmri_prox")
+    return out

@@ -203,6 +203,22 @@ class ext_sum_squares(sum_squares):
         return self._prox(xt, rho, len(b))
 
 
+class csmri(ext_sum_squares):
+    """CS-MRI data term |M F x - y|^2 with its closed-form x-update on complex iterates (proxfn/fast/csmri.py:8-25):
+    `z = fft2(v); z[mask] = ((rho z + y) / (1 + rho n_psi))[mask]; ifft2(z)` with the centred ortho transforms of
+    utils/misc.py:164-193, as ONE native call (`dpx_csmri_prox`: cuFFT C2C + fused masked update).  `mask` / `y` may be
+    Placeholders (tests/paper/test_csmri.py:29-46)."""
+
+    def __init__(self, linop, mask, y):
+        super().__init__(linop)
+        self.mask, self.y = mask, y
+
+    def _prox(self, v, lam, num_psi):
+        y = self.y.value if isinstance(self.y, Placeholder) else torch.as_tensor(self.y)
+        m = self.mask.value if isinstance(self.mask, Placeholder) else torch.as_tensor(self.mask)
+        return ops.csmri_prox(v, y, m, lam, float(num_psi))
+
+
 # ------------------------------------------------------------------------------------------------
 #  Plug-and-play prior                                   dprox/proxfn/pnp/prior.py:42-89
 # ------------------------------------------------------------------------------------------------
@@ -249,6 +265,8 @@ class deep_prior(ProxFn):
         sigma = safe_sqrt(lam) if self.sqrt else lam
         if self.clamp:
             v = v.clamp(0, 1)
+        if torch.is_complex(v):                            # complex iterates (CS-MRI): the denoiser sees the real part (prior.py:79)
+            v = ops.real_part(v)
         inp = v.unsqueeze(1) if v.ndim == 3 else v
         den = self.denoisers[self.step] if self.unroll else self.denoiser
         out = den.denoise(inp, sigma)          # under grad mode the tape runs through the denoiser (tests/test_grad.py:6-18)

@@ -232,6 +232,18 @@ int dpx_ffdnet_set_layer(dpx_ffdnet* net, int layer, const float* w, const float
 int dpx_ffdnet_forward(dpx_ffdnet* net, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H,
                        int W, void* stream);
 
+/* ---- CS-MRI closed-form data term on complex iterates (proxfn/fast/csmri.py:14-25; the ext_sum_squares hook,
+ * proxfn/sum_square.py:44-48).  v, y, out: complex64 [B,C,H,W] (interleaved re,im); mask: fp32 0/1 [mask_batch,C,H,W],
+ * mask_batch in {1,B}; y and mask in the reference's CENTRED k-space convention (utils/misc.py:164-193).
+ *   out = ifft2c( mask ? (rho fft2c(v) + y) / (1 + rho num_psi) : fft2c(v) ),  rho: device [B] or [1]. */
+int dpx_csmri_prox(const float* v, const float* y, const float* mask, int mask_batch, const float* rho,
+                   int rho_per_sample, float num_psi, float* out, int batch, int channels, int height, int width,
+                   void* stream);
+/* real [n] -> complex64 [n] (imaginary part 0) and the real part of complex64 [n]: glue for operators whose iterates
+ * are complex while a prox (deep denoiser) works on the real part (pnp/prior.py:79). */
+int dpx_real_to_complex(const float* x, float* out, size_t n, void* stream);
+int dpx_complex_real(const float* z, float* out, size_t n, void* stream);
+
 /* ---- end-to-end host-buffer entry point (the e2e leg of bench.py) -------------------------- */
 /* Copies x0 (HOST, pinned or pageable, [B,C,H,W]) to the device, initialises (v = K x0, u = 0),
  * runs n_iters iterations with HOST schedules rho_host [T] / lam_host [n_psi][T] (scalars per

@@ -526,6 +526,38 @@ LINEAR_SOLVERS = {"cg": cg, "pcg": pcg}
 # --------------------------------------------------------------------------------------------
 
 
+def fft2c(x):                                            # utils/misc.py:164-177 (centred, ortho)
+    return torch.fft.fftshift(torch.fft.fft2(torch.fft.ifftshift(x, dim=(-2, -1)), norm="ortho"), dim=(-2, -1))
+
+
+def ifft2c(x):                                           # utils/misc.py:180-193
+    return torch.fft.fftshift(torch.fft.ifft2(torch.fft.ifftshift(x, dim=(-2, -1)), norm="ortho"), dim=(-2, -1))
+
+
+def csmri_prox(v, lam, num_psi, mask, y):
+    """csmri._prox (proxfn/fast/csmri.py:14-25): closed-form x-update of |M F x - y|^2 + rho sum_i |x - b_i|^2 given
+    v = sum_i b_i; only the sampled k-space locations change."""
+    if lam.ndim == 1:
+        lam = lam.view(lam.shape[0], 1, 1, 1)
+    z = fft2c(v)
+    temp = (lam * z + y) / (1 + lam * num_psi)
+    return ifft2c(torch.where(mask.bool(), temp, z))
+
+
+def custom_admm_csmri(denoise, mask, y, x0, rhos, sigmas):
+    """CustomADMM (contrib/csmri.py:156-171) with one deep prior and the csmri data term: prox first, complex z / u.
+    `denoise(v_real, sigma[B,1,1,1]) -> real`; deep_prior takes the real part of a complex input (pnp/prior.py:79).
+    Returns the reference's state (x, z, u) after len(rhos) iterations (ADMM.initialize: x = x0, z = x0, u = 0)."""
+    x, z, u = x0, x0, torch.zeros_like(x0)
+    for it in range(len(rhos)):
+        w = z - u
+        x = denoise(w.real if torch.is_complex(w) else w, sigmas[it].reshape(-1, 1, 1, 1)).to(torch.float32)
+        b = x + u
+        z = csmri_prox(b, rhos[it], 1, mask, y)          # ext_sum_squares.solve: sum of b, num_psi = 1 (sum_square.py:44-48)
+        u = u + x - z
+    return x, z, u
+
+
 class LeastSquares:
     """least_squares (sum_square.py:87-197): argmin_x sum_q |A_q x - b_q|^2 + rho sum_i |A_i x - b_i|^2."""
 

@@ -538,6 +538,56 @@ def unrolled_grads_doe():
     return dict(gt=_np(gt), psf=_np(psf), noise=_np(noise), inp=_np(inp), rhos=_np(rhos), sigmas=_np(sigmas), out=_np(out),
                 loss=float(loss), g_rhos=_np(rhos.grad), g_sigmas=_np(sigmas.grad), g_psf=_np(psf.grad), seed=9, T=3)
 
+# ------------------------------------------------------------------------------------------------
+# §8f-2: csmri closed-form data term (ext_sum_squares hook) on complex state, driven by CustomADMM
+# ------------------------------------------------------------------------------------------------
+
+class _RandFFDNetGray(Denoiser):
+    def __init__(self, seed):
+        super().__init__()
+        self.model = FFDNet(in_nc=1, out_nc=1, nc=96, nb=12, act_mode="R")
+        ws = orc.ffdnet_random_weights(seed, in_nc=1)
+        sd = {}
+        for i, (w, b) in enumerate(ws):
+            sd[f"model.{2 * i}.weight"], sd[f"model.{2 * i}.bias"] = w, b
+        self.model.load_state_dict(sd, strict=True)
+
+    def _denoise(self, x, sigma):
+        return self.model(x, sigma)
+
+
+@case
+def csmri_custom_admm():
+    """tests/paper/test_csmri.py:29-65: csmri(x, mask, y) + deep_prior, CustomADMM (prox first), complex iterates."""
+    from dprox.contrib.csmri import CustomADMM
+    from dprox.proxfn.fast.csmri import csmri
+    from dprox.utils import fft2, ifft2
+    out = {}
+    for tag, (H, W) in (("even", (32, 48)), ("odd", (31, 33))):
+        g = torch.Generator().manual_seed(41)
+        img = torch.zeros(2, 1, H, W)
+        img[:, :, H // 4: 3 * H // 4, W // 3: 2 * W // 3] = 1.0
+        img = img + 0.1 * torch.rand(2, 1, H, W, generator=g)
+        mask = (torch.rand(2, 1, H, W, generator=g) < 0.35).float()
+        mask[:, :, H // 2 - 3: H // 2 + 3, W // 2 - 3: W // 2 + 3] = 1.0
+        noise = 0.01 * (torch.randn(2, 1, H, W, generator=g) + 1j * torch.randn(2, 1, H, W, generator=g))
+        y0 = mask * (fft2(img.to(torch.complex64)) + noise)
+        x0 = ifft2(y0)
+        den = _RandFFDNetGray(seed=12)
+        x, y, m = dp.Variable(), dp.Placeholder(), dp.Placeholder()
+        data_term, reg_term = csmri(x, m, y), dp.deep_prior(x, denoiser=den)
+        solver = CustomADMM([reg_term], [data_term])
+        y.value, m.value = y0, mask
+        rhos = torch.tensor([0.5, 0.8, 1.2, 2.0])
+        sigmas = torch.tensor([0.08, 0.06, 0.04, 0.03])
+        with torch.no_grad():
+            st = solver.solve(x0=x0, rhos=rhos, lams={reg_term: sigmas}, max_iter=4, return_full_states=True)
+            one = data_term._prox(x0 * (1 + 0.5j), torch.tensor([0.7, 1.3]), 1)
+        out.update({f"{tag}_mask": _np(mask), f"{tag}_y0": _np(y0), f"{tag}_x0": _np(x0), f"{tag}_x": _np(st[0]),
+                    f"{tag}_z": _np(st[1][0]), f"{tag}_u": _np(st[2][0]), f"{tag}_prox1": _np(one)})
+    out.update(rhos=_np(rhos), sigmas=_np(sigmas), seed=12, T=4)
+    return out
+
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

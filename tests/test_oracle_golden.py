@@ -251,3 +251,20 @@ def test_schedules():
     r2, s2 = orc.log_descent(49, 7.65, 10, sigma=7.65 / 255, sqrt=True)
     for a, b in ((r1, g["r1"]), (s1, g["s1"]), (r2, g["r2"]), (s2, g["s2"])):
         assert np.allclose(a.numpy(), b, rtol=1e-6)
+
+
+def test_csmri_closed_form_and_custom_admm():
+    """§8f-2: csmri._prox and the CustomADMM loop on complex iterates vs the reference (even and odd sizes: the centred
+    transforms shift by n//2, which differs between fftshift and ifftshift for odd n)."""
+    g = dict(np.load(os.path.join(GOLDEN, "csmri_custom_admm.npz"), allow_pickle=False))
+    ws = orc.ffdnet_random_weights(int(g["seed"]), in_nc=1)
+    den = lambda v, s_: orc.ffdnet_forward(ws, v, s_)
+    for tag in ("even", "odd"):
+        mask, y0, x0 = (torch.from_numpy(g[f"{tag}_{k}"]) for k in ("mask", "y0", "x0"))
+        one = orc.csmri_prox(x0 * (1 + 0.5j), torch.tensor([0.7, 1.3]), 1, mask, y0)
+        assert np.abs(one.numpy() - g[f"{tag}_prox1"]).max() < 2e-6
+        with torch.no_grad():
+            x, z, u = orc.custom_admm_csmri(den, mask, y0, x0, torch.from_numpy(g["rhos"]), torch.from_numpy(g["sigmas"]))
+        for got, name in ((x, "x"), (z, "z"), (u, "u")):
+            want = g[f"{tag}_{name}"]
+            assert np.linalg.norm(got.numpy() - want) / np.linalg.norm(want) < 1e-5, (tag, name)

@@ -515,3 +515,49 @@ def test_fused_engine_4096(dp):
         s = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), method="admm", device="cuda", fft_backend=backend)
         res[backend] = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=3)
     assert rel(res[2], res[1]) < 5e-6
+
+
+def test_csmri_closed_form_custom_admm(dp):
+    """§8f-2: `csmri` data term (ext_sum_squares hook) + deep prior through contrib.CustomADMM on complex iterates
+    (tests/paper/test_csmri.py:29-46), against the unmodified reference; even and odd image sizes."""
+    from dprox_b200.contrib import CustomADMM
+    from dprox_b200.denoisers import FFDNet
+    g = load("csmri_custom_admm")
+
+    class Gray(dp.Denoiser):
+        def __init__(self, seed):
+            super().__init__()
+            self.model = FFDNet(1, 1, 96, 12)
+            ws = orc.ffdnet_random_weights(seed, in_nc=1)
+            convs = [m for m in self.model.model if isinstance(m, torch.nn.Conv2d)]
+            with torch.no_grad():
+                for c, (w, b) in zip(convs, ws):
+                    c.weight.copy_(w)
+                    c.bias.copy_(b)
+
+        def _denoise(self, x, sigma):
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                return self.model(x, sigma)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+
+    den = Gray(int(g["seed"])).cuda()
+    for tag in ("even", "odd"):
+        mask, y0, x0 = T(g[f"{tag}_mask"]), T(g[f"{tag}_y0"]), T(g[f"{tag}_x0"])
+        x, y, m = dp.Variable(), dp.Placeholder(), dp.Placeholder()
+        data_term, reg_term = dp.csmri(x, m, y), dp.deep_prior(x, denoiser=den)
+        one = data_term
+        y.value, m.value = y0, mask
+        got1 = one._prox(x0 * (1 + 0.5j), torch.tensor([0.7, 1.3], device="cuda"), 1)
+        assert rel(torch.view_as_real(got1), np.stack([g[f"{tag}_prox1"].real, g[f"{tag}_prox1"].imag], -1)) < 2e-6
+        solver = CustomADMM([reg_term], [data_term]).to("cuda")
+        assert solver.spec.tier == "generic" and solver.spec.xupdate == "ext"
+        with torch.no_grad():
+            st = solver.solve(x0=x0, rhos=T(g["rhos"], "cpu"), lams={reg_term: T(g["sigmas"], "cpu")}, max_iter=int(g["T"]),
+                              return_full_states=True)
+        cplx = lambda a: np.stack([np.real(a), np.imag(a)], -1)
+        assert rel(st[0], np.real(g[f"{tag}_x"])) < 2e-5, (tag, "x")
+        assert rel(torch.view_as_real(st[1][0]), cplx(g[f"{tag}_z"])) < 2e-5, (tag, "z")
+        assert rel(torch.view_as_real(st[2][0]), cplx(g[f"{tag}_u"])) < 1e-4, (tag, "u")
