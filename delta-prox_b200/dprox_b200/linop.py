@@ -542,11 +542,19 @@ class conv(LinOp):
         g = (fb.conj() * fb).real if fb.is_complex() else fb * fb
         return g[..., : shape[-1] // 2 + 1].float().contiguous()
 
+    def _otf_on(self, shape, device):
+        """half-spectrum OTF resident on `device` (uploaded once per shape and device: the host copy is 8 B x H x W/2 per
+        channel, and re-sending it on every forward/adjoint stalled the host for milliseconds)"""
+        key = (tuple(shape), str(device))
+        if key not in self.cache:
+            self.cache[key] = self._otf_half(shape).to(device, torch.complex64).contiguous()
+        return self.cache[key]
+
     def forward(self, input, **kw):
-        return ops.spectral_filter(input, self._otf_half(_shape4(input)), conj=False)
+        return ops.spectral_filter(input, self._otf_on(_shape4(input), input.device), conj=False)
 
     def adjoint(self, input, **kw):
-        return ops.spectral_filter(input, self._otf_half(_shape4(input)), conj=True)
+        return ops.spectral_filter(input, self._otf_on(_shape4(input), input.device), conj=True)
 
     def is_diag(self, freq=False):
         return freq and self.input_nodes[0].is_diag(freq)
