@@ -131,6 +131,107 @@ class FFDNetColorDenoiser(Denoiser):
             torch.backends.cudnn.allow_tf32 = prev
 
 
+# ------------------------------------------------------------------------------------------------
+#  DRUNet (pnp/denoisers/models/network_unet.py:67-116, wrapper.py:89-146) — SURVEY §8f rank 4
+# ------------------------------------------------------------------------------------------------
+
+class _ResBlock(nn.Module):
+    """x + conv(relu(conv(x))), bias-free 3x3 convolutions; state_dict keys `res.0.weight`, `res.2.weight`."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.res = nn.Sequential(nn.Conv2d(c, c, 3, padding=1, bias=False), nn.ReLU(inplace=True), nn.Conv2d(c, c, 3, padding=1, bias=False))
+
+    def forward(self, x):
+        return x + self.res(x)
+
+
+class UNetRes(nn.Module):
+    """DRUNet body: head conv, 3 x (nb residual blocks + 2x2 stride-2 conv), nb residual blocks, 3 x (2x2 transposed conv +
+    nb residual blocks) with additive skips, tail conv.  Module names follow the reference so published weights load."""
+
+    def __init__(self, in_nc=2, out_nc=1, nc=(64, 128, 256, 512), nb=4):
+        super().__init__()
+        blocks = lambda c: [_ResBlock(c) for _ in range(nb)]
+        self.m_head = nn.Conv2d(in_nc, nc[0], 3, padding=1, bias=False)
+        self.m_down1 = nn.Sequential(*blocks(nc[0]), nn.Conv2d(nc[0], nc[1], 2, stride=2, bias=False))
+        self.m_down2 = nn.Sequential(*blocks(nc[1]), nn.Conv2d(nc[1], nc[2], 2, stride=2, bias=False))
+        self.m_down3 = nn.Sequential(*blocks(nc[2]), nn.Conv2d(nc[2], nc[3], 2, stride=2, bias=False))
+        self.m_body = nn.Sequential(*blocks(nc[3]))
+        self.m_up3 = nn.Sequential(nn.ConvTranspose2d(nc[3], nc[2], 2, stride=2, bias=False), *blocks(nc[2]))
+        self.m_up2 = nn.Sequential(nn.ConvTranspose2d(nc[2], nc[1], 2, stride=2, bias=False), *blocks(nc[1]))
+        self.m_up1 = nn.Sequential(nn.ConvTranspose2d(nc[1], nc[0], 2, stride=2, bias=False), *blocks(nc[0]))
+        self.m_tail = nn.Conv2d(nc[0], out_nc, 3, padding=1, bias=False)
+
+    def forward(self, x0):
+        x1 = self.m_head(x0)
+        x2 = self.m_down1(x1)
+        x3 = self.m_down2(x2)
+        x4 = self.m_down3(x3)
+        x = self.m_body(x4)
+        x = self.m_up3(x + x4)
+        x = self.m_up2(x + x3)
+        x = self.m_up1(x + x2)
+        return self.m_tail(x + x1)
+
+
+class DRUNetDenoiser(Denoiser):
+    """DRUNet behind `deep_prior(x, denoiser='drunet' | 'drunet_color')` (wrapper.py:89-146): the noise level enters as an
+    extra input channel; images larger than 256 x 256 are denoised as four overlapping quadrants (recursively), images up
+    to that size are replicate-padded to a multiple of 16.  An opaque torch module on the prox hook, like every denoiser
+    but FFDNet-color."""
+
+    REFIELD, MIN_SIZE, MODULO = 32, 256, 16
+
+    def __init__(self, n_channels=1, model_path=None):
+        super().__init__()
+        self.model = UNetRes(in_nc=n_channels + 1, out_nc=n_channels)
+        if model_path is not None:
+            self.model.load_state_dict(torch.load(model_path, map_location="cpu"), strict=True)
+
+    def load_seeded(self, seed: int):
+        """Deterministic random weights in state_dict order (U(-b, b), b = 1/sqrt(fan_in)) for the parity tests."""
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for _, w in self.model.state_dict().items():
+                bound = 1.0 / math.sqrt(w[0].numel())
+                w.copy_((torch.rand(w.shape, generator=g) * 2 - 1) * bound)
+        return self
+
+    def _denoise(self, x, sigma):
+        if sigma.shape[0] != x.shape[0]:
+            sigma = sigma.expand(x.shape[0], 1, 1, 1)
+        inp = torch.cat((x, sigma.to(x.dtype).expand(x.shape[0], 1, x.shape[2], x.shape[3])), dim=1)
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            return self._tiled(inp)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+
+    def _tiled(self, L):
+        h, w = L.shape[-2:]
+        if h * w <= self.MIN_SIZE ** 2:
+            ph, pw = (-h) % self.MODULO, (-w) % self.MODULO
+            return self.model(F.pad(L, (0, pw, 0, ph), mode="replicate"))[..., :h, :w]
+        th, tw = (h // 2 // self.REFIELD + 1) * self.REFIELD, (w // 2 // self.REFIELD + 1) * self.REFIELD
+        rows, cols = (slice(0, th), slice(h - th, h)), (slice(0, tw), slice(w - tw, w))
+        run = self.model if h * w <= 4 * self.MIN_SIZE ** 2 else self._tiled
+        E = None
+        for i, rs in enumerate(rows):
+            for j, cs in enumerate(cols):
+                e = run(L[..., rs, cs])
+                if E is None:
+                    E = torch.zeros(e.shape[0], e.shape[1], h, w, dtype=L.dtype, device=L.device)
+                # each quadrant of the output takes the matching corner of its (larger, overlapping) tile
+                dst_r = slice(0, h // 2) if i == 0 else slice(h // 2, h)
+                dst_c = slice(0, w // 2) if j == 0 else slice(w // 2, w)
+                src_r = slice(0, h // 2) if i == 0 else slice(th - (h - h // 2), th)
+                src_c = slice(0, w // 2) if j == 0 else slice(tw - (w - w // 2), tw)
+                E[..., dst_r, dst_c] = e[..., src_r, src_c]
+        return E
+
+
 def get_denoiser(name: str):
     """pnp/prior.py:14-35.  Weight files are looked up under $DPROX_WEIGHTS (no network access here)."""
     root = os.environ.get("DPROX_WEIGHTS", os.path.expanduser("~/.cache/dprox/pnp_denoisers"))
@@ -140,4 +241,10 @@ def get_denoiser(name: str):
             raise FileNotFoundError(f"pretrained weights for {name!r} not found at {path}; set $DPROX_WEIGHTS or pass a "
                                     f"Denoiser instance to deep_prior(x, denoiser=obj)")
         return FFDNetColorDenoiser(path)
+    if name in ("drunet", "drunet_color"):
+        path = os.path.join(root, "drunet_gray.pth" if name == "drunet" else "drunet_color.pth")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"pretrained weights for {name!r} not found at {path}; set $DPROX_WEIGHTS or pass a "
+                                    f"Denoiser instance to deep_prior(x, denoiser=obj)")
+        return DRUNetDenoiser(1 if name == "drunet" else 3, path)
     raise NotImplementedError(f"denoiser {name!r} is not part of the lowered path (SURVEY §2 row 12); pass a Denoiser object")

@@ -588,6 +588,32 @@ def csmri_custom_admm():
     out.update(rhos=_np(rhos), sigmas=_np(sigmas), seed=12, T=4)
     return out
 
+@case
+def drunet_forward():
+    """§8f-4: DRUNetDenoiser (UNetRes + the quadrant tiling of wrapper.py:111-146) with seeded random weights: a small
+    image (replicate-pad to a multiple of 16) and one just above 256 x 256 (four overlapping quadrants)."""
+    import tempfile
+    from dprox.proxfn.pnp.denoisers.models.network_unet import UNetRes
+    from dprox.proxfn.pnp.denoisers.wrapper import DRUNetDenoiser
+    net = UNetRes(in_nc=2, out_nc=1, nc=[64, 128, 256, 512], nb=4, act_mode="R", downsample_mode="strideconv",
+                  upsample_mode="convtranspose")
+    g = torch.Generator().manual_seed(3)
+    sd = net.state_dict()
+    with torch.no_grad():
+        for k, w in sd.items():
+            w.copy_((torch.rand(w.shape, generator=g) * 2 - 1) / (w[0].numel() ** 0.5))
+    with tempfile.NamedTemporaryFile(suffix=".pth") as f:
+        torch.save(sd, f.name)
+        den = DRUNetDenoiser(1, f.name)
+    gi = torch.Generator().manual_seed(8)
+    out = dict(seed=3, keys=np.array(list(sd.keys())))
+    for tag, (h, w) in (("small", (40, 52)), ("tiled", (272, 264))):
+        x = torch.rand(1, 1, h, w, generator=gi)
+        with torch.no_grad():
+            y = den.denoise(x, torch.tensor([0.07]))
+        out[f"{tag}_x"], out[f"{tag}_y"] = _np(x), _np(y)
+    return out
+
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
