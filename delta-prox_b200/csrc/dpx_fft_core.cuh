@@ -27,8 +27,27 @@
 namespace dpx {
 namespace fft {
 
+// Complex add / sub as ONE packed instruction (Blackwell FADD2: add.f32x2 / sub.f32x2 on an aligned register pair, same
+// IEEE round-to-nearest results as two scalar FADDs).  The butterflies are add-dominated (44 % of k_col's SASS was FADD) and
+// both fused kernels are limited by instruction issue before the FP32 pipes fill, so halving the add instructions is a
+// direct win (profiles/README.md, step 6).  -DDPX_NO_F32X2 or the CPU emulator use the scalar form.
+#if defined(__CUDA_ARCH__) && !defined(DPX_EMU) && !defined(DPX_NO_F32X2)
+DPX_HD float2 cadd(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+DPX_HD float2 csub(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+#else
 DPX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 DPX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 DPX_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 DPX_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
 // multiply by -i (forward) / +i (inverse)
@@ -60,11 +79,18 @@ DPX_HD void dft2(float2& a0, float2& a1) {
 template <bool INV>
 DPX_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
   const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
-  const float2 s13 = cadd(a1, a3), d13 = mul_mi<INV>(csub(a1, a3));   // (-i)(a1-a3) forward
+  const float2 s13 = cadd(a1, a3), t = csub(a1, a3);
   a0 = cadd(s02, s13);
   a2 = csub(s02, s13);
-  a1 = cadd(d02, d13);
-  a3 = csub(d02, d13);
+  // a1 = d02 + w t, a3 = d02 - w t with w = -i (forward) / +i (inverse): w t = (t.y, -t.x) / (-t.y, t.x).  Scalar adds:
+  // a packed add would first need the swapped pair in its own registers
+  if (INV) {
+    a1 = make_float2(d02.x - t.y, d02.y + t.x);
+    a3 = make_float2(d02.x + t.y, d02.y - t.x);
+  } else {
+    a1 = make_float2(d02.x + t.y, d02.y - t.x);
+    a3 = make_float2(d02.x - t.y, d02.y + t.x);
+  }
 }
 
 template <int R, bool INV>
@@ -86,14 +112,21 @@ struct Dft<8, INV> {   // A = 4, B = 2
     dft4<INV>(a[0], a[2], a[4], a[6]);      // m2 = 0 : y[0][q1] in a[2*q1]
     dft4<INV>(a[1], a[3], a[5], a[7]);      // m2 = 1 : y[1][q1] in a[2*q1+1]
     a[3] = cmul(a[3], w16<INV>(2));         // w8^1
-    a[5] = mul_mi<INV>(a[5]);               // w8^2 = -i
     a[7] = cmul(a[7], w16<INV>(6));         // w8^3
-    // out[q1 + 4*q2] = y[0][q1] +/- y[1][q1]
+    // out[q1 + 4*q2] = y[0][q1] +/- y[1][q1];  the twiddle w8^2 = -i (forward) / +i (inverse) of y[1][2] = a[5] is folded in
     float2 o[8];
 #pragma unroll
     for (int q1 = 0; q1 < 4; ++q1) {
+      if (q1 == 2) continue;
       o[q1] = cadd(a[2 * q1], a[2 * q1 + 1]);
       o[q1 + 4] = csub(a[2 * q1], a[2 * q1 + 1]);
+    }
+    if (INV) {
+      o[2] = make_float2(a[4].x - a[5].y, a[4].y + a[5].x);
+      o[6] = make_float2(a[4].x + a[5].y, a[4].y - a[5].x);
+    } else {
+      o[2] = make_float2(a[4].x + a[5].y, a[4].y - a[5].x);
+      o[6] = make_float2(a[4].x - a[5].y, a[4].y + a[5].x);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = o[i];

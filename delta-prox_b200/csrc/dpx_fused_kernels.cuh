@@ -1108,12 +1108,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
           }
         }
         fft::Dft<RA, false>::run(a);
-#ifndef DPX_EMU
-        asm volatile("" ::: "memory");
-#endif
-        fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
-        for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
+        for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);   // twiddles stay in registers (2 CTAs/SM leave 128 each)
 #pragma unroll
         for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
       }
