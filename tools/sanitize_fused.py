@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""Small fused-engine runs for compute-sanitizer (memcheck / racecheck / synccheck) on the GPU box:
+   compute-sanitizer --tool racecheck python tools/sanitize_fused.py
+Covers the plane-pair engine (persistent TMA/cp.async row kernel, k_col), the half-spectrum engine and the TMA column kernel."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "delta-prox_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import dprox_b200 as dp  # noqa: E402
+
+psf = np.ones((5, 5, 1), "float32") / 25.0
+for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64, "hqs")):
+    g = torch.Generator(device="cuda").manual_seed(B + H)
+    b = torch.rand(B, 3, H, W, device="cuda", generator=g) - 0.3
+    x = dp.Variable()
+    s = dp.compile(dp.sum_squares(dp.conv(x, psf) - b) + dp.nonneg(x), method=method, device="cuda")
+    out = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=4)
+    torch.cuda.synchronize()
+    print(B, H, W, method, float(out.abs().mean()))
