@@ -34,6 +34,13 @@ class FftEngine {
     set_error("fused iterations not available on this engine");
     return DPX_ERR_STATE;
   }
+  // x <- closed-form x-update of the current state (v, u) in three fused launches (staged form: an external prox follows)
+  virtual int fused_xupdate(const Geom& g, const PsiPack& psi, bool hqs, float* x, float wid, float eps, const float* rho,
+                            int rho_stride, int it, cudaStream_t s) {
+    (void)g; (void)psi; (void)hqs; (void)x; (void)wid; (void)eps; (void)rho; (void)rho_stride; (void)it; (void)s;
+    set_error("fused x-update not available on this engine");
+    return DPX_ERR_STATE;
+  }
 };
 
 // backend: 0 auto, 1 cuFFT, 2 fused

@@ -199,6 +199,44 @@ struct Driver {
       });
     });
   }
+
+  // ---- staged x-update (an external prox sits between the stages): x <- closed-form solve of the current state --------
+  //   rows: t = sum_i s_i (v_i - u_i) -> forward row FFT;  columns: FFT, solve, inverse FFT;  rows: inverse FFT -> x
+  void xupdate(bool pairs, int B, int C, int H, int W, float2* S, const PsiPack& psi, int hqs, float* x, const float2* fbp,
+               const float* dqp, int dq_batch, float wid, float eps, const float* rho, int rho_stride, int it,
+               const float2* tw_h, const float2* tw_w) {
+    const int P = B * C;
+    dispatch_size(W, [&](auto wn) {
+      dispatch_size(H, [&](auto hn) {
+        using TH = typename TileFor<decltype(hn)::value, CG>::type;
+        RowParams rp;
+        rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it; rp.x = x; rp.tw = tw_w;
+        ColParams cp;
+        cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.wid = wid; cp.eps = eps;
+        cp.inv_n = 1.0f / (float)((double)H * W);
+        cp.rho.p = rho; cp.rho.it = it; cp.tw = tw_h;
+        if (pairs) {
+          using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
+          const int G = W / CG;
+          cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.dq_batch = 1; cp.rho.stride = 0;
+          const dim3 rgrid(H / ROWS, P / 2);
+          const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2);
+          be.template rowz<TW, ROW_FIRST, false>(rgrid, rsm, rp);
+          launch_col<TH>(cp, B / 2, G, C);
+          be.template rowz<TW, ROW_XONLY, false>(rgrid, rsm, rp);
+        } else {
+          using TW = typename TileFor<decltype(wn)::value, ROWS / 2>::type;
+          const int G = (W / 2) / CG;
+          cp.groups = G + 1; cp.bmul = 1; cp.eps_im = 0.f; cp.dq_batch = dq_batch; cp.rho.stride = rho_stride;
+          const dim3 rgrid(H / ROWS, P);
+          const size_t rsm = RowSmem<TW>::BYTES;
+          be.template row<TW, ROW_FIRST, false>(rgrid, rsm, rp);
+          launch_col<TH>(cp, B, G + 1, C);
+          be.template row<TW, ROW_XONLY, false>(rgrid, rsm, rp);
+        }
+      });
+    });
+  }
 };
 
 }  // namespace fused

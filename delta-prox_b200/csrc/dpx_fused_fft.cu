@@ -153,13 +153,10 @@ class FusedEngine final : public FftEngine {
     return DPX_OK;
   }
 
-  int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2*, const float*, int, float wid,
-                  float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
-    CudaBackend be{s};
-    be.n_persist = persist_ctas_;
-    be.n_sm = col_tma_sms_;
+  // packs whatever changed, in the layout of the engine variant selected for this call; returns whether pairs are used
+  int prepare(const PsiPack& psi, int rho_stride, cudaStream_t s, CudaBackend& be, bool* pairs_out) {
     Driver<CudaBackend> drv(be);
-    const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g.B, dq_batch_, rho_stride, psi);
+    const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g_.B, dq_batch_, rho_stride, psi);
     if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = true; packed_pairs_ = pairs; }
     const int Cd = dq_batch_ > 1 ? g_.P : g_.C;
     const size_t nd = pairs ? Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W) : packed_elems(Cd, g_.H, g_.W);
@@ -175,11 +172,36 @@ class FusedEngine final : public FftEngine {
     if (pairs) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
     else drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
     fb_dirty_ = dq_dirty_ = false;
+    *pairs_out = pairs;
+    return DPX_OK;
+  }
+
+  int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2*, const float*, int, float wid,
+                  float eps, const float* rho, int rho_stride, int it0, int n_iters, cudaStream_t s) override {
+    CudaBackend be{s};
+    be.n_persist = persist_ctas_;
+    be.n_sm = col_tma_sms_;
+    bool pairs = false;
+    int rc = prepare(psi, rho_stride, s, be, &pairs);
+    if (rc) return rc;
+    Driver<CudaBackend> drv(be);
     if (pairs)
       drv.iterate_pairs(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, wid, eps, rho, it0, n_iters, tw_h_, tw_w_);
     else
       drv.iterate(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it0, n_iters,
                   tw_h_, tw_w_);
+    return be.rc;
+  }
+
+  int fused_xupdate(const Geom& g, const PsiPack& psi, bool hqs, float* x, float wid, float eps, const float* rho,
+                    int rho_stride, int it, cudaStream_t s) override {
+    CudaBackend be{s};
+    be.n_sm = col_tma_sms_;
+    bool pairs = false;
+    int rc = prepare(psi, rho_stride, s, be, &pairs);
+    if (rc) return rc;
+    Driver<CudaBackend> drv(be);
+    drv.xupdate(pairs, g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it, tw_h_, tw_w_);
     return be.rc;
   }
 

@@ -36,7 +36,7 @@ constexpr int kThreads = 256;
 constexpr int kPrefetchAhead = 148 * 3;   // ~ number of k_col CTAs resident on the chip
 constexpr int kPrefetchAhead4 = 148 * 4;  // ~ number of k_row CTAs resident on the chip
 
-enum RowMode { ROW_FIRST = 0, ROW_MID = 1, ROW_LAST = 2 };
+enum RowMode { ROW_FIRST = 0, ROW_MID = 1, ROW_LAST = 2, ROW_XONLY = 3 };   // XONLY: inverse transform -> x, nothing else (staged x-update)
 
 struct RowParams {
   int C, H;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
   {  // pull this CTA's own dual rows into L2 now; they are consumed two FFT passes later (step 3)
     const size_t e0 = ((size_t)p * H + r0) * W;
     for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
-      const float* base = P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u;
+      const float* base = MODE == ROW_XONLY ? nullptr : (P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u);
       if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) prefetch_l2(base + e0 + o);
     }
   }
@@ -315,10 +315,11 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
       fft::Dft<RA, true>::run(a);                       // a[m] = (x[row a][j + m MA], x[row b][j + m MA])
     }
     const size_t ea = ((size_t)p * H + r0 + 2 * c) * W + j, eb = ea + W;
-    if (MODE == ROW_LAST) {
+    if (MODE == ROW_LAST || MODE == ROW_XONLY) {
 #pragma unroll
       for (int m = 0; m < RA; ++m) { P.x[ea + m * MA] = a[m].x; P.x[eb + m * MA] = a[m].y; }
     }
+    if (MODE == ROW_XONLY) continue;
     if (SINGLE) {
       row_term<MODE, false, RA, MA>(P.psi.t[0], P.hqs, b, P.it, ea, eb, a, a);
     } else {
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
 #pragma unroll
     for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NPAIR] = a[m];
   }
-  if (MODE == ROW_LAST) return;
+  if (MODE == ROW_LAST || MODE == ROW_XONLY) return;
   __syncthreads();
 
   // ---- 4. forward row FFT, passes B and C ---------------------------------------------------------------------
@@ -856,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
   {  // pull this CTA's dual rows into L2 now; they are consumed two FFT passes later
     const size_t eA = ((size_t)pA * H + h0) * W, eB = ((size_t)pB * H + h0) * W;
     for (int i = 0; i < (SINGLE ? 1 : P.psi.n); ++i) {
-      const float* base = P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u;
+      const float* base = MODE == ROW_XONLY ? nullptr : (P.hqs ? (MODE == ROW_FIRST ? P.psi.t[i].v : nullptr) : P.psi.t[i].u);
       if (base) for (int o = tid * 32; o < ROWS * W; o += kThreads * 32) { prefetch_l2(base + eA + o); prefetch_l2(base + eB + o); }
     }
   }
@@ -887,7 +888,7 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
     const PsiTerm& tm = P.psi.t[0];
     const bool simple = SINGLE && MODE == ROW_MID && tm.scale == 1.f && tm.beta == 1.f && tm.off == nullptr &&
                         (tm.prox == DPX_PROX_NONNEG || tm.prox == DPX_PROX_L1 || tm.prox == DPX_PROX_L2SQ || tm.prox == DPX_PROX_BOX);
-    const float lam_eff = (MODE == ROW_FIRST) ? 0.f : tm.lam[(size_t)b * tm.lam_stride + P.it] * tm.alpha;
+    const float lam_eff = (MODE == ROW_FIRST || MODE == ROW_XONLY) ? 0.f : tm.lam[(size_t)b * tm.lam_stride + P.it] * tm.alpha;
     for (int t = tid; t < NSEQ * MA; t += kThreads) {
       const int c = t % NSEQ, j = t / NSEQ;
       const int p0 = TW::phys(j, c);
@@ -901,10 +902,11 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
         fft::Dft<RA, true>::run(a);                     // a[m] = (x_A[h0+c][j + m MA], x_B[h0+c][j + m MA])
       }
       const size_t ea = ((size_t)pA * H + h0 + c) * W + j, eb = ((size_t)pB * H + h0 + c) * W + j;
-      if (MODE == ROW_LAST) {
+      if (MODE == ROW_LAST || MODE == ROW_XONLY) {
 #pragma unroll
         for (int m = 0; m < RA; ++m) { P.x[ea + m * MA] = a[m].x; P.x[eb + m * MA] = a[m].y; }
       }
+      if (MODE == ROW_XONLY) continue;
       if (simple) {
         float* __restrict__ up = tm.u;
         switch (tm.prox) {
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
       for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
     }
   }
-  if (MODE == ROW_LAST) return;
+  if (MODE == ROW_LAST || MODE == ROW_XONLY) return;
   __syncthreads();
 
   // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ----------------------------

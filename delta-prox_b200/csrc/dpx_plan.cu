@@ -338,6 +338,10 @@ int dpx_stage_xupdate(dpx_plan* p, float* x, float* const* v, float* const* u, c
   PsiPack pk = make_pack(p, v, u, nullptr, nullptr);
   if (p->d.xupdate == DPX_X_SPATIAL_DIAG)
     return launch_spatial_xupdate(g, pk, hqs, false, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
+  // fused engine: rhs + row FFT, column FFT + solve + inverse, inverse row FFT -> x  (3 launches, 34 B/element
+  // instead of the 6 launches / ~60 B/element of rhs kernel + cuFFT R2C + solve + cuFFT C2R)
+  if (p->fft->fused() && p->all_identity && pk.n > 0 && (a == DPX_ALGO_ADMM || a == DPX_ALGO_LADMM || hqs))
+    return p->fft->fused_xupdate(g, pk, hqs, x, p->wid, p->d.eps, rho, rho_stride, it, s);
   if (pk.n > 0) {
     rc = launch_rhs(g, pk, hqs, p->t, s);
     if (rc) return rc;

@@ -84,6 +84,12 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C
     t.lam = lam + (size_t)i * T; t.lam_stride = 0;
   }
   const bool pairs = !getenv("DPX_EMU_NO_PAIRS") && Driver<EmuBackend>::pairs_ok(B, dq_batch, 0, pk);
+  if (getenv("DPX_EMU_XUPDATE")) {    // staged form: only the x-update of iteration 0 (rows: rhs + FFT, columns, rows: inverse -> x)
+    if (pairs) drv.pack_constants_pairs(B, C, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
+    else drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
+    drv.xupdate(pairs, B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), dq_batch, wid, eps, rho, 0, 0, twh.data(), tww.data());
+    return pairs ? 2 : 0;
+  }
   if (pairs) {      // plane-pair engine: what the CUDA engine selects for an even batch with shared schedules
     drv.pack_constants_pairs(B, C, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
     drv.iterate_pairs(B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), wid, eps, rho, 0, T, twh.data(), tww.data());

@@ -139,3 +139,21 @@ def test_tma_column_kernel_with_plane_pairs(emu, monkeypatch):
         x, v, u = run_emu(emu, b, psf, [0], [1.0], [1.0], 1.0, [0.02], T, False)
         assert run_emu.last_engine == ("planes" if no_pairs else "pairs")
         assert rel(x, want[0].numpy()) < 5e-6 and rel(u[0], want[2][0].numpy()) < 5e-5
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_staged_xupdate_matches_first_iteration(emu, B, monkeypatch):
+    """dpx_stage_xupdate's fused form (ROW_FIRST -> k_col -> ROW_XONLY, used when an external prox sits between the stages)
+    gives bit-for-bit the x of a one-iteration fused run, on both engines, and leaves v / u untouched."""
+    g = torch.Generator().manual_seed(29)
+    Cc, H, W = 3, 64, 128
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(5, 1.5)
+    b = (orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    monkeypatch.delenv("DPX_EMU_XUPDATE", raising=False)
+    full = run_emu(emu, b, psf, [1, 0], [1.0, 1.0], [0.5, 1.0], 0.7, [0.05, 0.02], 1, False)
+    monkeypatch.setenv("DPX_EMU_XUPDATE", "1")
+    x, v, u = run_emu(emu, b, psf, [1, 0], [1.0, 1.0], [0.5, 1.0], 0.7, [0.05, 0.02], 1, False)
+    assert run_emu.last_engine == ("pairs" if B == 2 else "planes")
+    assert np.array_equal(x, full[0])
+    assert np.array_equal(v[0], b) and not u[0].any()          # state untouched by the x-update stage
