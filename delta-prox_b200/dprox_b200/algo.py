@@ -163,9 +163,6 @@ class Algorithm(nn.Module):
         """The differentiable engine: the algorithm composed kernel by kernel, each with a native backward."""
         if not x0.is_cuda:
             raise RuntimeError(f"dprox_b200 computes on CUDA devices only; the solver lives on {x0.device}.")
-        if self.spec.xupdate == "cg":
-            raise NotImplementedError("dprox_b200: gradients through the CG x-update (LinearSolve's implicit differentiation, "
-                                      "linalg/custom.py:48-62) are not part of this backend yet")
         key = (tuple(x0.shape), str(x0.device))
         ckey = _placeholder_versions(list(self.psi_fns) + list(self.omega_fns))
         eng = getattr(self, "_engine_d", None)

@@ -114,7 +114,25 @@ def _build_solver(config: LinearSolveConfig):
                    **config.solver_kwargs)
 
 
+class ImplicitSolve(torch.autograd.Function):
+    """LinearSolve (linalg/custom.py:39-62): x = solve(A, b) with the implicit-differentiation backward
+    grad_b = solve(A^T, grad_x) -- a second run of the same fused-kernel CG (A is the symmetric normal-equation
+    operator, so A^T = A, sum_square.py:175-177).  Like the reference, whose KtK module multiplies by the closure `rho`
+    rather than by its own parameter (sum_square.py:160-173), nothing is propagated to quantities inside A: rho and the
+    measurements receive their gradients through the right-hand side only."""
+
+    @staticmethod
+    def forward(ctx, A, b, config):
+        ctx.A, ctx.config = A, config
+        return _build_solver(config)(A, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, _build_solver(ctx.config)(ctx.A, g.contiguous()), None
+
+
 def linear_solve(A: Callable, b: torch.Tensor, config: LinearSolveConfig = LinearSolveConfig()):
-    """Solve A x = b matrix-free (linalg/custom.py:65-82).  Forward only: the implicit-differentiation
-    backward of the reference (custom.py:48-62) is not part of this backend yet."""
+    """Solve A x = b matrix-free (linalg/custom.py:65-82); differentiable w.r.t. b by implicit differentiation."""
+    if config.use_analytic_grad and torch.is_grad_enabled() and b.requires_grad:
+        return ImplicitSolve.apply(A, b, config)
     return _build_solver(config)(A, b)

@@ -612,7 +612,28 @@ class LeastSquares:
             return out
 
         Ktb = self._rhs(b, rho, like)
-        return LINEAR_SOLVERS[self.solver_type](KtK, Ktb, rtol=self.rtol, max_iters=self.max_iters)
+        solve = lambda A, rhs: LINEAR_SOLVERS[self.solver_type](A, rhs, rtol=self.rtol, max_iters=self.max_iters)
+        if torch.is_grad_enabled() and Ktb.requires_grad:
+            return _ImplicitSolve.apply(KtK, Ktb, solve)
+        return solve(KtK, Ktb)
+
+
+class _ImplicitSolve(torch.autograd.Function):
+    """LinearSolve (linalg/custom.py:39-62): x = solve(A, b); backward grad_b = solve(A^T, grad_x) with A^T = A for the
+    normal equations.  The reference's KtK multiplies by the closure `rho` instead of its `self.rho` parameter
+    (sum_square.py:160-173), so `autograd.grad(-A(x), params(A), grad_b)` finds no path to rho: the matrix' dependence
+    on rho is NOT differentiated, only the right-hand side's -- restated as is."""
+
+    @staticmethod
+    def forward(ctx, A, b, solve):
+        ctx.A, ctx.solve = A, solve
+        with torch.no_grad():
+            return solve(A, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        with torch.no_grad():
+            return None, ctx.solve(ctx.A, g), None
 
 
 # --------------------------------------------------------------------------------------------

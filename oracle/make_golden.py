@@ -614,6 +614,29 @@ def drunet_forward():
         out[f"{tag}_x"], out[f"{tag}_y"] = _np(x), _np(y)
     return out
 
+@case
+def unrolled_grads_cg():
+    """a13: gradients through the CG x-update by LinearSolve's implicit differentiation (linalg/custom.py:39-62):
+    grad_b = solve(A^T, grad_x).  NB: the reference's KtK module multiplies by the closure `rho`, not by its own
+    `self.rho` parameter (sum_square.py:160-173), so the rho-dependence of the MATRIX is not differentiated -- only the
+    right-hand side's (rho * K_i^T b_i).  The golden vectors record what the reference actually returns."""
+    g = torch.Generator().manual_seed(19)
+    img = torch.rand(1, 3, 16, 24, generator=g)
+    psf = point_spread_function(5, 1.5)
+    x = dp.Variable()
+    b = dp.CompGraph(dp.mosaic(dp.conv(x, psf))).forward(img).float().detach()
+    wgt = torch.rand(1, 3, 16, 24, generator=g)
+    b = b.clone().requires_grad_(True)
+    x0 = torch.rand(1, 3, 16, 24, generator=g).requires_grad_(True)
+    rhos = torch.tensor([0.5, 0.8, 1.1]).requires_grad_(True)
+    cfg = LinearSolveConfig(rtol=1e-7, max_iters=60, solver_type="cg")
+    f = dp.nonneg(x)
+    solver = dp.compile(dp.sum_squares(dp.mosaic(dp.conv(x, psf)) - b) + f, method="admm", device="cpu", linear_solve_config=cfg)
+    out = solver.solve(x0=x0, rhos=rhos, lams={f: torch.full((3,), 0.02)}, max_iter=3)
+    (out * wgt).sum().backward()
+    return dict(psf=psf, b=_np(b), x0=_np(x0), wgt=_np(wgt), rhos=_np(rhos), out=_np(out), g_b=_np(b.grad), g_x0=_np(x0.grad),
+                g_rhos=_np(rhos.grad), T=3, cg_iters=60, rtol=1e-7)
+
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -152,3 +152,22 @@ def test_backward_kernels_directly(dp):
             assert rel(out, ref) < 1e-6 and rel(v.grad, vc.grad) < 1e-6, (name, alpha)
             if name != "nonneg":
                 assert rel(lam.grad, lc.grad) < 1e-5, (name, alpha, lam.grad, lc.grad)
+
+
+def test_implicit_cg_gradients(dp):
+    """a13: gradients through the CG x-update (joint demosaic + deconvolution, no closed form) by implicit differentiation:
+    backward = a second run of the fused-kernel CG; against the reference's LinearSolve.backward (golden)."""
+    g = load("unrolled_grads_cg")
+    b = T(g["b"]).requires_grad_(True)
+    x0 = T(g["x0"]).requires_grad_(True)
+    rhos = T(g["rhos"]).requires_grad_(True)
+    x = dp.Variable()
+    f = dp.nonneg(x)
+    cfg = dp.LinearSolveConfig(rtol=float(g["rtol"]), max_iters=int(g["cg_iters"]), solver_type="cg")
+    solver = dp.compile(dp.sum_squares(dp.mosaic(dp.conv(x, g["psf"])) - b) + f, method="admm", device="cuda", linear_solve_config=cfg)
+    assert solver.spec.xupdate == "cg"
+    out = solver.solve(x0=x0, rhos=rhos, lams={f: torch.full((3,), 0.02)}, max_iter=int(g["T"]))
+    (out * T(g["wgt"])).sum().backward()
+    assert rel(out, g["out"]) < 2e-5
+    for name, t in (("g_b", b), ("g_x0", x0), ("g_rhos", rhos)):
+        assert t.grad is not None and rel(t.grad, g[name]) < 2e-4, (name, rel(t.grad, g[name]))

@@ -76,3 +76,20 @@ def test_xsolve_backward_closed_form_matches_autograd():
         wgt[-1] = 1.0
         gr_m = (wgt * (Wh.conj() * (Q * (dq + eps) - torch.fft.rfft2(ktb) - eps)).real / Dn / (n * r)).sum((1, 2, 3))
     assert (gk - gk_m).abs().max() < 1e-12 and (gt - r * gk_m).abs().max() < 1e-12 and (gr - gr_m).abs().max() < 1e-10
+
+
+def test_oracle_implicit_cg_gradients_match_reference():
+    """a13: LinearSolve's implicit differentiation through the CG x-update (joint demosaic + deconvolution), including the
+    reference's omission of d(matrix)/d(rho) (see oracle._ImplicitSolve)."""
+    g = load("unrolled_grads_cg")
+    b = torch.from_numpy(g["b"]).requires_grad_(True)
+    x0 = torch.from_numpy(g["x0"]).requires_grad_(True)
+    rhos = torch.from_numpy(g["rhos"]).requires_grad_(True)
+    f = orc.Term("nonneg")
+    data = orc.Term("sum_squares", orc.Mosaic(orc.Conv(g["psf"], orc.Identity())), c=b)
+    out = orc.Solver([data, f], "admm", solver_type="cg", rtol=float(g["rtol"]), max_iters=int(g["cg_iters"])).solve(
+        x0, rhos=rhos, lams={f: torch.full((3,), 0.02)}, max_iter=int(g["T"]))
+    (out * torch.from_numpy(g["wgt"])).sum().backward()
+    assert rel(out, g["out"]) < 1e-5
+    for name, t in (("g_b", b), ("g_x0", x0), ("g_rhos", rhos)):
+        assert rel(t.grad, g[name]) < 1e-4, (name, rel(t.grad, g[name]))
