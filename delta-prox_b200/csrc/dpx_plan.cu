@@ -261,6 +261,18 @@ int dpx_plan_set_rhs(dpx_plan* p, const float* ktb, void* stream) {
   return p->fft->set_constants(p->fb, nullptr, p->dq_batch, s);      // engines re-pack F(K^T b) only
 }
 
+int dpx_plan_set_rhs_spectral(dpx_plan* p, const float* b, const float* otf, int otf_batch, float scale, void* stream) {
+  DPX_REQUIRE(p && b && otf, "null argument");
+  DPX_REQUIRE(p->consts_set, "constants not set yet (call dpx_plan_set_*_constants first)");
+  DPX_REQUIRE(p->d.xupdate == DPX_X_FREQ_DIAG && p->fft && p->fb, "dpx_plan_set_rhs_spectral needs a FREQ_DIAG plan");
+  DPX_REQUIRE(otf_batch == 1 || otf_batch == p->g.B, "otf_batch must be 1 or B");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = p->fft->r2c(b, p->fb, s);                       // F(b) ...
+  if (!rc) rc = launch_mul_otf(p->g, p->fb, (const float2*)otf, otf_batch, /*conj=*/true, scale, s);   // ... times scale * conj(OTF)
+  if (!rc) rc = p->fft->set_constants(p->fb, nullptr, p->dq_batch, s);
+  return rc;
+}
+
 int dpx_plan_set_spatial_constants(dpx_plan* p, const float* ktb, const float* dq, int dq_batch, void* stream) {
   DPX_REQUIRE(p, "null plan");
   DPX_REQUIRE(p->d.xupdate == DPX_X_SPATIAL_DIAG, "plan is not SPATIAL_DIAG");

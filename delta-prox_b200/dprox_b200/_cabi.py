@@ -54,6 +54,7 @@ SIGNATURES = {
     "dpx_plan_workspace_bytes": (_SZ, [_VP]),
     "dpx_plan_set_freq_constants": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "dpx_plan_set_rhs": (_I, [_VP, _VP, _VP]),
+    "dpx_plan_set_rhs_spectral": (_I, [_VP, _VP, _VP, _I, _F, _VP]),
     "dpx_plan_set_spatial_constants": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dpx_plan_set_psi_offset": (_I, [_VP, _I, _VP, _VP]),
     "dpx_iters": (_I, [_VP, _VP, _PP, _PP, _VP, _I, _PP, _IP, _I, _I, _VP, _VP]),

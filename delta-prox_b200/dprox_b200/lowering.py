@@ -299,9 +299,34 @@ class NativeEngine(_EngineBase):
                     cabi.check(lib.dpx_plan_set_psi_offset(self.plan.handle, i, cabi.ptr(off), s), "dpx_plan_set_psi_offset")
         self._keep = (ktb, dq)
 
+    def _rhs_in_fourier_domain(self) -> bool:
+        """sum_squares(s * conv(x) - b) as the only quadratic term: F(K^T b) = s conj(OTF) F(b) without leaving the
+        Fourier domain (dpx_plan_set_rhs_spectral) -- two FFTs less per new batch of measurements."""
+        spec = self.spec
+        if spec.xupdate != "freq" or len(spec.quad) != 1 or spec.quad[0].kind != "spectral" or spec.quad[0].low.otf_fn is None:
+            return False
+        t = spec.quad[0]
+        b = torch.as_tensor(t.fn.offset)
+        if b.is_complex() or not b.is_cuda:
+            return False
+        b = cabi.require_cuda_f32(b.to(self.device, torch.float32).expand(self.shape), "b")
+        otf = torch.as_tensor(t.low.otf_fn(self.shape4))
+        key = (id(t.low.otf_fn.__self__) if hasattr(t.low.otf_fn, "__self__") else id(t.low.otf_fn), otf.data_ptr())
+        if getattr(self, "_otf_dev_key", None) != key:
+            self._otf_dev = otf.to(self.device, torch.complex64).contiguous()
+            self._otf_dev_key = key
+        otf = self._otf_dev
+        with torch.cuda.device(self.device):
+            cabi.check(cabi.lib().dpx_plan_set_rhs_spectral(self.plan.handle, cabi.ptr(self._v(b).contiguous()), C.c_void_p(otf.data_ptr()),
+                                                            otf.shape[0] if otf.ndim == 4 else 1, float(t.scale),
+                                                            cabi.stream_ptr(self.device)), "dpx_plan_set_rhs_spectral")
+        return True
+
     def update_rhs(self, x0):
         """A Placeholder-fed measurement changed: re-hoist K^T b (and psi offsets) only; diagonals and plan stay."""
         spec, dev = self.spec, self.device
+        if not any(t.low is not None and t.low.const for t in spec.psi) and self._rhs_in_fourier_domain():
+            return
         like = torch.zeros(self.shape, device=dev, dtype=torch.float32)
         for t in spec.psi + spec.quad:
             for v in t.fn.linop.variables:

@@ -561,3 +561,24 @@ def test_csmri_closed_form_custom_admm(dp):
         assert rel(st[0], np.real(g[f"{tag}_x"])) < 2e-5, (tag, "x")
         assert rel(torch.view_as_real(st[1][0]), cplx(g[f"{tag}_z"])) < 2e-5, (tag, "z")
         assert rel(torch.view_as_real(st[2][0]), cplx(g[f"{tag}_u"])) < 1e-4, (tag, "u")
+
+
+def test_placeholder_measurements_reuse_the_plan(dp):
+    """New measurements through a Placeholder keep the plan and only refresh F(K^T b) — formed directly in the Fourier
+    domain (dpx_plan_set_rhs_spectral) — and give the same answer as a freshly compiled solver."""
+    g = load("admm_conv_nonneg")
+    psf = g["psf"]
+    b1 = T(g["b"])
+    b2 = (b1 * 0.7 + 0.1).contiguous()
+    x, y = dp.Variable(), dp.Placeholder()
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method="admm", device="cuda")
+    y.value = b1
+    out1 = solver.solve(x0=b1, rhos=float(g["rho"]) if "rho" in g else None, max_iter=int(g["T"])).clone()
+    assert rel(out1, g["s0"]) < TOL_X
+    eng = solver._engine
+    y.value = b2
+    out2 = solver.solve(x0=b2, max_iter=5)
+    assert solver._engine is eng                                  # same plan
+    x2 = dp.Variable()
+    fresh = dp.compile(dp.sum_squares(dp.conv(x2, psf) - b2) + dp.nonneg(x2), method="admm", device="cuda").solve(x0=b2, max_iter=5)
+    assert rel(out2, fresh) < 2e-6
