@@ -24,6 +24,8 @@ class FftEngine {
     return DPX_OK;
   }
   virtual void reset_constants() {}
+  // per-channel diagonal of the non-identity psi linops, standard layout [C,H,Wc] (nullptr = none)
+  virtual void set_dpsi(const float* dpsi_std) { (void)dpsi_std; }
   // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true
   virtual bool fused() const { return false; }
   virtual int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2* fb, const float* dq,

@@ -80,7 +80,7 @@ struct Driver {
   template <class TH>
   void launch_col(const ColParams& cp, int nb, int groups, int C) {
     if constexpr (TH::N == 1024 || TH::N == 2048) {
-      if (be.sm_count() > 0) {
+      if (be.sm_count() > 0 && cp.dpsp == nullptr) {
         const int n_tiles = nb * groups * C, per_sm = TH::N >= 2048 ? 1 : 2;
         const int ctas = n_tiles < be.sm_count() * per_sm ? n_tiles : be.sm_count() * per_sm;
         be.template col_tma<TH>(dim3(ctas), ColTmaCfg<TH>::BYTES, cp, n_tiles, nb);
@@ -91,12 +91,14 @@ struct Driver {
   }
 
   // packs F(K^T b) (complex, [P,H,Wc]) and sum|OTF|^2 (real, [Cd,H,Wc]) into k_col's record layout
-  void pack_constants(int P, int Cd, int H, int W, const float2* fb_std, float2* fbp, const float* dq_std, float* dqp) {
+  void pack_constants(int P, int Cd, int H, int W, const float2* fb_std, float2* fbp, const float* dq_std, float* dqp,
+                      int C = 0, const float* dpsi_std = nullptr, float* dpsp = nullptr) {
     const int G = (W / 2) / CG;
     dispatch_size(H, [&](auto hn) {
       using TH = typename TileFor<decltype(hn)::value, CG>::type;
       if (fb_std) be.template pack<TH, float2>(fb_std, fbp, P, H, W, G, make_float2(0.f, 0.f));
       if (dq_std) be.template pack<TH, float>(dq_std, dqp, Cd, H, W, G, 0.f);
+      if (dpsi_std) be.template pack<TH, float>(dpsi_std, dpsp, C, H, W, G, 0.f);
     });
   }
 
@@ -113,7 +115,7 @@ struct Driver {
         RowParams rp;
         rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
         ColParams cp;
-        cp.C = C; cp.W = W; cp.groups = G + 1; cp.bmul = 1; cp.eps_im = 0.f; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
+        cp.C = C; cp.W = W; cp.groups = G + 1; cp.bmul = 1; cp.eps_im = 0.f; cp.dpsp = nullptr; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dq_batch = dq_batch;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = rho_stride; cp.rho.it = it0; cp.tw = tw_h;
         const dim3 rgrid(H / ROWS, P);
@@ -150,13 +152,15 @@ struct Driver {
   }
   static size_t pair_elems(int planes, int H, int W) { return (size_t)planes * H * W; }   // float2 (fbz, S) / float (dqz) count
 
-  void pack_constants_pairs(int B, int C, int H, int W, const float2* fb_std, float2* fbz, const float* dq_std, float* dqz) {
+  void pack_constants_pairs(int B, int C, int H, int W, const float2* fb_std, float2* fbz, const float* dq_std, float* dqz,
+                            const float* dpsi_std = nullptr, float* dpsz = nullptr) {
     dispatch_size(W, [&](auto wn) {
       dispatch_size(H, [&](auto hn) {
         using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         if (fb_std) be.template packz_fb<TH, TW>(fb_std, fbz, (B / 2) * C, C, H, W);
         if (dq_std) be.template packz_dq<TH, TW>(dq_std, dqz, C, H, W);
+        if (dpsi_std) be.template packz_dq<TH, TW>(dpsi_std, dpsz, C, H, W);
       });
     });
   }
@@ -173,7 +177,7 @@ struct Driver {
         RowParams rp;
         rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it0; rp.x = x; rp.tw = tw_w;
         ColParams cp;
-        cp.C = C; cp.W = W; cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.S = S; cp.fbp = fbz; cp.dqp = dqz; cp.dq_batch = 1;
+        cp.C = C; cp.W = W; cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.dpsp = nullptr; cp.S = S; cp.fbp = fbz; cp.dqp = dqz; cp.dq_batch = 1;
         cp.wid = wid; cp.eps = eps; cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.stride = 0; cp.rho.it = it0; cp.tw = tw_h;
         const dim3 rgrid(H / ROWS, PP);
@@ -204,7 +208,7 @@ struct Driver {
   //   rows: t = sum_i s_i (v_i - u_i) -> forward row FFT;  columns: FFT, solve, inverse FFT;  rows: inverse FFT -> x
   void xupdate(bool pairs, int B, int C, int H, int W, float2* S, const PsiPack& psi, int hqs, float* x, const float2* fbp,
                const float* dqp, int dq_batch, float wid, float eps, const float* rho, int rho_stride, int it,
-               const float2* tw_h, const float2* tw_w) {
+               const float2* tw_h, const float2* tw_w, const float* dpsp = nullptr) {
     const int P = B * C;
     dispatch_size(W, [&](auto wn) {
       dispatch_size(H, [&](auto hn) {
@@ -212,7 +216,7 @@ struct Driver {
         RowParams rp;
         rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it; rp.x = x; rp.tw = tw_w;
         ColParams cp;
-        cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.wid = wid; cp.eps = eps;
+        cp.C = C; cp.W = W; cp.S = S; cp.fbp = fbp; cp.dqp = dqp; cp.dpsp = dpsp; cp.wid = wid; cp.eps = eps;
         cp.inv_n = 1.0f / (float)((double)H * W);
         cp.rho.p = rho; cp.rho.it = it; cp.tw = tw_h;
         if (pairs) {

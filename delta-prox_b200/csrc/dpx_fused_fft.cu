@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -137,11 +138,12 @@ class FusedEngine final : public FftEngine {
   size_t workspace_bytes() const override { return bytes_ + (inner_ ? inner_->workspace_bytes() : 0); }
   void destroy() override {
     if (inner_) inner_->destroy();
-    cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(tw_h_); cudaFree(tw_w_);
+    cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(dpsp_); cudaFree(tw_h_); cudaFree(tw_w_);
     delete this;
   }
   bool fused() const override { return true; }
   void reset_constants() override { dq_set_ = false; dq_std_ = nullptr; dq_dirty_ = true; }
+  void set_dpsi(const float* dpsi_std) override { dpsi_std_ = dpsi_std; dpsi_dirty_ = true; }
 
   // Constants are packed lazily, in the layout of the engine variant the next fused_iters call selects (half-spectrum
   // planes or plane pairs): set_constants only records which standard-layout arrays (owned by the plan) changed.
@@ -157,7 +159,13 @@ class FusedEngine final : public FftEngine {
   int prepare(const PsiPack& psi, int rho_stride, cudaStream_t s, CudaBackend& be, bool* pairs_out) {
     Driver<CudaBackend> drv(be);
     const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g_.B, dq_batch_, rho_stride, psi);
-    if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = true; packed_pairs_ = pairs; }
+    if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = dpsi_dirty_ = true; packed_pairs_ = pairs; }
+    if (dpsi_std_ && !dpsp_) {
+      const size_t np = std::max(Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W), packed_elems(g_.C, g_.H, g_.W));
+      DPX_CUDA(cudaMalloc(&dpsp_, np * sizeof(float)));
+      bytes_ += np * sizeof(float);
+      dpsi_dirty_ = true;
+    }
     const int Cd = dq_batch_ > 1 ? g_.P : g_.C;
     const size_t nd = pairs ? Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W) : packed_elems(Cd, g_.H, g_.W);
     if (dqp_cap_ < nd) {
@@ -169,9 +177,10 @@ class FusedEngine final : public FftEngine {
     }
     if (dq_dirty_ && !dq_std_) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));
     if (fb_dirty_ && !fb_std_) DPX_CUDA(cudaMemsetAsync(fbp_, 0, s_elems(g_.P, g_.H, g_.W) * sizeof(float2), s));
-    if (pairs) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
-    else drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_);
-    fb_dirty_ = dq_dirty_ = false;
+    const float* dps = (dpsi_dirty_ && dpsi_std_) ? dpsi_std_ : nullptr;
+    if (pairs) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_, dps, dpsp_);
+    else drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_, g_.C, dps, dpsp_);
+    fb_dirty_ = dq_dirty_ = dpsi_dirty_ = false;
     *pairs_out = pairs;
     return DPX_OK;
   }
@@ -201,7 +210,8 @@ class FusedEngine final : public FftEngine {
     int rc = prepare(psi, rho_stride, s, be, &pairs);
     if (rc) return rc;
     Driver<CudaBackend> drv(be);
-    drv.xupdate(pairs, g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it, tw_h_, tw_w_);
+    drv.xupdate(pairs, g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it, tw_h_, tw_w_,
+                dpsi_std_ ? dpsp_ : nullptr);
     return be.rc;
   }
 
@@ -222,6 +232,9 @@ class FusedEngine final : public FftEngine {
   int col_tma_sms_ = 0;
   const float2* fb_std_ = nullptr;
   const float* dq_std_ = nullptr;
+  const float* dpsi_std_ = nullptr;
+  float* dpsp_ = nullptr;
+  bool dpsi_dirty_ = false;
   bool fb_dirty_ = true, dq_dirty_ = true, dq_set_ = false;
   bool packed_pairs_ = false, pairs_enabled_ = true;
 };

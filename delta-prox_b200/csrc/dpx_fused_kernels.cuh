@@ -56,6 +56,7 @@ struct ColParams {
   float2* S;
   const float2* fbp;             // packed F(K^T b)      [(P*(G+1)), H/RC, CG, RC]
   const float* dqp;              // packed sum|OTF|^2    [(Cd*(G+1)), H/RC, CG, RC]
+  const float* dpsp;             // packed sum_i s_i^2 |F(K_i)|^2 of the non-identity psi linops (per channel), or nullptr
   int dq_batch;                  // 1: shared by the batch (indexed by channel), else per plane
   float wid, eps, inv_n;
   RhoRef rho;
@@ -640,6 +641,14 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     for (int m = 0; m < RC / 4; ++m) {
       const float4 v = ld_stream4(dq4 + m * NT);
       d[4 * m] = v.x; d[4 * m + 1] = v.y; d[4 * m + 2] = v.z; d[4 * m + 3] = v.w;
+    }
+    if (P.dpsp) {              // TV-type terms: the denominator gains rho * sum_i s_i^2 |F(K_i)|^2 (sum_square.py:145-148)
+      const float4* ps4 = reinterpret_cast<const float4*>(P.dpsp) + ((size_t)(p % P.C) * NG + g) * (H * CG / 4) + t;
+#pragma unroll
+      for (int m = 0; m < RC / 4; ++m) {
+        const float4 v = ld_stream4(ps4 + m * NT);
+        d[4 * m] += rho * v.x; d[4 * m + 1] += rho * v.y; d[4 * m + 2] += rho * v.z; d[4 * m + 3] += rho * v.w;
+      }
     }
     float2 a[RC];
 #pragma unroll

@@ -84,10 +84,33 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C
     t.lam = lam + (size_t)i * T; t.lam_stride = 0;
   }
   const bool pairs = !getenv("DPX_EMU_NO_PAIRS") && Driver<EmuBackend>::pairs_ok(B, dq_batch, 0, pk);
+  // DPX_EMU_LINOPS="1,2": the solve's denominator gains the diagonal of stencil-gradient psi linops (1 = along H, 2 = along
+  // W), sum_i |F(K_i)|^2 = 2 - 2 cos(2 pi k / n), built here and packed like the plan does (their right-hand side
+  // sum_i K_i^T (v_i - u_i) is formed by the stencil kernel and handed to the fused engine as one identity term)
+  std::vector<float> dpsi_std, dpsp;
+  if (const char* lo = getenv("DPX_EMU_LINOPS")) {
+    const int Wc = W / 2 + 1;
+    dpsi_std.assign((size_t)C * H * Wc, 0.f);
+    int i = 0;
+    for (const char* q = lo; *q; ++q) {
+      if (*q == ',') continue;
+      const int l = *q - '0';
+      const double two_pi = 6.283185307179586476925286766559;
+      if (l == 1 || l == 2)
+        for (int c = 0; c < C; ++c)
+          for (int h = 0; h < H; ++h)
+            for (int k = 0; k < Wc; ++k)
+              dpsi_std[((size_t)c * H + h) * Wc + k] += (float)(2.0 - 2.0 * cos(two_pi * (l == 1 ? (double)h / H : (double)k / W)));
+      ++i;
+    }
+    dpsp.assign(std::max(packed_elems(C, H, W), (size_t)C * H * W), 0.f);
+  }
   if (getenv("DPX_EMU_XUPDATE")) {    // staged form: only the x-update of iteration 0 (rows: rhs + FFT, columns, rows: inverse -> x)
-    if (pairs) drv.pack_constants_pairs(B, C, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
-    else drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data());
-    drv.xupdate(pairs, B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), dq_batch, wid, eps, rho, 0, 0, twh.data(), tww.data());
+    const float* ds = dpsi_std.empty() ? nullptr : dpsi_std.data();
+    if (pairs) drv.pack_constants_pairs(B, C, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data(), ds, dpsp.data());
+    else drv.pack_constants(P, Cd, H, W, reinterpret_cast<const float2*>(fb_std), fbp.data(), dq_std, dqp.data(), C, ds, dpsp.data());
+    drv.xupdate(pairs, B, C, H, W, S.data(), pk, hqs, x, fbp.data(), dqp.data(), dq_batch, wid, eps, rho, 0, 0, twh.data(), tww.data(),
+                ds ? dpsp.data() : nullptr);
     return pairs ? 2 : 0;
   }
   if (pairs) {      // plane-pair engine: what the CUDA engine selects for an even batch with shared schedules

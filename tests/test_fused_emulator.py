@@ -157,3 +157,34 @@ def test_staged_xupdate_matches_first_iteration(emu, B, monkeypatch):
     assert run_emu.last_engine == ("pairs" if B == 2 else "planes")
     assert np.array_equal(x, full[0])
     assert np.array_equal(v[0], b) and not u[0].any()          # state untouched by the x-update stage
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_staged_xupdate_with_stencil_gradients(emu, B, monkeypatch):
+    """Anisotropic TV through the fused engine: the right-hand side t = sum_i K_i^T (v_i - u_i) (stencil kernel; here the
+    oracle's adjoint) enters as ONE identity term and the solve's denominator gains rho sum_i |F(K_i)|^2 (packed like the
+    quadratic diagonal); x must equal the oracle's x after one ADMM iteration from the state v_i = K_i x0, u_i = 0."""
+    g = torch.Generator().manual_seed(37)
+    Cc, H, W = 1, 64, 128
+    img = torch.rand(B, Cc, H, W, generator=g)
+    psf = orc.point_spread_function(5, 1.5)
+    conv = orc.Conv(psf, orc.Identity())
+    b = (conv.fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    th, tw = orc.Term("norm1", orc.Grad(0, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))
+    data = orc.Term("sum_squares", conv, c=torch.from_numpy(b))
+    want = orc.Solver([data, th, tw], "admm").solve(torch.from_numpy(b), rhos=0.7, lams=0.05, max_iter=1)
+    bt = torch.from_numpy(b)
+    t = sum(tm.op.adj(tm.op.fwd(bt)) for tm in (th, tw)).numpy()          # sum_i K_i^T (v_i - 0)
+    v, x = [np.ascontiguousarray(t)], b.copy()
+    ktb = conv.adj(bt).numpy()
+    fb = np.ascontiguousarray(np.fft.rfft2(ktb.astype(np.float64)).astype(np.complex64).reshape(B * Cc, H, W // 2 + 1))
+    dq = np.ascontiguousarray((np.abs(conv.FB(b.shape).numpy()) ** 2)[0, :, :, : W // 2 + 1].astype(np.float32))
+    monkeypatch.setenv("DPX_EMU_XUPDATE", "1")
+    monkeypatch.setenv("DPX_EMU_LINOPS", "1,2")
+    arr = lambda lst: (C.POINTER(C.c_float) * 1)(*[fptr(a) for a in lst])
+    rho_a, lam_a = np.full(1, 0.7, np.float32), np.full((1, 1), 0.05, np.float32)
+    rc = emu.emu_fused_run(B, Cc, H, W, 1, (C.c_int * 1)(1), (C.c_float * 1)(1.0), (C.c_float * 1)(1.0), (C.c_float * 1)(1.0),
+                           fptr(x), arr(v), arr([np.zeros_like(b)]), None, fb.view(np.float32).ctypes.data_as(C.POINTER(C.c_float)),
+                           fptr(dq), 1, C.c_float(0.0), C.c_float(1e-7), fptr(rho_a), fptr(lam_a), 1, 1)
+    assert rc == (2 if B == 2 else 0)
+    assert rel(x, want.numpy()) < 5e-6
