@@ -397,6 +397,14 @@ int dpx_xsolve(dpx_plan* p, const float* t, const float* rho, int rho_stride, in
     one.t[0].v = const_cast<float*>(t);
     return launch_spatial_xupdate(g, one, /*hqs=*/true, false, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
   }
+  if (p->fft->fused() && aligned16(t) && aligned16(x)) {      // rows: FFT of t; columns: solve; rows: inverse -> x (3 fused launches)
+    PsiPack one;
+    one.n = 1;
+    memset(&one.t[0], 0, sizeof(PsiTerm));
+    one.t[0].linop = DPX_LINOP_IDENTITY; one.t[0].scale = 1.f; one.t[0].alpha = one.t[0].beta = one.t[0].inv_beta = 1.f;
+    one.t[0].v = const_cast<float*>(t);
+    return p->fft->fused_xupdate(g, one, /*hqs: rhs = v*/ true, x, p->wid, p->d.eps, rho, rho_stride, it, s);
+  }
   int rc = p->fft->r2c(t, p->spec, s);
   if (!rc) rc = launch_spec_solve(g, p->spec, p->fb, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps,
                                   1.0f / (float)((double)g.H * g.W), rr, s);

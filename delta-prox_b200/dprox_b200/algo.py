@@ -246,13 +246,18 @@ class Algorithm(nn.Module):
         return state
 
     def _iters_with_stop(self, eng, state, rhos, lams, max_iter, stop: ResidualStop):
+        """Residual stopping rule: the first `every - 1` iterations of each block run in the fused loop (which keeps v only
+        implicitly, so it has no v - v_prev to measure); the block's last iteration runs through the kernel that also
+        accumulates {|r|^2, |s|^2, |Kx|^2, |v|^2} per sample with warp-shuffle reductions, and those sums are tested."""
         B = eng.shape4[0]
         n_elems = state[0].numel() * max(1, len(self.psi_fns))
         it = 0
         while it < max_iter:
             n = min(stop.every, max_iter - it)
-            resid = torch.zeros(n, B, 4, device=state[0].device, dtype=torch.float32)
-            state = eng.run(state, rhos, lams, it, n, resid=resid)
+            if n > 1:
+                state = eng.run(state, rhos, lams, it, n - 1)
+            resid = torch.zeros(1, B, 4, device=state[0].device, dtype=torch.float32)
+            state = eng.run(state, rhos, lams, it + n - 1, 1, resid=resid)
             it += n
             if stop.converged(resid[-1].sum(dim=0), n_elems):
                 break

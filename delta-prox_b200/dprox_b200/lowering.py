@@ -455,7 +455,7 @@ class GenericEngine(_EngineBase):
             d = cabi.ProblemDesc()
             d.abi_version = cabi.ABI_VERSION
             d.batch, d.channels, d.height, d.width = B, Cc, H, W
-            d.algo, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, 0, self.eps, cabi.FFT_CUFFT
+            d.algo, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, 0, self.eps, cabi.FFT_AUTO     # fused x-update for 2^k sizes
             d.xupdate, d.eps_delta = cabi.X_FREQ_DIAG, 0
             self.plan = cabi.NativePlan(d, self.device)
         self.set_constants()
