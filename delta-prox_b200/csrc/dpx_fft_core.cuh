@@ -154,6 +154,47 @@ struct Dft<16, INV> {  // A = 4, B = 4
   }
 };
 
+// radix 3 and 12 = 3 x 4: image sides 3 * 2^k (192 ... 3072; the reference's own test image is 768 x 1024)
+#define DPX_S3 0.86602540378443865f
+template <bool INV>
+DPX_HD float2 w12(int k) {   // exp(-2 pi i k / 12) forward, conj for inverse; k compile-time after unrolling
+  const float c[12] = {1.f, DPX_S3, 0.5f, 0.f, -0.5f, -DPX_S3, -1.f, -DPX_S3, -0.5f, 0.f, 0.5f, DPX_S3};
+  const float s[12] = {0.f, 0.5f, DPX_S3, 1.f, DPX_S3, 0.5f, 0.f, -0.5f, -DPX_S3, -1.f, -DPX_S3, -0.5f};
+  return make_float2(c[k % 12], INV ? s[k % 12] : -s[k % 12]);
+}
+template <bool INV>
+DPX_HD void dft3(float2& a0, float2& a1, float2& a2) {
+  const float2 sm = cadd(a1, a2), df = csub(a1, a2);
+  const float2 t = make_float2(a0.x - 0.5f * sm.x, a0.y - 0.5f * sm.y);
+  const float2 r = make_float2(DPX_S3 * df.x, DPX_S3 * df.y);
+  a0 = cadd(a0, sm);
+  // forward: y1 = t - i r, y2 = t + i r; inverse: swapped
+  const float2 p = make_float2(t.x + r.y, t.y - r.x), q = make_float2(t.x - r.y, t.y + r.x);
+  a1 = INV ? q : p;
+  a2 = INV ? p : q;
+}
+template <bool INV>
+struct Dft<12, INV> {  // A = 3, B = 4: m = 4 m1 + m2, q = q1 + 3 q2
+  static DPX_HD void run(float2 (&a)[12]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 4; ++m2) dft3<INV>(a[m2], a[4 + m2], a[8 + m2]);            // y[m2][q1] in a[4*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 3; ++q1) {
+#pragma unroll
+      for (int m2 = 1; m2 < 4; ++m2) a[4 * q1 + m2] = cmul(a[4 * q1 + m2], w12<INV>(m2 * q1));
+    }
+    float2 o[12];
+#pragma unroll
+    for (int q1 = 0; q1 < 3; ++q1) {
+      float2 y0 = a[4 * q1], y1 = a[4 * q1 + 1], y2 = a[4 * q1 + 2], y3 = a[4 * q1 + 3];
+      dft4<INV>(y0, y1, y2, y3);
+      o[q1] = y0; o[q1 + 3] = y1; o[q1 + 6] = y2; o[q1 + 9] = y3;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = o[i];
+  }
+};
+
 // ---- tile geometry ------------------------------------------------------------------------------------
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 

@@ -23,10 +23,16 @@ DPX_TILE_FOR(512, 8, 8, 8)
 DPX_TILE_FOR(1024, 16, 8, 8)
 DPX_TILE_FOR(2048, 16, 16, 8)
 DPX_TILE_FOR(4096, 16, 16, 16)
+DPX_TILE_FOR(192, 12, 4, 4)        // 3 * 2^k sides: radix-12 first pass
+DPX_TILE_FOR(384, 12, 8, 4)
+DPX_TILE_FOR(768, 12, 8, 8)
+DPX_TILE_FOR(1536, 12, 16, 8)
+DPX_TILE_FOR(3072, 12, 16, 16)
 #undef DPX_TILE_FOR
 
 inline bool size_supported(int n) {
-  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
+  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 192 || n == 384 ||
+         n == 768 || n == 1536 || n == 3072;
 }
 
 // calls f(std::integral_constant<int, N>{}) for the matching supported N; returns false if unsupported
@@ -40,6 +46,11 @@ inline bool dispatch_size(int n, F&& f) {
     case 1024: f(std::integral_constant<int, 1024>{}); return true;
     case 2048: f(std::integral_constant<int, 2048>{}); return true;
     case 4096: f(std::integral_constant<int, 4096>{}); return true;
+    case 192: f(std::integral_constant<int, 192>{}); return true;
+    case 384: f(std::integral_constant<int, 384>{}); return true;
+    case 768: f(std::integral_constant<int, 768>{}); return true;
+    case 1536: f(std::integral_constant<int, 1536>{}); return true;
+    case 3072: f(std::integral_constant<int, 3072>{}); return true;
     default: return false;
   }
 }

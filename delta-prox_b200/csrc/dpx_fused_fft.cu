@@ -244,7 +244,7 @@ class FusedEngine final : public FftEngine {
 int make_fused_engine(const Geom& g, FftEngine** out) {
   *out = nullptr;
   if (!fused::size_supported(g.H) || !fused::size_supported(g.W)) {
-    set_error("fused FFT engine: shape [%d x %d] not supported (power-of-two sides in 64..4096)", g.H, g.W);
+    set_error("fused FFT engine: shape [%d x %d] not supported (sides 2^k in 64..4096 or 3*2^k in 192..3072)", g.H, g.W);
     return DPX_ERR_INVALID;
   }
   FusedEngine* e = new (std::nothrow) FusedEngine();

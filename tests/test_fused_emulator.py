@@ -68,7 +68,8 @@ def rel(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
-@pytest.mark.parametrize("H,W,method", [(64, 64, "admm"), (64, 128, "admm"), (128, 64, "hqs"), (256, 64, "admm")])
+@pytest.mark.parametrize("H,W,method", [(64, 64, "admm"), (64, 128, "admm"), (128, 64, "hqs"), (256, 64, "admm"),
+                                        (192, 64, "admm"), (64, 384, "hqs")])          # 3 * 2^k sides: radix-12 first pass
 def test_fused_kernels_match_oracle(emu, H, W, method):
     g = torch.Generator().manual_seed(H + W)
     B, Cc, T = 2, 1 if H > 64 else 3, 4          # the reference's OTF builder only handles C in {1, 3}
@@ -86,7 +87,8 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
         assert rel(u[0], want[2][0].numpy()) < 5e-5 and rel(u[1], want[2][1].numpy()) < 5e-5
 
 
-@pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm")])   # H = 1024: k_col_tma
+@pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm"),      # H = 1024: k_col_tma
+                                        (192, 192, "admm")])
 def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     """One psi term: the in-place register path of k_row (template SINGLE)."""
     g = torch.Generator().manual_seed(H * 3 + W)
