@@ -116,8 +116,11 @@ class FFDNetColorDenoiser(Denoiser):
         if self.precision == "bf16" and wants_grad:
             # training (unrolled solver, BASELINE config 5): the tcgen05 forward has no backward yet, so the tape runs
             # through the framework's convolutions with bf16 operands / fp32 accumulation
+            if not getattr(self, "_nhwc", False):          # NHWC weights: cuDNN's tensor-core kernels for forward, dgrad and wgrad
+                self.model.to(memory_format=torch.channels_last)
+                self._nhwc = True
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                return self.model(x, sigma).float()
+                return self.model(x.contiguous(memory_format=torch.channels_last), sigma).float().contiguous()
         if self.precision == "bf16":
             if self._native is None or self._native.device != x.device:
                 self._native = NativeFFDNet(self.model, x.device)
