@@ -83,6 +83,15 @@ SIGNATURES = {
     "dpx_csmri_prox": (_I, [_VP, _VP, _VP, _I, _VP, _I, _F, _VP, _I, _I, _I, _I, _VP]),
     "dpx_real_to_complex": (_I, [_VP, _VP, _SZ, _VP]),
     "dpx_complex_real": (_I, [_VP, _VP, _SZ, _VP]),
+    "dpx_c2c": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "dpx_cmul": (_I, [_VP, _VP, _VP, _SZ, _SZ, _I, _F, _VP]),
+    "dpx_cmul_reduce": (_I, [_VP, _VP, _VP, _SZ, _I, _F, _VP]),
+    "dpx_doe_field": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "dpx_doe_field_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "dpx_abs2_pool": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _VP]),
+    "dpx_abs2_pool_backward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
+    "dpx_normalize_sum": (_I, [_VP, _VP, _VP, _SZ, _VP]),
+    "dpx_normalize_sum_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "dpx_solve_host": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dpx_resid_reduce": (_I, [_VP, _VP, _I, _I, _VP]),
 }

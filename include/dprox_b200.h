@@ -249,6 +249,34 @@ int dpx_csmri_prox(const float* v, const float* y, const float* mask, int mask_b
 int dpx_real_to_complex(const float* x, float* out, size_t n, void* stream);
 int dpx_complex_real(const float* z, float* out, size_t n, void* stream);
 
+/* ---- DOE optics forward model feeding the unrolled solver (contrib/optic/{common,doe_model}.py) --------
+ * Building blocks with their backward counterparts (the reference differentiates the pipeline by autograd).  Complex
+ * arrays are complex64 (interleaved re,im). */
+/* batched 2-D C2C transform of `planes` [H,W] arrays, unnormalised in both directions (torch.fft.fft2 / ifft2 * H*W);
+ * its adjoint is the opposite direction.  FresnelPropagator.forward common.py:155-164, img_psf_conv common.py:107-110. */
+int dpx_c2c(const float* in, float* out, int planes, int height, int width, int inverse, void* stream);
+/* out[i] = scale * a[i] * b[i mod n_b] (b conjugated if conj_b): transfer-function / OTF products with a broadcast factor;
+ * dpx_cmul_reduce gives the gradient of that broadcast factor, out[j] = scale * sum_k g[k n_b + j] conj(a[k n_b + j]). */
+int dpx_cmul(const float* a, const float* b, float* out, size_t n_a, size_t n_b, int conj_b, float scale, void* stream);
+int dpx_cmul_reduce(const float* g, const float* a, float* out, size_t n_b, int batch, float scale, void* stream);
+/* field[l] = aperture * exp(i coef[l] h^2) on the N x N wavefront, zero-padded by `pad` on every side
+ * (HeightMap.get_phase_profile doe_model.py:37-51 with coef[l] = k_l * (n_l - 1); aperture and padding of
+ * RGBCollimator.get_psf :103-104 / FresnelPropagator.forward common.py:156-157).  h: [N,N], field: [L, N+2pad, N+2pad]. */
+int dpx_doe_field(const float* h_sqrt, const float* coef, const float* aperture, float* field, int n_lambda, int n, int pad,
+                  void* stream);
+int dpx_doe_field_backward(const float* h_sqrt, const float* coef, const float* aperture, const float* g_field, float* g_h,
+                           int n_lambda, int n, int pad, void* stream);
+/* out[l] = scale * avg_pool_factor(|crop_pad(field[l])|^2): intensity + area_downsampling (doe_model.py:106-107,
+ * common.py:27-44).  field: [L, N+2pad, N+2pad] complex, out: [L, N/factor, N/factor]. */
+int dpx_abs2_pool(const float* field, float* out, int n_lambda, int n, int pad, int factor, float scale, void* stream);
+int dpx_abs2_pool_backward(const float* field, const float* g, float* g_field, int n_lambda, int n, int pad, int factor,
+                           float scale, void* stream);
+/* out = x / sum(x) (psfs / psfs.sum(), doe_model.py:109); sum_out: device scalar kept for the backward
+ * g_x = (g - <g, out>) / sum  (scratch1: device scalar). */
+int dpx_normalize_sum(const float* x, float* out, float* sum_out, size_t n, void* stream);
+int dpx_normalize_sum_backward(const float* g, const float* out, const float* sum, float* scratch1, float* g_x, size_t n,
+                               void* stream);
+
 /* ---- end-to-end host-buffer entry point (the e2e leg of bench.py) -------------------------- */
 /* Copies x0 (HOST, pinned or pageable, [B,C,H,W]) to the device, initialises (v = K x0, u = 0),
  * runs n_iters iterations with HOST schedules rho_host [T] / lam_host [n_psi][T] (scalars per

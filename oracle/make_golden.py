@@ -637,6 +637,37 @@ def unrolled_grads_cg():
     return dict(psf=psf, b=_np(b), x0=_np(x0), wgt=_np(wgt), rhos=_np(rhos), out=_np(out), g_b=_np(b.grad), g_x0=_np(x0.grad),
                 g_rhos=_np(rhos.grad), T=3, cg_iters=60, rtol=1e-7)
 
+# ------------------------------------------------------------------------------------------------
+# §8f-3: DOE optics forward model (contrib/optic): get_psf pipeline + img_psf_conv, values and autograd gradients
+# ------------------------------------------------------------------------------------------------
+
+@case
+def doe_forward_model():
+    from dprox.contrib.optic.doe_model import RGBCollimator
+    from dprox.contrib.optic.common import img_psf_conv
+    N, n = 64, 32
+    kw = dict(sensor_distance=15e-3, refractive_idcs=torch.tensor([1.4648, 1.4599, 1.4568]),
+              wave_lengths=torch.tensor([460, 550, 640]) * 1e-9, patch_size=n, sample_interval=2e-6 * (1496 / N) * 0.25,
+              wave_resolution=(N, N))
+    m = RGBCollimator(**kw)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():                                   # a non-trivial operating point: perturb the Fresnel-lens init
+        m.height_map.height_map_sqrt.mul_(1.0 + 0.05 * torch.rand(1, 1, N, N, generator=g))
+    h0 = m.height_map.height_map_sqrt.detach().clone()
+    wgt = torch.rand(1, 3, n, n, generator=g)
+    psf = m.get_psf()
+    (psf * wgt).sum().backward()
+    out = dict(N=N, n=n, sample_interval=kw["sample_interval"], h0=_np(h0), wgt=_np(wgt), psf=_np(psf),
+               g_h=_np(m.height_map.height_map_sqrt.grad), aperture=_np(m.aperture), H=_np(m.propagator.H))
+    # data formation with a smaller PSF than the image (even pad: the off-by-one quirk) and gradients to both inputs
+    img = torch.rand(2, 3, 40, 40, generator=g).requires_grad_(True)
+    p2 = psf.detach().clone().requires_grad_(True)
+    w2 = torch.rand(2, 3, 40, 40, generator=g)
+    y = img_psf_conv(img, p2, circular=True)
+    (y * w2).sum().backward()
+    out.update(img=_np(img), w2=_np(w2), y=_np(y), g_img=_np(img.grad), g_psf=_np(p2.grad))
+    return out
+
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """cfg5 of BASELINE.json: unrolled 10-iteration ADMM (conv_doe + deep_prior(ffdnet_color, sqrt=True)) with end-to-end
-backward, data-parallel over the ranks of a torchrun job (one process per GPU, NCCL gradient all-reduce of the shared
-trainable parameters).  Shapes follow the reference trainer: batch 2 per GPU, 768x768 images, 748x748 PSF
+backward, fed by the DOE optics forward model (height map -> PSF -> data formation), data-parallel over the ranks of a
+torchrun job (one process per GPU, NCCL gradient all-reduce of the shared trainable parameters).  Shapes follow the reference trainer: batch 2 per GPU, 768x768 images, 748x748 PSF
 (optic/utils.py:158-166, optic/doe_model.py:165).  The x-update forward/backward are native kernels; the denoiser is a
 torch module under bf16 autocast (its tcgen05 forward has no backward yet).  Random (seeded) weights.  Not the headline.
 
@@ -21,7 +21,7 @@ import torch.distributed as dist  # noqa: E402
 import dprox_b200 as dp  # noqa: E402
 from dprox_b200 import dist as ddist  # noqa: E402
 from dprox_b200.denoisers import FFDNetColorDenoiser  # noqa: E402
-from dprox_b200.linop import psf2otf2  # noqa: E402
+from dprox_b200.optics import DOEModelConfig, build_doe_model, img_psf_conv  # noqa: E402
 
 
 def main():
@@ -41,12 +41,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, H, T = args.batch, args.size, args.iters
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    # stand-in for the DOE model: a trainable height-map-sized parameter -> normalised PSF (the optics forward model is §8f-3)
-    torch.manual_seed(0)
-    hm = torch.nn.Parameter(torch.rand(1, 3, args.psf, args.psf, device=dev))
+    # the DOE model of the reference trainer (optic/doe_model.py:156-187): 1496^2 wavefront, Fresnel propagation, 748^2 PSF --
+    # native forward and backward kernels (dprox_b200/optics.py); the trainable height map is ~9 MB
+    doe = build_doe_model(DOEModelConfig(patch_size=args.psf, wave_resolution=(2 * args.psf, 2 * args.psf))).to(dev)
     r0, s0 = dp.log_descent(49, 7.65, T, sigma=7.65 / 255)
     rhos, sigmas = torch.nn.Parameter(r0.to(dev)), torch.nn.Parameter(s0.to(dev))
-    params = [hm, rhos, sigmas]
+    params = [doe.height_map.height_map_sqrt, rhos, sigmas]
     opt = torch.optim.Adam(params, lr=1e-4)
     den = FFDNetColorDenoiser(seed=4, precision=args.precision).to(dev)
     x, y, PSF = dp.Variable(), dp.Placeholder(), dp.Placeholder()
@@ -56,9 +56,8 @@ def main():
 
     def step():
         gt = torch.rand(B, 3, H, H, device=dev, generator=g)
-        psf = hm.abs() / hm.abs().sum(dim=(-2, -1), keepdim=True)
-        otf = psf2otf2(psf, gt.shape)
-        inp = torch.real(torch.fft.ifftn(otf * torch.fft.fftn(gt, dim=[-2, -1]), dim=[-2, -1])).float()
+        psf = doe.get_psf()                                   # height map -> phase -> Fresnel -> intensity -> 2x area pool -> / sum
+        inp = img_psf_conv(gt, psf, circular=True)            # data formation (carries d/d height map)
         inp = inp + (7.65 / 255) * torch.randn(gt.shape, device=dev, generator=g)
         y.value, PSF.value = inp, psf.detach()
         out = solver.solve(x0=inp, rhos=rhos, lams={reg_term: sigmas})
