@@ -307,12 +307,18 @@ def run_native(args):
         main = torch.cuda.current_stream(dev)
         start = torch.cuda.Event()
         start.record(main)
-        for sc, yc, bh, oh, st in chunks:
+        done = []
+        for k, (sc, yc, bh, oh, st) in enumerate(chunks):
             st.wait_event(start)
             with torch.cuda.stream(st):
                 bd = bh.to(dev, non_blocking=True)             # H2D of this chunk's measurements (pinned)
-                yc.value = bd                                  # new measurements -> K^T b re-hoisted on the same plan
+                if args.e2e_wave and k >= args.e2e_wave:
+                    st.wait_event(done[k - args.e2e_wave])     # at most `e2e_wave` sub-batches iterate concurrently
+                yc.value = bd                                  # new measurements -> F(K^T b) re-hoisted on the same plan
                 xs = sc.solve(x0=bd, rhos=rhos, lams=lams, max_iter=T)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
                 oh.copy_(xs, non_blocking=True)                # D2H of the result
                 bd.record_stream(st)
                 xs.record_stream(st)
@@ -393,6 +399,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="experiments: resident-input number only (not a bench line)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")
+    ap.add_argument("--e2e-wave", type=int, default=0, help="max sub-batches iterating concurrently (0 = all)")
     ap.add_argument("--e2e-priority", type=int, default=0, help="1: earlier sub-batches on higher-priority streams (measured: no gain)")
     args = ap.parse_args()
     if args.impl == "reference":
