@@ -195,6 +195,73 @@ struct Dft<12, INV> {  // A = 3, B = 4: m = 4 m1 + m2, q = q1 + 3 q2
   }
 };
 
+// radix 5, 10 = 5 x 2 and 20 = 5 x 4: image sides 5 * 2^k (320 ... 2560)
+template <bool INV>
+DPX_HD float2 w20(int k) {   // exp(-2 pi i k / 20) forward, conj for inverse; k compile-time after unrolling
+  const float c[20] = {1.f, 0.95105651629515357f, 0.80901699437494742f, 0.58778525229247313f, 0.30901699437494742f, 0.f,
+                       -0.30901699437494742f, -0.58778525229247313f, -0.80901699437494742f, -0.95105651629515357f, -1.f,
+                       -0.95105651629515357f, -0.80901699437494742f, -0.58778525229247313f, -0.30901699437494742f, 0.f,
+                       0.30901699437494742f, 0.58778525229247313f, 0.80901699437494742f, 0.95105651629515357f};
+  const float s[20] = {0.f, 0.30901699437494742f, 0.58778525229247313f, 0.80901699437494742f, 0.95105651629515357f, 1.f,
+                       0.95105651629515357f, 0.80901699437494742f, 0.58778525229247313f, 0.30901699437494742f, 0.f,
+                       -0.30901699437494742f, -0.58778525229247313f, -0.80901699437494742f, -0.95105651629515357f, -1.f,
+                       -0.95105651629515357f, -0.80901699437494742f, -0.58778525229247313f, -0.30901699437494742f};
+  return make_float2(c[k % 20], INV ? s[k % 20] : -s[k % 20]);
+}
+template <bool INV>
+DPX_HD void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
+  const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f, S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;
+  const float2 t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+  const float2 p1 = make_float2(a0.x + C1 * t1.x + C2 * t2.x, a0.y + C1 * t1.y + C2 * t2.y);
+  const float2 p2 = make_float2(a0.x + C2 * t1.x + C1 * t2.x, a0.y + C2 * t1.y + C1 * t2.y);
+  const float2 q1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
+  const float2 q2 = make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+  a0 = cadd(a0, cadd(t1, t2));
+  // forward: y1 = p1 - i q1, y4 = p1 + i q1, y2 = p2 - i q2, y3 = p2 + i q2 (-i q = (q.y, -q.x)); inverse: conjugate roles
+  const float2 m1 = make_float2(p1.x + q1.y, p1.y - q1.x), n1 = make_float2(p1.x - q1.y, p1.y + q1.x);
+  const float2 m2 = make_float2(p2.x + q2.y, p2.y - q2.x), n2 = make_float2(p2.x - q2.y, p2.y + q2.x);
+  a1 = INV ? n1 : m1; a4 = INV ? m1 : n1;
+  a2 = INV ? n2 : m2; a3 = INV ? m2 : n2;
+}
+template <bool INV>
+struct Dft<10, INV> {  // A = 5, B = 2: m = 2 m1 + m2, q = q1 + 5 q2
+  static DPX_HD void run(float2 (&a)[10]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2) dft5<INV>(a[m2], a[2 + m2], a[4 + m2], a[6 + m2], a[8 + m2]);      // y[m2][q1] in a[2*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 5; ++q1) a[2 * q1 + 1] = cmul(a[2 * q1 + 1], w20<INV>(2 * q1));
+    float2 o[10];
+#pragma unroll
+    for (int q1 = 0; q1 < 5; ++q1) {
+      o[q1] = cadd(a[2 * q1], a[2 * q1 + 1]);
+      o[q1 + 5] = csub(a[2 * q1], a[2 * q1 + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = o[i];
+  }
+};
+template <bool INV>
+struct Dft<20, INV> {  // A = 5, B = 4: m = 4 m1 + m2, q = q1 + 5 q2
+  static DPX_HD void run(float2 (&a)[20]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 4; ++m2) dft5<INV>(a[m2], a[4 + m2], a[8 + m2], a[12 + m2], a[16 + m2]);    // y[m2][q1] in a[4*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 5; ++q1) {
+#pragma unroll
+      for (int m2 = 1; m2 < 4; ++m2) a[4 * q1 + m2] = cmul(a[4 * q1 + m2], w20<INV>(m2 * q1));
+    }
+    float2 o[20];
+#pragma unroll
+    for (int q1 = 0; q1 < 5; ++q1) {
+      float2 y0 = a[4 * q1], y1 = a[4 * q1 + 1], y2 = a[4 * q1 + 2], y3 = a[4 * q1 + 3];
+      dft4<INV>(y0, y1, y2, y3);
+      o[q1] = y0; o[q1 + 5] = y1; o[q1 + 10] = y2; o[q1 + 15] = y3;
+    }
+#pragma unroll
+    for (int i = 0; i < 20; ++i) a[i] = o[i];
+  }
+};
+
 // ---- tile geometry ------------------------------------------------------------------------------------
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 

@@ -28,11 +28,15 @@ DPX_TILE_FOR(384, 12, 8, 4)
 DPX_TILE_FOR(768, 12, 8, 8)
 DPX_TILE_FOR(1536, 12, 16, 8)
 DPX_TILE_FOR(3072, 12, 16, 16)
+DPX_TILE_FOR(320, 10, 8, 4)        // 5 * 2^k sides: radix-10 / radix-20 first pass
+DPX_TILE_FOR(640, 10, 8, 8)
+DPX_TILE_FOR(1280, 20, 8, 8)
+DPX_TILE_FOR(2560, 20, 16, 8)
 #undef DPX_TILE_FOR
 
 inline bool size_supported(int n) {
   return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 192 || n == 384 ||
-         n == 768 || n == 1536 || n == 3072;
+         n == 768 || n == 1536 || n == 3072 || n == 320 || n == 640 || n == 1280 || n == 2560;
 }
 
 // calls f(std::integral_constant<int, N>{}) for the matching supported N; returns false if unsupported
@@ -51,6 +55,10 @@ inline bool dispatch_size(int n, F&& f) {
     case 768: f(std::integral_constant<int, 768>{}); return true;
     case 1536: f(std::integral_constant<int, 1536>{}); return true;
     case 3072: f(std::integral_constant<int, 3072>{}); return true;
+    case 320: f(std::integral_constant<int, 320>{}); return true;
+    case 640: f(std::integral_constant<int, 640>{}); return true;
+    case 1280: f(std::integral_constant<int, 1280>{}); return true;
+    case 2560: f(std::integral_constant<int, 2560>{}); return true;
     default: return false;
   }
 }
@@ -133,7 +141,9 @@ struct Driver {
         const size_t rsm = RowSmem<TW>::BYTES;
         auto row = [&](auto mode) {
           constexpr int MODE = decltype(mode)::value;
-          if (psi.n == 1) be.template row<TW, MODE, true>(rgrid, rsm, rp);
+          // the once-per-solve first pass only exists in its general (accumulating) form: fewer kernels to compile
+          if constexpr (MODE == ROW_FIRST) be.template row<TW, MODE, false>(rgrid, rsm, rp);
+          else if (psi.n == 1) be.template row<TW, MODE, true>(rgrid, rsm, rp);
           else be.template row<TW, MODE, false>(rgrid, rsm, rp);
         };
         row(std::integral_constant<int, ROW_FIRST>{});
@@ -169,9 +179,10 @@ struct Driver {
       dispatch_size(H, [&](auto hn) {
         using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
-        if (fb_std) be.template packz_fb<TH, TW>(fb_std, fbz, (B / 2) * C, C, H, W);
-        if (dq_std) be.template packz_dq<TH, TW>(dq_std, dqz, C, H, W);
-        if (dpsi_std) be.template packz_dq<TH, TW>(dpsi_std, dpsz, C, H, W);
+        const PackGeom q{H, W, TH::RA, TH::RB, TH::RC, TW::RA, TW::RB, TW::RC};
+        if (fb_std) be.packz_fb(fb_std, fbz, (B / 2) * C, C, q);
+        if (dq_std) be.packz_dq(dq_std, dqz, C, q);
+        if (dpsi_std) be.packz_dq(dpsi_std, dpsz, C, q);
       });
     });
   }
@@ -195,7 +206,8 @@ struct Driver {
         const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2);
         auto row = [&](auto mode) {
           constexpr int MODE = decltype(mode)::value;
-          if (psi.n == 1) be.template rowz<TW, MODE, true>(rgrid, rsm, rp);
+          if constexpr (MODE == ROW_FIRST) be.template rowz<TW, MODE, false>(rgrid, rsm, rp);
+          else if (psi.n == 1) be.template rowz<TW, MODE, true>(rgrid, rsm, rp);
           else be.template rowz<TW, MODE, false>(rgrid, rsm, rp);
         };
         row(std::integral_constant<int, ROW_FIRST>{});

@@ -83,18 +83,16 @@ struct CudaBackend {
     k_rowz_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
     after();
   }
-  template <class TH, class TW>
-  void packz_fb(const float2* src, float2* dst, int pairs, int C, int H, int W) {
+  void packz_fb(const float2* src, float2* dst, int pairs, int C, const PackGeom& q) {
     if (rc) return;
-    const size_t total = (size_t)pairs * H * W;
-    k_packz_fb<TH, TW><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, pairs, C, H, W);
+    const size_t total = (size_t)pairs * q.H * q.W;
+    k_packz_fb<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, pairs, C, q);
     after();
   }
-  template <class TH, class TW>
-  void packz_dq(const float* src, float* dst, int C, int H, int W) {
+  void packz_dq(const float* src, float* dst, int C, const PackGeom& q) {
     if (rc) return;
-    const size_t total = (size_t)C * H * W;
-    k_packz_dq<TH, TW><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, C, H, W);
+    const size_t total = (size_t)C * q.H * q.W;
+    k_packz_dq<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, C, q);
     after();
   }
   template <class TH, typename V>
@@ -244,7 +242,7 @@ class FusedEngine final : public FftEngine {
 int make_fused_engine(const Geom& g, FftEngine** out) {
   *out = nullptr;
   if (!fused::size_supported(g.H) || !fused::size_supported(g.W)) {
-    set_error("fused FFT engine: shape [%d x %d] not supported (sides 2^k in 64..4096 or 3*2^k in 192..3072)", g.H, g.W);
+    set_error("fused FFT engine: shape [%d x %d] not supported (sides 2^k in 64..4096, 3*2^k in 192..3072 or 5*2^k in 320..2560)", g.H, g.W);
     return DPX_ERR_INVALID;
   }
   FusedEngine* e = new (std::nothrow) FusedEngine();

@@ -1149,11 +1149,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, i
 }
 
 // Constant packing for the pair engine (cold path).  Standard R2C half spectra -> full-spectrum records of pair pp in
-// k_col's per-thread record order, columns in the row transform's digit-reversed order:
+// k_col's per-thread record order, columns in the row transform's storage order:
 //   fbz = F(K^T b)_A + i F(K^T b)_B   (bins k > W/2 by Hermitian symmetry),  dqz = sum|OTF|^2 (even symmetry).
-template <class TH, class TW>
-__global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, int H, int W) {
-  constexpr int RC = TH::RC;
+// The tile radices are run-time arguments here: templating on (TH, TW) would instantiate one kernel per H x W combination.
+struct PackGeom {
+  int H, W;
+  int hRA, hRB, hRC;             // radices of the column (H) transform
+  int wRA, wRB, wRC;             // radices of the row (W) transform
+};
+DPX_HD int freq_of_pos_rt(int p, int N, int RA, int RB) {   // fft::Tile::freq_of_pos with run-time radices
+  const int MA = N / RA, MB = MA / RB;
+  return p / MA + RA * ((p % MA) / MB) + RA * RB * (p % MB);
+}
+__global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, PackGeom q) {
+  const int H = q.H, W = q.W, RC = q.hRC;
   const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
   const size_t total = (size_t)pairs * G * H * CG;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1166,7 +1175,8 @@ __global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ 
   const int pp = (int)(r / G);
   const int m = mg * 2 + lane, c = task % CG, blk = task / CG;
   const int sc = g * CG + c;                          // storage column -> digit-reversed position -> frequency
-  const int h = TH::freq_of_pos(blk * RC + m), k = TW::freq_of_pos((sc % (W / TW::RC)) * TW::RC + sc / (W / TW::RC));
+  const int h = freq_of_pos_rt(blk * RC + m, H, q.hRA, q.hRB);
+  const int k = freq_of_pos_rt((sc % (W / q.wRC)) * q.wRC + sc / (W / q.wRC), W, q.wRA, q.wRB);
   const int bq = pp / C, pA = 2 * bq * C + (pp - bq * C), pB = pA + C;
   float2 fa, fb;
   if (k < Wc) {
@@ -1179,9 +1189,8 @@ __global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ 
   }
   dst[i] = make_float2(fa.x - fb.y, fa.y + fb.x);
 }
-template <class TH, class TW>
-__global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
-  constexpr int RC = TH::RC;
+__global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, PackGeom q) {
+  const int H = q.H, W = q.W, RC = q.hRC;
   const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
   const size_t total = (size_t)C * G * H * CG;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1194,7 +1203,8 @@ __global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ ds
   const int ch = (int)(r / G);
   const int m = mg * 4 + lane, c = task % CG, blk = task / CG;
   const int sc = g * CG + c;
-  const int h = TH::freq_of_pos(blk * RC + m), k = TW::freq_of_pos((sc % (W / TW::RC)) * TW::RC + sc / (W / TW::RC));
+  const int h = freq_of_pos_rt(blk * RC + m, H, q.hRA, q.hRB);
+  const int k = freq_of_pos_rt((sc % (W / q.wRC)) * q.wRC + sc / (W / q.wRC), W, q.wRA, q.wRB);
   dst[i] = k < Wc ? src[((size_t)ch * H + h) * Wc + k] : src[((size_t)ch * H + (H - h) % H) * Wc + (W - k)];
 }
 

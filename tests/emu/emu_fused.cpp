@@ -41,15 +41,13 @@ struct EmuBackend {
   void rowz_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz_mid_persist<TW>(p, n_tiles); });
   }
-  template <class TH, class TW>
-  void packz_fb(const float2* src, float2* dst, int pairs, int C, int H, int W) {
-    const size_t total = (size_t)pairs * H * W;
-    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_fb<TH, TW>(src, dst, pairs, C, H, W); });
+  void packz_fb(const float2* src, float2* dst, int pairs, int C, PackGeom q) {
+    const size_t total = (size_t)pairs * q.H * q.W;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_fb(src, dst, pairs, C, q); });
   }
-  template <class TH, class TW>
-  void packz_dq(const float* src, float* dst, int C, int H, int W) {
-    const size_t total = (size_t)C * H * W;
-    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_dq<TH, TW>(src, dst, C, H, W); });
+  void packz_dq(const float* src, float* dst, int C, PackGeom q) {
+    const size_t total = (size_t)C * q.H * q.W;
+    emu::launch(dim3((unsigned)((total + 255) / 256)), dim3(256), 0, [=]() { k_packz_dq(src, dst, C, q); });
   }
   template <class TH, typename V>
   void pack(const V* src, V* dst, int planes, int H, int W, int G, V zero) {

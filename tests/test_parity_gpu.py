@@ -410,10 +410,10 @@ def test_fused_engine_matches_oracle(dp, H, W, method):
     assert rel(outs[2][0], outs[1][0]) < 5e-6
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 2048, 2048), (2, 768, 1024), (2, 1536, 384), (1, 192, 3072)])
+@pytest.mark.parametrize("B,H,W", [(1, 2048, 2048), (2, 768, 1024), (2, 1536, 384), (1, 192, 3072), (2, 1280, 640), (1, 320, 2560)])
 def test_fused_engine_headline_size_vs_cufft(dp, B, H, W):
-    """5 ADMM iterations: the fused engine (plane pairs for B = 2; radix-12 first pass for the 3 * 2^k sides -- 768 x 1024 is
-    the reference's own test image, tests/test_algorithms.py:6-20) and the cuFFT engine agree to fp32 round-off."""
+    """5 ADMM iterations: the fused engine (plane pairs for B = 2; radix-12 / radix-10 / radix-20 first pass for the 3 * 2^k and 5 * 2^k
+    sides -- 768 x 1024 is the reference's own test image, tests/test_algorithms.py:6-20) and the cuFFT engine agree to fp32 round-off."""
     g = torch.Generator(device="cuda").manual_seed(3)
     b = torch.rand(B, 3, H, W, device="cuda", generator=g)
     psf = orc.point_spread_function(15, 5)
