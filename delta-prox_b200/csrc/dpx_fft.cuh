@@ -24,6 +24,8 @@ class FftEngine {
     return DPX_OK;
   }
   virtual void reset_constants() {}
+  // hint: the quadratic diagonal is the same for every channel (grey PSF) -> planes may pair across channels
+  virtual void set_channel_shared(bool shared) { (void)shared; }
   // per-channel diagonal of the non-identity psi linops, standard layout [C,H,Wc] (nullptr = none)
   virtual void set_dpsi(const float* dpsi_std) { (void)dpsi_std; }
   // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true

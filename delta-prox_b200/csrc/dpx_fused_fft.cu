@@ -136,7 +136,9 @@ class FusedEngine final : public FftEngine {
   size_t workspace_bytes() const override { return bytes_ + (inner_ ? inner_->workspace_bytes() : 0); }
   void destroy() override {
     if (inner_) inner_->destroy();
-    cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(dpsp_); cudaFree(tw_h_); cudaFree(tw_w_);
+    cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(dpsp_); cudaFree(S1_); cudaFree(fbp1_); cudaFree(dqp1_);
+    cudaFree(tw_h_); cudaFree(tw_w_);
+    if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_join_); }
     delete this;
   }
   bool fused() const override { return true; }
@@ -153,11 +155,42 @@ class FusedEngine final : public FftEngine {
     return DPX_OK;
   }
 
-  // packs whatever changed, in the layout of the engine variant selected for this call; returns whether pairs are used
-  int prepare(const PsiPack& psi, int rho_stride, cudaStream_t s, CudaBackend& be, bool* pairs_out) {
+  // FLAT mode runs the odd last plane on a side stream, concurrently with the pairs (small grids: they fill each other's tails)
+  int fork_side(cudaStream_t s) {
+    if (!side_) {
+      DPX_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+      DPX_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+      DPX_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+    }
+    DPX_CUDA(cudaEventRecord(ev_fork_, s));
+    DPX_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
+    return DPX_OK;
+  }
+  int join_side(cudaStream_t s) {
+    DPX_CUDA(cudaEventRecord(ev_join_, side_));
+    DPX_CUDA(cudaStreamWaitEvent(s, ev_join_, 0));
+    return DPX_OK;
+  }
+
+  void set_channel_shared(bool shared) override { if (shared != channel_shared_) { channel_shared_ = shared; fb_dirty_ = dq_dirty_ = true; } }
+
+  enum Mode { PLANES = 0, PAIRS = 1, FLAT = 2 };
+  // PLANES: half-spectrum engine.  PAIRS: planes (b, ch) + i (b+1, ch), even batch.  FLAT: the diagonal is shared by all
+  // channels (grey PSF), so ANY two planes pair: planes (2k, 2k+1) of the flat plane list ride the pair engine as a
+  // (B' = P_even, C' = 1) problem and an odd last plane goes through the half-spectrum engine on its own (B' = C' = 1) --
+  // this is what a single RGB image (B = 1, C = 3) gets.
+  Mode select_mode(const PsiPack& psi, int rho_stride) const {
+    if (!pairs_enabled_) return PLANES;
+    if (Driver<CudaBackend>::pairs_ok(g_.B, dq_batch_, rho_stride, psi)) return PAIRS;
+    if (channel_shared_ && !dpsi_std_ && g_.P >= 2 && Driver<CudaBackend>::pairs_ok(2, dq_batch_, rho_stride, psi)) return FLAT;
+    return PLANES;
+  }
+
+  // packs whatever changed, in the layout of the engine variant selected for this call
+  int prepare(const PsiPack& psi, int rho_stride, cudaStream_t s, CudaBackend& be, Mode* mode_out) {
     Driver<CudaBackend> drv(be);
-    const bool pairs = pairs_enabled_ && Driver<CudaBackend>::pairs_ok(g_.B, dq_batch_, rho_stride, psi);
-    if (pairs != packed_pairs_) { fb_dirty_ = dq_dirty_ = dpsi_dirty_ = true; packed_pairs_ = pairs; }
+    const Mode mode = select_mode(psi, rho_stride);
+    if (mode != packed_mode_) { fb_dirty_ = dq_dirty_ = dpsi_dirty_ = true; packed_mode_ = mode; }
     if (dpsi_std_ && !dpsp_) {
       const size_t np = std::max(Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W), packed_elems(g_.C, g_.H, g_.W));
       DPX_CUDA(cudaMalloc(&dpsp_, np * sizeof(float)));
@@ -165,7 +198,7 @@ class FusedEngine final : public FftEngine {
       dpsi_dirty_ = true;
     }
     const int Cd = dq_batch_ > 1 ? g_.P : g_.C;
-    const size_t nd = pairs ? Driver<CudaBackend>::pair_elems(g_.C, g_.H, g_.W) : packed_elems(Cd, g_.H, g_.W);
+    const size_t nd = mode == PLANES ? packed_elems(Cd, g_.H, g_.W) : Driver<CudaBackend>::pair_elems(mode == FLAT ? 1 : g_.C, g_.H, g_.W);
     if (dqp_cap_ < nd) {
       cudaFree(dqp_); dqp_ = nullptr;
       DPX_CUDA(cudaMalloc(&dqp_, nd * sizeof(float)));
@@ -173,14 +206,47 @@ class FusedEngine final : public FftEngine {
       dqp_cap_ = nd;
       dq_dirty_ = true;
     }
+    if (mode == FLAT && (g_.P % 2) && !S1_) {            // the odd last plane: its own spectrum and packed constants
+      const size_t n1 = s_elems(1, g_.H, g_.W);
+      DPX_CUDA(cudaMalloc(&S1_, n1 * sizeof(float2)));
+      DPX_CUDA(cudaMemsetAsync(S1_, 0, n1 * sizeof(float2), s));
+      DPX_CUDA(cudaMalloc(&fbp1_, n1 * sizeof(float2)));
+      DPX_CUDA(cudaMalloc(&dqp1_, packed_elems(1, g_.H, g_.W) * sizeof(float)));
+      bytes_ += 2 * n1 * sizeof(float2) + packed_elems(1, g_.H, g_.W) * sizeof(float);
+      fb_dirty_ = dq_dirty_ = true;
+    }
     if (dq_dirty_ && !dq_std_) DPX_CUDA(cudaMemsetAsync(dqp_, 0, nd * sizeof(float), s));
     if (fb_dirty_ && !fb_std_) DPX_CUDA(cudaMemsetAsync(fbp_, 0, s_elems(g_.P, g_.H, g_.W) * sizeof(float2), s));
     const float* dps = (dpsi_dirty_ && dpsi_std_) ? dpsi_std_ : nullptr;
-    if (pairs) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_, dps, dpsp_);
-    else drv.pack_constants(g_.P, Cd, g_.H, g_.W, fb_dirty_ ? fb_std_ : nullptr, fbp_, dq_dirty_ ? dq_std_ : nullptr, dqp_, g_.C, dps, dpsp_);
+    const float2* fbs = fb_dirty_ ? fb_std_ : nullptr;
+    const float* dqs = dq_dirty_ ? dq_std_ : nullptr;
+    if (mode == PAIRS) drv.pack_constants_pairs(g_.B, g_.C, g_.H, g_.W, fbs, fbp_, dqs, dqp_, dps, dpsp_);
+    else if (mode == PLANES) drv.pack_constants(g_.P, Cd, g_.H, g_.W, fbs, fbp_, dqs, dqp_, g_.C, dps, dpsp_);
+    else {
+      const int Pe = g_.P - g_.P % 2;
+      drv.pack_constants_pairs(Pe, 1, g_.H, g_.W, fbs, fbp_, dqs, dqp_);
+      if (g_.P % 2) {
+        if (fb_dirty_ && !fb_std_) DPX_CUDA(cudaMemsetAsync(fbp1_, 0, s_elems(1, g_.H, g_.W) * sizeof(float2), s));
+        if (dq_dirty_ && !dq_std_) DPX_CUDA(cudaMemsetAsync(dqp1_, 0, packed_elems(1, g_.H, g_.W) * sizeof(float), s));
+        drv.pack_constants(1, 1, g_.H, g_.W, fbs ? fbs + (size_t)Pe * g_.splane : nullptr, fbp1_, dqs, dqp1_);
+      }
+    }
     fb_dirty_ = dq_dirty_ = dpsi_dirty_ = false;
-    *pairs_out = pairs;
+    *mode_out = mode;
     return DPX_OK;
+  }
+
+  // the last plane of an odd plane count as a (B = C = 1) problem of its own: every per-element pointer shifted to it
+  PsiPack last_plane(const PsiPack& psi, float** x) const {
+    const size_t off = (size_t)(g_.P - 1) * g_.plane;
+    PsiPack q = psi;
+    for (int i = 0; i < q.n; ++i) {
+      if (q.t[i].v) q.t[i].v += off;
+      if (q.t[i].u) q.t[i].u += off;
+      if (q.t[i].off) q.t[i].off += off;
+    }
+    if (*x) *x += off;
+    return q;
   }
 
   int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2*, const float*, int, float wid,
@@ -188,15 +254,30 @@ class FusedEngine final : public FftEngine {
     CudaBackend be{s};
     be.n_persist = persist_ctas_;
     be.n_sm = col_tma_sms_;
-    bool pairs = false;
-    int rc = prepare(psi, rho_stride, s, be, &pairs);
+    Mode mode = PLANES;
+    int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
     Driver<CudaBackend> drv(be);
-    if (pairs)
+    if (mode == PAIRS)
       drv.iterate_pairs(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, wid, eps, rho, it0, n_iters, tw_h_, tw_w_);
-    else
+    else if (mode == PLANES)
       drv.iterate(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it0, n_iters,
                   tw_h_, tw_w_);
+    else {
+      if (g.P % 2) {
+        rc = fork_side(s);
+        if (rc) return rc;
+        CudaBackend be1{side_};
+        be1.n_persist = persist_ctas_;
+        Driver<CudaBackend> drv1(be1);
+        float* x1 = x;
+        const PsiPack one = last_plane(psi, &x1);
+        drv1.iterate(1, 1, g.H, g.W, S1_, one, hqs ? 1 : 0, x1, fbp1_, dqp1_, 1, wid, eps, rho, 0, it0, n_iters, tw_h_, tw_w_);
+        if (be1.rc) return be1.rc;
+      }
+      drv.iterate_pairs(g.P - g.P % 2, 1, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, wid, eps, rho, it0, n_iters, tw_h_, tw_w_);
+      if (g.P % 2) { rc = join_side(s); if (rc) return rc; }
+    }
     return be.rc;
   }
 
@@ -204,12 +285,22 @@ class FusedEngine final : public FftEngine {
                     int rho_stride, int it, cudaStream_t s) override {
     CudaBackend be{s};
     be.n_sm = col_tma_sms_;
-    bool pairs = false;
-    int rc = prepare(psi, rho_stride, s, be, &pairs);
+    Mode mode = PLANES;
+    int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
     Driver<CudaBackend> drv(be);
-    drv.xupdate(pairs, g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it, tw_h_, tw_w_,
-                dpsi_std_ ? dpsp_ : nullptr);
+    const float* dps = dpsi_std_ ? dpsp_ : nullptr;
+    if (mode != FLAT) {
+      drv.xupdate(mode == PAIRS, g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, dq_batch_, wid, eps, rho, rho_stride, it, tw_h_,
+                  tw_w_, dps);
+    } else {
+      drv.xupdate(true, g.P - g.P % 2, 1, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, 1, wid, eps, rho, 0, it, tw_h_, tw_w_);
+      if (g.P % 2) {
+        float* x1 = x;
+        const PsiPack one = last_plane(psi, &x1);
+        drv.xupdate(false, 1, 1, g.H, g.W, S1_, one, hqs ? 1 : 0, x1, fbp1_, dqp1_, 1, wid, eps, rho, 0, it, tw_h_, tw_w_);
+      }
+    }
     return be.rc;
   }
 
@@ -234,7 +325,12 @@ class FusedEngine final : public FftEngine {
   float* dpsp_ = nullptr;
   bool dpsi_dirty_ = false;
   bool fb_dirty_ = true, dq_dirty_ = true, dq_set_ = false;
-  bool packed_pairs_ = false, pairs_enabled_ = true;
+  bool pairs_enabled_ = true, channel_shared_ = false;
+  Mode packed_mode_ = PLANES;
+  float2 *S1_ = nullptr, *fbp1_ = nullptr;
+  float* dqp1_ = nullptr;
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
 };
 
 }  // namespace

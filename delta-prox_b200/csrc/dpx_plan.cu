@@ -279,6 +279,13 @@ int dpx_plan_set_rhs(dpx_plan* p, const float* ktb, void* stream) {
   return p->fft->set_constants(p->fb, nullptr, p->dq_batch, s);      // engines re-pack F(K^T b) only
 }
 
+int dpx_plan_set_hint(dpx_plan* p, int hint, int value) {
+  DPX_REQUIRE(p, "null plan");
+  DPX_REQUIRE(hint == DPX_HINT_CHANNEL_SHARED_DIAG, "unknown hint %d", hint);
+  if (p->fft) p->fft->set_channel_shared(value != 0);
+  return DPX_OK;
+}
+
 int dpx_plan_set_rhs_spectral(dpx_plan* p, const float* b, const float* otf, int otf_batch, float scale, void* stream) {
   DPX_REQUIRE(p && b && otf, "null argument");
   DPX_REQUIRE(p->consts_set, "constants not set yet (call dpx_plan_set_*_constants first)");

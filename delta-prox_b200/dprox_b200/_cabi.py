@@ -11,6 +11,7 @@ from typing import Optional, Sequence
 
 import torch
 
+HINT_CHANNEL_SHARED_DIAG = 1
 ABI_VERSION = 1
 MAX_PSI = 8
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "dpx_plan_workspace_bytes": (_SZ, [_VP]),
     "dpx_plan_set_freq_constants": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "dpx_plan_set_rhs": (_I, [_VP, _VP, _VP]),
+    "dpx_plan_set_hint": (_I, [_VP, _I, _I]),
     "dpx_plan_set_rhs_spectral": (_I, [_VP, _VP, _VP, _I, _F, _VP]),
     "dpx_plan_set_spatial_constants": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dpx_plan_set_psi_offset": (_I, [_VP, _I, _VP, _VP]),

@@ -286,6 +286,11 @@ class NativeEngine(_EngineBase):
                 dpsi = _gram_diag([t for t in spec.psi if t.kind != "identity"], self.shape4, dev, True, include_identity=False)
                 if dpsi is not None and dpsi.shape[0] != 1:
                     raise NotImplementedError("per-sample psi OTFs")
+                # a grey PSF gives every channel the same diagonal: then any two planes can share a complex transform, which
+                # is what lets a single RGB image (odd plane count) use the plane-pair engine.  One comparison per constant set.
+                B, Cc = self.shape4[0], self.shape4[1]
+                shared = dq.shape[0] == 1 and Cc > 1 and B % 2 == 1 and bool((dq[:, 1:] == dq[:, :1]).all())
+                cabi.check(lib.dpx_plan_set_hint(self.plan.handle, cabi.HINT_CHANNEL_SHARED_DIAG, int(shared)), "dpx_plan_set_hint")
                 cabi.check(lib.dpx_plan_set_freq_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0],
                                                            cabi.ptr(dpsi), s), "dpx_plan_set_freq_constants")
             else:

@@ -125,6 +125,11 @@ int dpx_plan_set_freq_constants(dpx_plan* plan, const float* ktb, const float* d
 /* Replace only the right-hand side K^T b (a new batch of measurements through the same operators): re-transforms
  * ktb, keeps the diagonals.  ktb real [B,C,H,W] or NULL (= 0).  Valid for both x-update kinds. */
 int dpx_plan_set_rhs(dpx_plan* plan, const float* ktb, void* stream);
+/* Hints about the constants the caller knows and the library would have to synchronise to find out.
+ * DPX_HINT_CHANNEL_SHARED_DIAG = 1: the quadratic diagonal dq is identical for every channel (a single-channel PSF
+ * broadcast over RGB, psf2otf.py:29): the fused engine may then pair ANY two planes, e.g. the channels of a single image. */
+#define DPX_HINT_CHANNEL_SHARED_DIAG 1
+int dpx_plan_set_hint(dpx_plan* plan, int hint, int value);
 /* Same for the common data term sum_squares(scale * conv(x) - b): F(K^T b) = scale * conj(OTF) * F(b) is formed directly
  * in the Fourier domain (one R2C + one product) instead of conv.adjoint(b) (R2C, product, C2R) followed by another R2C.
  * b: real [B,C,H,W]; otf: complex64 half spectrum [otf_batch,C,H,W/2+1].  (sum_square.py:127-132, conv.py:37-41) */
