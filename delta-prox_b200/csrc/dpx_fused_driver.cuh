@@ -218,7 +218,8 @@ struct Driver {
           if (k + 1 < n_iters) {
             if (psi.n == 1 && be.persistent_ctas() > 0) {
               using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
-              be.template rowz_persist<TW2>(dim3(be.persistent_ctas()), RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);
+              be.template rowz_persist<TW2>(dim3(be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM), RowZPersistSmem<TW2>::BYTES, rp,
+                                            (H / ZR) * PP);
             } else row(std::integral_constant<int, ROW_MID>{});
           }
           else row(std::integral_constant<int, ROW_LAST>{});

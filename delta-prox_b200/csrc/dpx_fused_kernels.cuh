@@ -979,6 +979,8 @@ struct RowZPersistSmem {
   static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
   static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
   static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t);
+  // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
+  static constexpr int CTAS_PER_SM = (TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2;
 };
 
 struct RowZTile { int pp, h0, pA, pB; };
@@ -1012,7 +1014,7 @@ DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar
 }
 
 template <class TW>
-__global__ void __launch_bounds__(kThreads, 2) k_rowz_mid_persist(RowParams P, int n_tiles) {
+__global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_rowz_mid_persist(RowParams P, int n_tiles) {
   static_assert(TW::COLS == ZR, "tile holds one complex sequence per image row");
   constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
   constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
