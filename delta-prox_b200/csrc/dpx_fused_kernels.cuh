@@ -976,16 +976,11 @@ constexpr int ZR = 2;
 template <class TW>
 struct RowZPersistSmem {
   static constexpr int G = TW::N / CG;
-#ifdef DPX_ROWZ_NOSTAGE
-  static constexpr bool STAGE_S = TW::N < 2048;                  // experiment: rows of >= 2048 points load the spectrum directly, 3 CTAs/SM
-#else
-  static constexpr bool STAGE_S = true;
-#endif
-  static constexpr int STS_F2 = STAGE_S ? G * ZR * CG : 0;       // staged spectrum rows: [g][r][c]
+  static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
   static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
   static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t);
   // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
-  static constexpr int CTAS_PER_SM = ((TW::N <= 1024 || !STAGE_S) && BYTES * 3 <= 225 * 1024) ? 3 : 2;
+  static constexpr int CTAS_PER_SM = (TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2;
 };
 
 struct RowZTile { int pp, h0, pA, pB; };
@@ -1025,7 +1020,6 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
   constexpr int NT1 = NSEQ * (W / RC);
   constexpr unsigned U_BYTES = 2 * ZR * W * sizeof(float);
-  constexpr bool STAGE_S = RowZPersistSmem<TW>::STAGE_S;
   static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass fall into the same column of different groups");
   DPX_DYN_SMEM(float2, sm);
   float2* stS = sm + TW::SMEM_FLOAT2;
@@ -1049,7 +1043,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   if (tile < n_tiles) {
     if (tid == 0 && !hqs) mbar_expect_tx(bars + 1, U_BYTES);
     __syncthreads();
-    if (STAGE_S) rowz_stage_S<TW>(P, cur, stS, tid);
+    rowz_stage_S<TW>(P, cur, stS, tid);
     if (!hqs) rowz_stage_u<TW>(P, cur, stU, bars + 1, tid);
   }
   cp_async_commit();
@@ -1069,23 +1063,17 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     for (int t = tid; t < NT1; t += kThreads) {
       const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
       const int blk = gq * CG + cc;
+      const float2* src = stS + gq * (ZR * CG) + r * CG + cc;
       float2 a[RC];
-      if (STAGE_S) {
-        const float2* src = stS + gq * (ZR * CG) + r * CG + cc;
 #pragma unroll
-        for (int m = 0; m < RC; ++m) a[m] = src[m * (W / RC / CG) * (ZR * CG)];
-      } else {
-        const float2* src = P.S + (((size_t)pp * G + gq) * H + h0 + r) * CG + cc;
-#pragma unroll
-        for (int m = 0; m < RC; ++m) a[m] = ld_stream2(src + (size_t)m * (W / RC / CG) * H * CG);
-      }
+      for (int m = 0; m < RC; ++m) a[m] = src[m * (W / RC / CG) * (ZR * CG)];
       fft::Dft<RC, true>::run(a);
       const int p0 = TW::phys(blk * RC, r);
 #pragma unroll
       for (int m = 0; m < RC; ++m) sm[p0 + TW::template delta<1>(m) * NSEQ] = a[m];
     }
     __syncthreads();                                   // stS consumed
-    if (STAGE_S && next < n_tiles) rowz_stage_S<TW>(P, nxt, stS, tid);
+    if (next < n_tiles) rowz_stage_S<TW>(P, nxt, stS, tid);
     cp_async_commit();
     fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
     __syncthreads();
