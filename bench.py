@@ -72,6 +72,23 @@ def workload_config(args, world):
             "parallelism": f"dp{world} (problem shards, no collective)"}
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end leg
+    are allocated on that NUMA node (eight ranks otherwise cross the socket interconnect for half of their copies)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:                                      # noqa: BLE001 -- affinity is an optimisation, never a requirement
+        pass
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -217,6 +234,7 @@ def run_native(args):
         raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pin_to_gpu_numa_node(local)                            # before the pinned host buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = cabi.lib()
