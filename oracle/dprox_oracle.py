@@ -275,19 +275,41 @@ def prox_iso_tv(v, lam):
     return torch.cat([f * v[:, :C], f * v[:, C:]], dim=1)
 
 
-class ConvDOE(Op):
-    """conv_doe, circular mode (linop/conv.py:83-156); OTF rebuilt on every call."""
+def _linear_pad(x):
+    """zero padding of the `circular=False` mode (linop/conv.py:103-110): BOTH sides are padded towards 2 * H (the height),
+    ceil before / floor after."""
+    target = 2 * x.shape[2]
+    hp, wp = (target - x.shape[2]) / 2, (target - x.shape[3]) / 2
+    pt, pb = int(np.ceil(hp)), int(np.floor(hp))
+    pl, pr = int(np.ceil(wp)), int(np.floor(wp))
+    return torch.nn.functional.pad(x, [pl, pr, pt, pb]), (pt, pb, pl, pr)
 
-    def __init__(self, psf: Tensor, inner: Op):
-        self.psf, self.inner = psf, inner
+
+class ConvDOE(Op):
+    """conv_doe (linop/conv.py:83-156); OTF rebuilt on every call.  `circular=False` zero-pads to twice the size, convolves
+    circularly there and crops (:100-121); its `get_diag` nevertheless stays the circular |OTF|^2 at the image size (:143-152)."""
+
+    def __init__(self, psf: Tensor, inner: Op, circular: bool = True):
+        self.psf, self.inner, self.circular = psf, inner, circular
+
+    def _apply(self, x, conj):
+        crop = None
+        if not self.circular:
+            x, crop = _linear_pad(x)
+        otf = psf2otf2(self.psf, x.shape)
+        if conj:
+            otf = torch.conj(otf)
+        out = torch.real(torch.fft.ifftn(otf * torch.fft.fftn(x, dim=[-2, -1]), dim=[-2, -1])).float()
+        if crop is not None:
+            pt, pb, pl, pr = crop
+            out = out[:, :, pt:-pb, pl:-pr]
+        return out
 
     def _fwd(self, x):
-        otf = psf2otf2(self.psf, x.shape)
-        return torch.real(torch.fft.ifftn(otf * torch.fft.fftn(x, dim=[-2, -1]), dim=[-2, -1])).to(x.dtype)
+        return self._apply(x, False).to(x.dtype)
 
     def _adj(self, y):
-        otf = psf2otf2(self.psf, y.shape)
-        return torch.real(torch.fft.ifftn(torch.conj(otf) * torch.fft.fftn(y, dim=[-2, -1]), dim=[-2, -1])).to(y.dtype)
+        return self._apply(y, True).to(y.dtype)
 
     def freq_diag_ok(self):
         return self.inner.freq_diag_ok()
@@ -296,6 +318,51 @@ class ConvDOE(Op):
         assert freq
         otf = psf2otf2(self.psf, ref.shape)
         return torch.abs(torch.conj(otf) * otf)
+
+
+def img_psf_conv(img: Tensor, psf: Tensor, circular: bool = True) -> Tensor:
+    """contrib/optic/common.py:85-118 (differentiable through torch's own FFT autograd, like the reference)."""
+    crop = None
+    if not circular:
+        img, crop = _linear_pad(img)
+    out = torch.fft.ifft2(torch.fft.fft2(img) * psf2otf2(psf, img.shape)).real
+    if crop is not None:
+        pt, pb, pl, pr = crop
+        out = out[:, :, pt:-pb, pl:-pr]
+    return out
+
+
+def augment(img: Tensor, mode: int) -> Tensor:
+    """Augment.augment (pnp/denoisers/composite.py:30-47): the 8 flips / rotations of the x8 test-time augmentation."""
+    if mode == 0:
+        return img
+    if mode == 1:
+        return img.rot90(1, [2, 3]).flip([2])
+    if mode == 2:
+        return img.flip([2])
+    if mode == 3:
+        return img.rot90(3, [2, 3])
+    if mode == 4:
+        return img.rot90(2, [2, 3]).flip([2])
+    if mode == 5:
+        return img.rot90(1, [2, 3])
+    if mode == 6:
+        return img.rot90(2, [2, 3])
+    return img.rot90(3, [2, 3]).flip([2])
+
+
+class Augment:
+    """Augment (composite.py:6-28): one augmentation mode per call, cycling with the call counter."""
+
+    def __init__(self, denoise: Callable):
+        self.denoise, self.iter = denoise, 0
+
+    def __call__(self, x, sigma):
+        m = self.iter % 8
+        y = self.denoise(augment(x, m), sigma)
+        y = augment(y, 8 - m if m in (3, 5) else m)
+        self.iter += 1
+        return y
 
 
 def bayer_mask(h: int, w: int) -> Tensor:

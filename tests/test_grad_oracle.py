@@ -93,3 +93,47 @@ def test_oracle_implicit_cg_gradients_match_reference():
     assert rel(out, g["out"]) < 1e-5
     for name, t in (("g_b", b), ("g_x0", x0), ("g_rhos", rhos)):
         assert rel(t.grad, g[name]) < 1e-4, (name, rel(t.grad, g[name]))
+
+
+def test_oracle_autograd_spatial_diag_unrolled():
+    """unrolled training of a demosaicking objective (spatial-diagonal x-update)."""
+    g = load("unrolled_grads_mosaic")
+    b = torch.from_numpy(g["b"]).requires_grad_(True)
+    x0 = torch.from_numpy(g["x0"]).requires_grad_(True)
+    rhos = torch.from_numpy(g["rhos"]).requires_grad_(True)
+    lam1 = torch.from_numpy(g["lam1"]).requires_grad_(True)
+    f1 = orc.Term("norm1")
+    data = orc.Term("sum_squares", orc.Mosaic(orc.Identity()), c=b)
+    out = orc.Solver([data, f1], "admm").solve(x0, rhos=rhos, lams={f1: lam1}, max_iter=int(g["T"]))
+    (out * torch.from_numpy(g["wgt"])).sum().backward()
+    assert rel(out, g["out"]) < 2e-6
+    for name, t in (("g_b", b), ("g_x0", x0), ("g_rhos", rhos), ("g_lam1", lam1)):
+        assert rel(t.grad, g[name]) < 2e-5, name
+
+
+def test_oracle_unrolled_share_false():
+    """UnrolledSolver(share=False) (unroll.py:20-58): learned schedules, and per-iteration denoiser copies."""
+    g = load("unrolled_share_false")
+    b, wgt = torch.from_numpy(g["b"]), torch.from_numpy(g["wgt"])
+    rhos = torch.tensor([0.6, 0.9, 1.3], requires_grad=True)
+    lam = torch.tensor([0.05, 0.03, 0.02], requires_grad=True)
+    f1 = orc.Term("norm1")
+    data = orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), c=b)
+    out = orc.Solver([data, f1], "admm").solve(b, rhos=rhos, lams={f1: lam}, max_iter=3)
+    (out * wgt).sum().backward()
+    assert rel(out, g["lp_out"]) < 2e-6 and rel(rhos.grad, g["lp_g_rhos"]) < 2e-5 and rel(lam.grad, g["lp_g_lam"]) < 2e-5
+    copies = [[(w.clone().requires_grad_(True), bb.clone().requires_grad_(True)) for w, bb in orc.ffdnet_random_weights(int(g["seed"]))]
+              for _ in range(3)]
+    calls = []
+
+    def den(v, s_):
+        calls.append(1)
+        return orc.ffdnet_forward(copies[len(calls) - 1], v, s_)
+
+    prior = orc.Term("deep_prior", denoiser=den)
+    data = orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), c=b)
+    out = orc.Solver([data, prior], "admm").solve(b, rhos=torch.tensor([0.6, 0.9, 1.3]), lams={prior: torch.from_numpy(g["sig"])},
+                                                  max_iter=3)
+    (out * wgt).sum().backward()
+    assert rel(out, g["dn_out"]) < 1e-5
+    assert rel(copies[0][0][0].grad, g["dn_g_w0"]) < 1e-3 and rel(copies[1][0][0].grad, g["dn_g_w1"]) < 1e-3

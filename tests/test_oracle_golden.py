@@ -268,3 +268,105 @@ def test_csmri_closed_form_and_custom_admm():
         for got, name in ((x, "x"), (z, "z"), (u, "u")):
             want = g[f"{tag}_{name}"]
             assert np.linalg.norm(got.numpy() - want) / np.linalg.norm(want) < 1e-5, (tag, name)
+
+
+# ---- round 2: reference vectors at fused-engine sizes, BASELINE cfg1 / cfg3 as stated, formerly partial rows --------
+
+def test_cfg1_256_50_iterations():
+    """BASELINE configs[0] ([1,3,256,256], 50 it): the reference's own fp32 round-off is ~1e-5 at 50 iterations, so the
+    oracle is held to it at 2e-5 and both are compared with the fp64 run."""
+    g = load("cfg1_admm_256_50it")
+    x = orc.Solver(deconv_terms(g, [orc.Term("nonneg")]), "admm").solve(T(g["b"]), rhos=1.0, lams=0.02, max_iter=50)
+    x64 = orc.Solver([orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), c=T(g["b"]).double()), orc.Term("nonneg")],
+                     "admm", dtype=torch.float64).solve(T(g["b"]).double(), rhos=1.0, lams=0.02, max_iter=50)
+    assert rel(x.numpy(), g["s0"]) < 2e-5
+    assert rel(x.numpy(), x64.numpy()) < 1e-5 and rel(g["s0"], x64.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("case,method", [("admm_fused_128x192", "admm"), ("hqs_fused_64x320", "hqs")])
+def test_fused_engine_size_goldens(case, method):
+    g = load(case)
+    st = orc.Solver(deconv_terms(g, [orc.Term("nonneg")]), method).solve(T(g["b"]), rhos=float(g["rho"]), lams=0.02,
+                                                                         max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 3e-6)
+
+
+def test_cfg3_blackbox_tv_ladmm_pcg():
+    g = load("ladmm_csmri_blackbox_3it")
+    fwd, adj = csmri_ops(T(g["mask"]))
+    y0 = torch.complex(T(g["y0_re"]), T(g["y0_im"]))
+    data = orc.Term("sum_squares", orc.BlackBox(fwd, adj, orc.Identity()), b=y0)
+    psi = [orc.Term("norm1", orc.Grad(0, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))]
+    s = orc.Solver([data] + psi, "ladmm", solver_type="pcg", rtol=1e-6, max_iters=int(g["cg_iters"]))
+    st = s.solve(T(g["x0"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 1e-5)
+
+
+def test_conv_doe_linear():
+    g = load("conv_doe_linear")
+    for tag in ("even", "small", "odd"):
+        psf, t = T(g[f"{tag}_psf"]), T(g[f"{tag}_t"])
+        op = orc.ConvDOE(psf, orc.Identity(), circular=False)
+        assert rel(op.fwd(t).numpy(), g[f"{tag}_fwd"]) < 1e-6 and rel(op.adj(t).numpy(), g[f"{tag}_adj"]) < 1e-6
+        data = orc.Term("sum_squares", op, c=T(g[f"{tag}_b"]))
+        st = orc.Solver([data, orc.Term("nonneg")], "hqs").solve(T(g[f"{tag}_b"]), rhos=float(g["rho"]), max_iter=int(g["T"]),
+                                                               return_full_states=True)
+        check_state(st, {k[len(tag) + 1:]: v for k, v in g.items() if k.startswith(tag + "_s")}, 3e-6)
+
+
+def test_img_psf_conv_linear():
+    g = load("img_psf_conv_linear")
+    for tag in ("same", "small"):
+        img, psf = T(g[f"{tag}_img"]).requires_grad_(True), T(g[f"{tag}_psf"]).requires_grad_(True)
+        y = orc.img_psf_conv(img, psf, circular=False)
+        (y * T(g[f"{tag}_w"])).sum().backward()
+        assert rel(y.detach().numpy(), g[f"{tag}_y"]) < 1e-6
+        assert rel(img.grad.numpy(), g[f"{tag}_g_img"]) < 1e-6 and rel(psf.grad.numpy(), g[f"{tag}_g_psf"]) < 1e-6
+
+
+def test_grad_channel_axis():
+    g = load("admm_grad_dim2")
+    psi = [orc.Term("norm1", orc.Grad(2, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))]
+    st = orc.Solver(deconv_terms(g, psi), "admm").solve(T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]),
+                                                        max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 3e-6)
+
+
+def test_vxu_with_deep_prior_and_x8():
+    ws = orc.ffdnet_random_weights(4)
+    den = lambda v, s: orc.ffdnet_forward(ws, v, s)
+    g = load("vxu_deep_prior")
+    prior, nn_ = orc.Term("deep_prior", denoiser=den), orc.Term("nonneg")
+    st = orc.Solver(deconv_terms(g, [prior, nn_]), "admm_vxu").solve(T(g["b"]), rhos=float(g["rho"]),
+                                                                     lams={prior: T(g["sigmas"]), nn_: 0.02}, max_iter=int(g["T"]),
+                                                                     return_full_states=True)
+    check_state(st, g, 1e-5)
+    g = load("deep_prior_x8")
+    prior, nn_ = orc.Term("deep_prior", denoiser=orc.Augment(den)), orc.Term("nonneg")
+    st = orc.Solver(deconv_terms(g, [prior, nn_]), "admm").solve(T(g["b"]), rhos=float(g["rho"]),
+                                                                 lams={prior: T(g["sigmas"]), nn_: 0.02}, max_iter=int(g["T"]),
+                                                                 return_full_states=True)
+    check_state(st, g, 1e-5)
+
+
+def test_advisor_cases():
+    g = load("pc_identity")
+    st = orc.Solver([orc.Term("sum_squares", c=T(g["b"])), orc.Term("norm1")], "pc").solve(
+        T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 2e-6)
+    g = load("admm_mask_psi")
+    st = orc.Solver([orc.Term("sum_squares", c=T(g["b"])), orc.Term("norm1", orc.Mosaic(orc.Identity()))], "admm").solve(
+        T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 2e-6)
+    g = load("ladmm_scaled_identity")
+    st = orc.Solver(deconv_terms(g, [orc.Term("norm1", orc.Scale(2.0, orc.Identity()))]), "ladmm").solve(
+        T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]), return_full_states=True)
+    check_state(st, g, 3e-6)
+    g = load("pgd_psi_linop")
+    data = lambda: orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), b=T(g["b"]))
+    x = orc.Solver([data(), orc.Term("norm1", orc.Grad(1, orc.Identity()))], "pgd").solve(
+        T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]))
+    assert rel(x.numpy(), g["s0"]) < 3e-6
+    x = orc.Solver([data(), orc.Term("norm1", orc.Scale(2.0, orc.Identity()))], "pgd").solve(
+        T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]), max_iter=int(g["T"]))
+    assert rel(x.numpy(), g["scaled_s0"]) < 3e-6
