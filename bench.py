@@ -212,7 +212,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": dict(workload_config(args, args.gpus), reference_sample=sample,
+                       note="the CPU arm times a bounded SAMPLE of the workload (one problem, fewer iterations per step); the rate "
+                            "is normalised to problem-iterations, and a batch of 1 is the CPU's best case (BASELINE.md §2)"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

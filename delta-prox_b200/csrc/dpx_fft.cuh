@@ -30,6 +30,8 @@ class FftEngine {
   virtual void set_dpsi(const float* dpsi_std) { (void)dpsi_std; }
   // fully fused ADMM/HQS loop (identity psi linops, no residuals); only valid when fused() is true
   virtual bool fused() const { return false; }
+  // which transform engine the last iteration call used (DPX_ENGINE_*)
+  virtual int engine_mode() const { return DPX_ENGINE_CUFFT; }
   virtual int fused_iters(const Geom& g, const PsiPack& psi, bool hqs, float* x, const float2* fb, const float* dq,
                           int dq_batch, float wid, float eps, const float* rho, int rho_stride, int it0, int n_iters,
                           cudaStream_t s) {

@@ -142,6 +142,9 @@ class FusedEngine final : public FftEngine {
     delete this;
   }
   bool fused() const override { return true; }
+  int engine_mode() const override {
+    return packed_mode_ == PAIRS ? DPX_ENGINE_FUSED_PAIRS : (packed_mode_ == FLAT ? DPX_ENGINE_FUSED_FLAT : DPX_ENGINE_FUSED_PLANES);
+  }
   void reset_constants() override { dq_set_ = false; dq_std_ = nullptr; dq_dirty_ = true; }
   void set_dpsi(const float* dpsi_std) override { dpsi_std_ = dpsi_std; dpsi_dirty_ = true; }
 

@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(kThreads)
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     k_spatial_x(Geom g, PsiPack psi, bool hqs, bool vxu, const float* __restrict__ ktb, const float* __restrict__ dq,
-                int dq_batch, float wid, float eps, bool eps_delta, RhoRef rho, float* __restrict__ x) {
+                int dq_batch, const float* __restrict__ dpsi, float wid, float eps, bool eps_delta, RhoRef rho,
+                float* __restrict__ x) {
   const int p = blockIdx.y;
   const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (e >= g.plane) return;
@@ -394,9 +395,92 @@ __global__ void __launch_bounds__(kThreads)
     for (int k = 0; k < VEC; ++k) num[k] += r * (tm.scale * vv[k]);
   }
   if (eps_delta && e == 0) num[0] += eps;
+  if (dpsi) {                // mask-type psi linops: the denominator gains rho * sum_i s_i^2 diag_i (sum_square.py:145-148)
+    float dp[VEC];
+    loadv<VEC>(dp, dpsi + (size_t)c * g.plane + e);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) den[k] += r * dp[k];
+  }
 #pragma unroll
   for (int k = 0; k < VEC; ++k) num[k] = num[k] / (den[k] + r * wid + eps);
   storev<VEC>(x + base + e, num);
+}
+
+// Backward of the spatial-diagonal x-update x = (ktb + rho t + eps delta_0) / D, D = dq + rho (dpsi + wid) + eps:
+//   g_ktb = g / D   (dL/dt = rho g_ktb),   g_rho[b] = sum g_ktb (x (dq + eps) - ktb - eps delta_0) / rho
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_spatial_x_bwd(Geom g, const float* __restrict__ gin, const float* __restrict__ x, const float* __restrict__ ktb,
+                    const float* __restrict__ dq, int dq_batch, const float* __restrict__ dpsi, float wid, float eps,
+                    bool eps_delta, RhoRef rho, float* __restrict__ g_ktb, float* __restrict__ g_rho, int g_rho_stride) {
+  __shared__ float red[32];
+  const int p = blockIdx.y;
+  const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const int b = p / g.C, c = p - b * g.C;
+  const float r = rho_of(rho, b);
+  const size_t base = (size_t)p * g.plane;
+  float acc[1] = {0.f};
+  if (e < g.plane) {
+    float gv[VEC], d0[VEC], dp[VEC], kb[VEC], xv[VEC];
+    loadv<VEC>(gv, gin + base + e);
+    if (dq) loadv<VEC>(d0, dq + (size_t)(dq_batch > 1 ? p : c) * g.plane + e);
+    if (dpsi) loadv<VEC>(dp, dpsi + (size_t)c * g.plane + e);
+    if (g_rho) {
+      loadv<VEC>(xv, x + base + e);
+      if (ktb) loadv<VEC>(kb, ktb + base + e);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float q = dq ? d0[k] : 0.f;
+      const float D = q + r * ((dpsi ? dp[k] : 0.f) + wid) + eps;
+      gv[k] = gv[k] / D;
+      if (g_rho) {
+        float num0 = ktb ? kb[k] : 0.f;
+        if (eps_delta && e + k == 0) num0 += eps;
+        acc[0] += gv[k] * (xv[k] * (q + eps) - num0) / r;
+      }
+    }
+    storev<VEC>(g_ktb + base + e, gv);
+  }
+  if (g_rho) {
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(g_rho + (size_t)b * g_rho_stride, acc[0]);
+  }
+}
+
+// out[y][x] = in[y - top][x - left] where that lies inside the input, else 0: zero padding (top, left >= 0) and cropping
+// (negative offsets) of the `circular=False` convolutions (linop/conv.py:100-121, contrib/optic/common.py:97-117)
+__global__ void __launch_bounds__(kThreads)
+    k_pad2d(const float* __restrict__ in, float* __restrict__ out, int hi, int wi, int ho, int wo, int top, int left) {
+  const int p = blockIdx.y;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)ho * wo) return;
+  const int y = (int)(e / wo), xx = (int)(e - (size_t)y * wo);
+  const int sy = y - top, sx = xx - left;
+  out[(size_t)p * ho * wo + e] = (sy >= 0 && sy < hi && sx >= 0 && sx < wi) ? in[((size_t)p * hi + sy) * wi + sx] : 0.f;
+}
+
+// the 8 flips / rotations of Augment.augment (pnp/denoisers/composite.py:30-47); out is [wo = h][..] for the transposing modes
+__global__ void __launch_bounds__(kThreads)
+    k_augment(const float* __restrict__ in, float* __restrict__ out, int h, int w, int mode) {
+  const int p = blockIdx.y;
+  const bool tr = mode == 1 || mode == 3 || mode == 5 || mode == 7;       // output is [w, h]
+  const int ho = tr ? w : h, wo = tr ? h : w;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)h * w) return;
+  const int i = (int)(e / wo), j = (int)(e - (size_t)i * wo);
+  int sy, sx;                                                             // source pixel of output (i, j)
+  switch (mode) {
+    case 0: sy = i; sx = j; break;
+    case 1: sy = j; sx = i; break;                      // rot90(1).flip(rows)   = transpose
+    case 2: sy = ho - 1 - i; sx = j; break;             // flip(rows)
+    case 3: sy = h - 1 - j; sx = i; break;              // rot90(3)
+    case 4: sy = i; sx = wo - 1 - j; break;             // rot90(2).flip(rows)   = flip(cols)
+    case 5: sy = j; sx = w - 1 - i; break;              // rot90(1)
+    case 6: sy = ho - 1 - i; sx = wo - 1 - j; break;    // rot90(2)
+    default: sy = h - 1 - j; sx = w - 1 - i; break;     // rot90(3).flip(rows)   = anti-transpose
+  }
+  out[(size_t)p * h * w + e] = in[((size_t)p * h + sy) * w + sx];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -796,7 +880,10 @@ __global__ void __launch_bounds__(kThreads)
                 size_t per_sample) {
   __shared__ float red[32];
   const int b = blockIdx.y;
-  const float alpha = gamma[b] / pq[b];
+  // a gated (converged) solve has pq = +inf (k_cg_gate): the step is skipped outright so that x and r stay frozen even
+  // if the search direction has degenerated (0 * NaN would not be 0)
+  const bool frozen = isinf(pq[b]);
+  const float alpha = frozen ? 0.f : gamma[b] / pq[b];
   float acc[1] = {0.f};
   const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
   for (size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; e < per_sample; e += stride) {
@@ -805,15 +892,39 @@ __global__ void __launch_bounds__(kThreads)
     loadv<VEC>(xv, x + o); loadv<VEC>(rv, r + o); loadv<VEC>(pv, p + o); loadv<VEC>(qv, q + o);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      xv[k] = xv[k] + alpha * pv[k];
-      rv[k] = rv[k] - alpha * qv[k];
+      if (!frozen) {
+        xv[k] = xv[k] + alpha * pv[k];
+        rv[k] = rv[k] - alpha * qv[k];
+      }
       acc[0] += rv[k] * rv[k];
     }
-    storev<VEC>(x + o, xv);
-    storev<VEC>(r + o, rv);
+    if (!frozen) {
+      storev<VEC>(x + o, xv);
+      storev<VEC>(r + o, rv);
+    }
   }
   block_sum<1>(acc, red);
   if (threadIdx.x == 0) atomicAdd(gamma_new + b, acc[0]);
+}
+
+// Device-side stop test of (P)CG (solver_cg.py:103-107 / :225-229): *done becomes (and stays) 1 once val[b] <= tol[b]
+// (strict: <) holds for every b; while it is set the step scale of the following k_cg_update is forced to zero by
+// pq = +inf, so the iterate is frozen at exactly the iteration where the reference breaks -- without a host round trip.
+__global__ void k_cg_gate(const float* __restrict__ val, const float* __restrict__ tol, int tol_n, int strict,
+                          float* __restrict__ pq, int* __restrict__ done, int batch) {
+  __shared__ int all_ok;
+  if (threadIdx.x == 0) all_ok = 1;
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const float t = tol[tol_n > 1 ? b : 0];
+    const bool ok = strict ? (val[b] < t) : (val[b] <= t);
+    if (!ok) all_ok = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && all_ok) *done = 1;
+  __syncthreads();
+  if (*done)
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) pq[b] = __int_as_float(0x7f800000);
 }
 
 template <int VEC>
@@ -914,11 +1025,39 @@ int launch_prox_dual(const Geom& g, const PsiPack& psi, const float* x, bool hqs
 }
 
 int launch_spatial_xupdate(const Geom& g, const PsiPack& psi, bool hqs, bool vxu, const float* ktb, const float* dq,
-                           int dq_batch, float wid, float eps, bool eps_delta, RhoRef rho, float* x, cudaStream_t s) {
-  const int vec = pick_vec_psi(g, psi, !hqs, {ktb, dq, x});
+                           int dq_batch, const float* dpsi, float wid, float eps, bool eps_delta, RhoRef rho, float* x,
+                           cudaStream_t s) {
+  const int vec = pick_vec_psi(g, psi, !hqs, {ktb, dq, dpsi, x});
   DPX_DISPATCH_VEC(vec, k_spatial_x<VEC><<<plane_grid(g.plane, VEC, g.P), kThreads, 0, s>>>(g, psi, hqs, vxu, ktb, dq,
-                                                                                           dq_batch, wid, eps, eps_delta,
-                                                                                           rho, x));
+                                                                                           dq_batch, dpsi, wid, eps,
+                                                                                           eps_delta, rho, x));
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_spatial_xupdate_bwd(const Geom& g, const float* gin, const float* x, const float* ktb, const float* dq, int dq_batch,
+                               const float* dpsi, float wid, float eps, bool eps_delta, RhoRef rho, float* g_ktb, float* g_rho,
+                               int g_rho_stride, cudaStream_t s) {
+  PsiPack none;
+  none.n = 0;
+  const int vec = pick_vec_psi(g, none, false, {gin, x, ktb, dq, dpsi, g_ktb});
+  if (g_rho) DPX_CUDA(cudaMemsetAsync(g_rho, 0, sizeof(float) * (g_rho_stride ? g.B : 1), s));
+  DPX_DISPATCH_VEC(vec, k_spatial_x_bwd<VEC><<<plane_grid(g.plane, VEC, g.P), kThreads, 0, s>>>(
+                            g, gin, x, ktb, dq, dq_batch, dpsi, wid, eps, eps_delta, rho, g_ktb, g_rho, g_rho_stride));
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_pad2d(const float* in, float* out, int planes, int hi, int wi, int ho, int wo, int top, int left, cudaStream_t s) {
+  const dim3 grid((unsigned)(((size_t)ho * wo + kThreads - 1) / kThreads), planes);
+  k_pad2d<<<grid, kThreads, 0, s>>>(in, out, hi, wi, ho, wo, top, left);
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_augment(const float* in, float* out, int planes, int h, int w, int mode, cudaStream_t s) {
+  const dim3 grid((unsigned)(((size_t)h * w + kThreads - 1) / kThreads), planes);
+  k_augment<<<grid, kThreads, 0, s>>>(in, out, h, w, mode);
   DPX_LAUNCH_CHECK();
   return DPX_OK;
 }
@@ -1075,6 +1214,12 @@ int launch_cg_update(float* x, float* r, const float* p, const float* q, const f
   const int vec = flat_vec(per_sample, {x, r, p, q});
   DPX_DISPATCH_VEC(vec, k_cg_update<VEC><<<reduce_grid(per_sample, VEC, batch), kThreads, 0, s>>>(x, r, p, q, gamma, pq,
                                                                                                  gamma_new, per_sample));
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+int launch_cg_gate(const float* val, const float* tol, int tol_n, bool strict, float* pq, int* done, int batch, cudaStream_t s) {
+  k_cg_gate<<<1, 128, 0, s>>>(val, tol, tol_n, strict ? 1 : 0, pq, done, batch);
   DPX_LAUNCH_CHECK();
   return DPX_OK;
 }

@@ -22,7 +22,14 @@ int launch_prox_dual(const Geom& g, const PsiPack& psi, const float* x, bool hqs
 
 // spatial-diagonal x-update (sum_square.py:154): x = (ktb + rho*sum_i s_i b_i) / (dq + rho*wid + eps)
 int launch_spatial_xupdate(const Geom& g, const PsiPack& psi, bool hqs, bool vxu, const float* ktb, const float* dq,
-                           int dq_batch, float wid, float eps, bool eps_delta, RhoRef rho, float* x, cudaStream_t s);
+                           int dq_batch, const float* dpsi, float wid, float eps, bool eps_delta, RhoRef rho, float* x,
+                           cudaStream_t s);
+int launch_spatial_xupdate_bwd(const Geom& g, const float* gin, const float* x, const float* ktb, const float* dq, int dq_batch,
+                               const float* dpsi, float wid, float eps, bool eps_delta, RhoRef rho, float* g_ktb, float* g_rho,
+                               int g_rho_stride, cudaStream_t s);
+// zero-pad / crop copy and the 8 dihedral image transforms (data movement of conv_doe(circular=False) and the x8 prior)
+int launch_pad2d(const float* in, float* out, int planes, int hi, int wi, int ho, int wo, int top, int left, cudaStream_t s);
+int launch_augment(const float* in, float* out, int planes, int h, int w, int mode, cudaStream_t s);
 
 // ADMM_vxu (admm.py:107-120): x_i = prox(K_i z - u_i); t = sum_i s_i (x_i + u_i)   |   u_i += x_i - z
 int launch_vxu_prox(const Geom& g, const PsiPack& psi, const float* z, int it, float* t, cudaStream_t s);
@@ -66,5 +73,6 @@ int launch_cg_update(float* x, float* r, const float* p, const float* q, const f
                      float* gamma_new, int batch, size_t per_sample, cudaStream_t s);
 int launch_cg_direction(float* p, const float* r, const float* gn, const float* go, int batch, size_t per_sample,
                         cudaStream_t s);
+int launch_cg_gate(const float* val, const float* tol, int tol_n, bool strict, float* pq, int* done, int batch, cudaStream_t s);
 
 }  // namespace dpx

@@ -324,6 +324,24 @@ int dpx_plan_set_spatial_constants(dpx_plan* p, const float* ktb, const float* d
   return DPX_OK;
 }
 
+int dpx_plan_set_spatial_psi_diag(dpx_plan* p, const float* dpsi, void* stream) {
+  DPX_REQUIRE(p, "null plan");
+  DPX_REQUIRE(p->d.xupdate == DPX_X_SPATIAL_DIAG, "plan is not SPATIAL_DIAG");
+  if (!dpsi) { cudaFree(p->dpsi); p->dpsi = nullptr; return DPX_OK; }
+  const size_t n = sizeof(float) * (size_t)p->g.C * p->g.plane;
+  if (!p->dpsi) {
+    int rc = dev_alloc(p, (void**)&p->dpsi, n);
+    if (rc) return rc;
+  }
+  DPX_CUDA(cudaMemcpyAsync(p->dpsi, dpsi, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return DPX_OK;
+}
+
+int dpx_plan_engine_mode(const dpx_plan* p) {
+  if (!p || !p->fft) return DPX_ENGINE_NONE;
+  return p->fft->engine_mode();
+}
+
 int dpx_plan_set_psi_offset(dpx_plan* p, int i, const float* c, void* stream) {
   DPX_REQUIRE(p, "null plan");
   DPX_REQUIRE(i >= 0 && i < p->d.n_psi, "psi index %d out of range", i);
@@ -374,7 +392,7 @@ int dpx_stage_xupdate(dpx_plan* p, float* x, float* const* v, float* const* u, c
   DPX_REQUIRE(a != DPX_ALGO_ADMM_VXU, "ADMM_vxu is only lowered through dpx_iters (or compose it with dpx_xsolve)");
   PsiPack pk = make_pack(p, v, u, nullptr, nullptr);
   if (p->d.xupdate == DPX_X_SPATIAL_DIAG)
-    return launch_spatial_xupdate(g, pk, hqs, false, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
+    return launch_spatial_xupdate(g, pk, hqs, false, p->ktb_sp, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
   // fused engine: rhs + row FFT, column FFT + solve + inverse, inverse row FFT -> x  (3 launches, 34 B/element
   // instead of the 6 launches / ~60 B/element of rhs kernel + cuFFT R2C + solve + cuFFT C2R)
   if (p->fft->fused() && pk.n > 0 && (a == DPX_ALGO_ADMM || a == DPX_ALGO_LADMM || hqs)) {
@@ -402,7 +420,7 @@ int dpx_xsolve(dpx_plan* p, const float* t, const float* rho, int rho_stride, in
     memset(&one.t[0], 0, sizeof(PsiTerm));
     one.t[0].scale = 1.f;
     one.t[0].v = const_cast<float*>(t);
-    return launch_spatial_xupdate(g, one, /*hqs=*/true, false, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
+    return launch_spatial_xupdate(g, one, /*hqs=*/true, false, p->ktb_sp, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
   }
   if (p->fft->fused() && aligned16(t) && aligned16(x)) {      // rows: FFT of t; columns: solve; rows: inverse -> x (3 fused launches)
     PsiPack one;
@@ -423,9 +441,12 @@ int dpx_xsolve_backward(dpx_plan* p, const float* g, const float* x, const float
                         float* g_rho, void* stream) {
   DPX_REQUIRE(p && g && x && rho && g_ktb, "null argument");
   DPX_REQUIRE(p->consts_set, "constants not set (dpx_plan_set_*_constants)");
-  DPX_REQUIRE(p->d.xupdate == DPX_X_FREQ_DIAG && p->fft, "dpx_xsolve_backward needs a FREQ_DIAG plan");
   cudaStream_t s = (cudaStream_t)stream;
   const Geom& gm = p->g;
+  if (p->d.xupdate == DPX_X_SPATIAL_DIAG)
+    return launch_spatial_xupdate_bwd(gm, g, x, p->ktb_sp, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps, p->d.eps_delta != 0,
+                                      RhoRef{rho, rho_stride, it}, g_ktb, g_rho, rho_stride ? 1 : 0, s);
+  DPX_REQUIRE(p->fft, "plan has no FFT engine");
   if (!p->spec2) {
     int rc = dev_alloc(p, (void**)&p->spec2, sizeof(float2) * gm.P * gm.splane);
     if (rc) return rc;
@@ -540,7 +561,7 @@ int dpx_iters(dpx_plan* p, float* x, float* const* v, float* const* u, const flo
       rc = launch_vxu_prox(g, pk, x, it, freq ? p->t : nullptr, s);
       if (rc) return rc;
       if (freq) rc = xupdate_freq_from_t(p, x, rr, s);
-      else rc = launch_spatial_xupdate(g, pk, false, true, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
+      else rc = launch_spatial_xupdate(g, pk, false, true, p->ktb_sp, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
       if (!rc) rc = launch_vxu_dual(g, pk, x, s);
       if (rc) return rc;
       continue;
@@ -554,7 +575,7 @@ int dpx_iters(dpx_plan* p, float* x, float* const* v, float* const* u, const flo
       }
       rc = xupdate_freq_from_t(p, x, rr, s);
     } else {
-      rc = launch_spatial_xupdate(g, pk, hqs, false, p->ktb_sp, p->dq, p->dq_batch, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
+      rc = launch_spatial_xupdate(g, pk, hqs, false, p->ktb_sp, p->dq, p->dq_batch, p->dpsi, p->wid, p->d.eps, p->d.eps_delta != 0, rr, x, s);
     }
     if (rc) return rc;
     if (pk.n > 0) {
@@ -604,6 +625,18 @@ int dpx_grad_apply(const float* x, float* y, int planes, int height, int width, 
   return launch_grad(x, y, planes, height, width, axis, adjoint != 0, scale, (cudaStream_t)stream);
 }
 
+int dpx_pad2d(const float* in, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int top, int left, void* stream) {
+  DPX_REQUIRE(in && out && in != out, "null or aliased argument");
+  DPX_REQUIRE(planes > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "bad shape");
+  return launch_pad2d(in, out, planes, h_in, w_in, h_out, w_out, top, left, (cudaStream_t)stream);
+}
+
+int dpx_augment(const float* in, float* out, int planes, int height, int width, int mode, void* stream) {
+  DPX_REQUIRE(in && out && in != out, "null or aliased argument");
+  DPX_REQUIRE(mode >= 0 && mode < 8, "mode must be 0..7");
+  return launch_augment(in, out, planes, height, width, mode, (cudaStream_t)stream);
+}
+
 int dpx_axpby(float* out, float a, const float* x, float b, const float* y, size_t n, void* stream) {
   DPX_REQUIRE(out && x, "null argument");
   return launch_axpby(out, a, x, b, y, n, (cudaStream_t)stream);
@@ -633,6 +666,12 @@ int dpx_cg_direction(float* p, const float* r, const float* gamma_new, const flo
   return launch_cg_direction(p, r, gamma_new, gamma_old, batch, per_sample, (cudaStream_t)stream);
 }
 
+int dpx_cg_gate(const float* val, const float* tol, int tol_n, int strict, float* pq, int* done, int batch, void* stream) {
+  DPX_REQUIRE(val && tol && pq && done, "null argument");
+  DPX_REQUIRE(batch > 0 && (tol_n == 1 || tol_n == batch), "tol_n must be 1 or batch");
+  return launch_cg_gate(val, tol, tol_n, strict != 0, pq, done, batch, (cudaStream_t)stream);
+}
+
 int dpx_resid_reduce(const float* resid, float* out, int n, int batch, void* stream) {
   DPX_REQUIRE(resid && out && n > 0 && batch > 0, "bad argument");
   return launch_resid_reduce(resid, out, n, batch, (cudaStream_t)stream);
@@ -652,8 +691,10 @@ int dpx_solve_host(dpx_plan* p, const float* x0_host, float* x_out_host, const f
   if (!p->hx) { rc = dev_alloc(p, (void**)&p->hx, nbytes); if (rc) return rc; }
   const bool need_v = p->d.algo != DPX_ALGO_PGD, need_u = need_v && p->d.algo != DPX_ALGO_HQS;
   for (int i = 0; i < m; ++i) {
-    if (need_v && !p->hv[i]) { rc = dev_alloc(p, (void**)&p->hv[i], nbytes); if (rc) return rc; }
-    if (need_u && !p->hu[i]) { rc = dev_alloc(p, (void**)&p->hu[i], nbytes); if (rc) return rc; }
+    // a stacked-gradient term (grad2d / iso_tv) carries [B,2C,H,W] state
+    const size_t nb = p->d.psi[i].linop == DPX_LINOP_GRAD_HW ? 2 * nbytes : nbytes;
+    if (need_v && !p->hv[i]) { rc = dev_alloc(p, (void**)&p->hv[i], nb); if (rc) return rc; }
+    if (need_u && !p->hu[i]) { rc = dev_alloc(p, (void**)&p->hu[i], nb); if (rc) return rc; }
   }
   const int nsched = n_iters * (1 + m);
   if (p->hsched_cap < nsched) {

@@ -5,7 +5,7 @@ the reference it deliberately shadows the builtins `sum`, `eval`, `compile` and 
 """
 from . import linalg  # noqa: F401
 from .algo import (ADMM, ADMM_vxu, HQS, Algorithm, LinearizedADMM, PockChambolle, Problem, ProximalGradientDescent, ResidualStop,
-                   SOLVERS, compile, log_descent, specialize)
+                   SOLVERS, UnrolledSolver, build_unrolled_solver, compile, log_descent, specialize)
 from .linalg import LinearSolveConfig, linear_solve
 from .linop import (BlackBox, CompGraph, Constant, LinOp, LinOpFactory, Placeholder, Variable, adjoint, conv, conv_doe,
                     copy, eval, grad, grad2d, gram, mosaic, mul_elementwise, scale, split, sum, validate, vstack)
@@ -17,7 +17,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "ADMM", "ADMM_vxu", "HQS", "Algorithm", "LinearizedADMM", "PockChambolle", "Problem", "ProximalGradientDescent", "ResidualStop",
-    "SOLVERS", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg", "contrib",
+    "SOLVERS", "UnrolledSolver", "build_unrolled_solver", "compile", "log_descent", "specialize", "LinearSolveConfig", "linear_solve", "linalg", "contrib",
     "BlackBox", "CompGraph", "Constant", "LinOp", "LinOpFactory", "Placeholder", "Variable", "adjoint", "conv", "conv_doe",
     "copy", "eval", "grad", "grad2d", "gram", "mosaic", "mul_elementwise", "scale", "split", "sum", "validate", "vstack",
     "Denoiser", "ProxFn", "box", "csmri", "deep_prior", "ext_sum_squares", "iso_tv", "nonneg", "norm1", "norm2", "sum_squares",

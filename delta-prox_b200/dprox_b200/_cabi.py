@@ -21,6 +21,7 @@ X_FREQ_DIAG, X_SPATIAL_DIAG = 0, 1
 PROX_NONNEG, PROX_L1, PROX_L2SQ, PROX_BOX, PROX_EXTERNAL, PROX_ISO_TV = 0, 1, 2, 3, 4, 5
 LINOP_IDENTITY, LINOP_GRAD_H, LINOP_GRAD_W, LINOP_GRAD_HW = 0, 1, 2, 3
 FFT_AUTO, FFT_CUFFT, FFT_FUSED = 0, 1, 2
+ENGINE_NONE, ENGINE_CUFFT, ENGINE_FUSED_PLANES, ENGINE_FUSED_PAIRS, ENGINE_FUSED_FLAT = -1, 0, 1, 2, 3
 
 
 class PsiDesc(C.Structure):
@@ -59,6 +60,10 @@ SIGNATURES = {
     "dpx_plan_set_rhs_spectral": (_I, [_VP, _VP, _VP, _I, _F, _VP]),
     "dpx_plan_set_spatial_constants": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dpx_plan_set_psi_offset": (_I, [_VP, _I, _VP, _VP]),
+    "dpx_plan_set_spatial_psi_diag": (_I, [_VP, _VP, _VP]),
+    "dpx_plan_engine_mode": (_I, [_VP]),
+    "dpx_pad2d": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "dpx_augment": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "dpx_iters": (_I, [_VP, _VP, _PP, _PP, _VP, _I, _PP, _IP, _I, _I, _VP, _VP]),
     "dpx_stage_xupdate": (_I, [_VP, _VP, _PP, _PP, _VP, _I, _I, _VP]),
     "dpx_stage_prox": (_I, [_VP, _VP, _PP, _PP, _PP, _IP, _I, _VP]),
@@ -77,6 +82,7 @@ SIGNATURES = {
     "dpx_cg_update": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _SZ, _VP]),
     "dpx_cg_direction": (_I, [_VP, _VP, _VP, _VP, _I, _SZ, _VP]),
     "dpx_absmax": (_I, [_VP, _VP, _I, _SZ, _VP]),
+    "dpx_cg_gate": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _VP]),
     "dpx_ffdnet_available": (_I, []),
     "dpx_ffdnet_create": (_I, [_I, _I, C.POINTER(_VP)]),
     "dpx_ffdnet_destroy": (None, [_VP]),
@@ -169,6 +175,7 @@ class NativePlan:
     def __init__(self, desc: ProblemDesc, device: torch.device):
         self.desc = desc
         self.device = device
+        self.const_version = 0          # bumped by whoever re-sets the plan's constants (see autograd.XSolve)
         self._h = C.c_void_p()
         with torch.cuda.device(device):
             check(lib().dpx_plan_create(C.byref(desc), C.byref(self._h)), "dpx_plan_create")
@@ -178,6 +185,10 @@ class NativePlan:
         if not self._h:
             raise RuntimeError("plan already destroyed")
         return self._h
+
+    def engine_mode(self) -> int:
+        """ENGINE_* of the last fused call (which transform engine ran)."""
+        return int(lib().dpx_plan_engine_mode(self.handle))
 
     def workspace_bytes(self) -> int:
         return int(lib().dpx_plan_workspace_bytes(self.handle))

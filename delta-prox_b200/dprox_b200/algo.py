@@ -11,6 +11,8 @@ schedules resident on the device.  State tensors are updated in place.
 """
 from __future__ import annotations
 
+import copy as _copy
+import warnings
 from functools import partial
 from typing import Callable, Dict, Iterable, List, Optional, Union
 
@@ -39,24 +41,71 @@ def _to_tensor(x, batch=False):
 class ResidualStop:
     """Opt-in residual stopping rule (absent from the reference's imaging loop; semantics follow
     lp/solvers.py:324-336): stop when  |r| <= abstol*sqrt(n) + reltol*max(|Kx|,|v|)  and  |s| <= abstol*sqrt(n) +
-    reltol*|v|, with r = Kx - v and s = rho*(v - v_prev), summed over all psi terms, all samples and — through
-    `group` — all ranks (one NCCL all-reduce of 4 floats every `every` iterations)."""
+    reltol*|v|, with r = Kx - v and s = rho*(v - v_prev), summed over all psi terms, all samples and -- through
+    `group` -- all ranks.
 
-    def __init__(self, abstol=1e-4, reltol=1e-3, every=4, group=None):
-        self.abstol, self.reltol, self.every, self.group = abstol, reltol, max(1, int(every)), group
+    The check is ASYNCHRONOUS: every `every` iterations the per-sample sums are reduced on the device, the
+    5-float vector is all-reduced on a SIDE stream (NCCL) and copied to pinned host memory behind an event; the loop keeps
+    enqueueing iterations and consumes the decision `lag` checks later (default: one check late), by which time the event
+    has long fired, so neither the device nor the host ever waits for the collective.  The solve therefore runs
+    `lag * every` iterations past the first satisfied check.  `lag=0` gives the blocking variant."""
+
+    def __init__(self, abstol=1e-4, reltol=1e-3, every=4, group=None, lag=1):
+        self.abstol, self.reltol, self.every, self.group, self.lag = abstol, reltol, max(1, int(every)), group, max(0, int(lag))
         self.history = []
+        self._side = None
+        self._pending = []
 
-    def converged(self, sums: torch.Tensor, n_elems: int) -> bool:
-        """sums = [sum|r|^2, sum|s|^2, sum|Kx|^2, sum|v|^2] (device or CPU tensor), already local-summed."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            tot = torch.cat([sums.double(), torch.tensor([float(n_elems)], dtype=torch.float64, device=sums.device)])
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
-            sums, n_elems = tot[:4], float(tot[4])
-        r, s, kx, v = [float(t) ** 0.5 for t in sums]
+    def _decide(self, tot) -> bool:
+        r, s, kx, v = [max(float(t), 0.0) ** 0.5 for t in tot[:4]]
+        n_elems = float(tot[4])
         self.history.append((r, s))
         eps_abs = self.abstol * (n_elems ** 0.5)
         return r <= eps_abs + self.reltol * max(kx, v) and s <= eps_abs + self.reltol * v
+
+    def converged(self, sums: torch.Tensor, n_elems: int) -> bool:
+        """Blocking form.  sums = [sum|r|^2, sum|s|^2, sum|Kx|^2, sum|v|^2] (device or CPU tensor), already local-summed."""
+        import torch.distributed as dist
+        tot = torch.cat([sums.double(), torch.tensor([float(n_elems)], dtype=torch.float64, device=sums.device)])
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+        return self._decide(tot.cpu())
+
+    # -- asynchronous form ---------------------------------------------------------------------------------------------
+    def submit(self, sums: torch.Tensor, n_elems: int):
+        """Queue the all-reduce + host copy of one check behind the work already enqueued on the current stream."""
+        import torch.distributed as dist
+        dev = sums.device
+        tot = torch.cat([sums.double(), torch.tensor([float(n_elems)], dtype=torch.float64, device=dev)])
+        host = torch.empty(5, dtype=torch.float64).pin_memory() if dev.type == "cuda" else None
+        if dev.type != "cuda":                                        # CPU tensors (gloo tests): nothing to overlap with
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            self._pending.append((None, tot, tot))
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)     # NCCL enqueues on the side stream
+            host.copy_(tot, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        tot.record_stream(self._side)
+        self._pending.append((done, host, tot))
+
+    def poll(self, flush: bool = False) -> bool:
+        """Consume the checks that are at least `lag` submissions old (all of them with flush=True)."""
+        hit = False
+        while self._pending and (flush or len(self._pending) > self.lag):
+            done, host, _keep = self._pending.pop(0)
+            if done is not None:
+                done.synchronize()                                    # fired long ago unless lag == 0
+            hit = self._decide(host) or hit
+        return hit
 
 
 def _flat_tensors(*objs):
@@ -95,6 +144,15 @@ class Algorithm(nn.Module):
         self._dev_anchor = nn.Parameter(torch.tensor(0.0), requires_grad=False)
         self.spec: PlanSpec = analyze(list(psi_fns), list(omega_fns), self.method, try_diagonalize, try_freq_diagonalize)
         self._engine = None
+
+    def __deepcopy__(self, memo):
+        """Per-iteration copies of a solver (UnrolledSolver(share=False), unroll.py:10-27): everything but the native plans,
+        which every copy rebuilds on first use."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_engine", "_engine_d") else _copy.deepcopy(v, memo)
+        return new
 
     # reference attribute: `solver.least_square.{diagonalizable,freq_diagonalizable}`
     @property
@@ -223,11 +281,15 @@ class Algorithm(nn.Module):
         rhos = torch.as_tensor(rhos, dtype=torch.float32).to(dev)         # schedules live on the device
         lams = {k: torch.as_tensor(v, dtype=torch.float32).to(dev) for k, v in lams.items()}
         per_iter = callback is not None or pbar or isinstance(eng, GenericEngine)
+        self.iterations_run = max_iter
         if stop is not None and isinstance(eng, NativeEngine) and not eng.spec.has_external and not per_iter:
             state = self._iters_with_stop(eng, state, rhos, lams, max_iter, stop)
         elif not per_iter:
             state = eng.run(state, rhos, lams, 0, max_iter)                 # ONE native call for the whole loop
         else:
+            if stop is not None:
+                warnings.warn("dprox_b200: the residual stop rule only applies to the fused native loop (no callback / progress "
+                              "bar / external prox / node-by-node engine); running the fixed max_iter iterations", stacklevel=2)
             it_range = range(max_iter)
             if pbar:
                 from tqdm import tqdm
@@ -248,19 +310,30 @@ class Algorithm(nn.Module):
     def _iters_with_stop(self, eng, state, rhos, lams, max_iter, stop: ResidualStop):
         """Residual stopping rule: the first `every - 1` iterations of each block run in the fused loop (which keeps v only
         implicitly, so it has no v - v_prev to measure); the block's last iteration runs through the kernel that also
-        accumulates {|r|^2, |s|^2, |Kx|^2, |v|^2} per sample with warp-shuffle reductions, and those sums are tested."""
+        accumulates {|r|^2, |s|^2, |Kx|^2, |v|^2} per sample with warp-shuffle reductions.  Those sums are reduced over the
+        samples on the device (`dpx_resid_reduce`) and handed to the rule's asynchronous check (side-stream all-reduce,
+        decision consumed one check later): the host never waits for the check of the block it has just enqueued."""
         B = eng.shape4[0]
         n_elems = state[0].numel() * max(1, len(self.psi_fns))
+        dev = state[0].device
         it = 0
+        stop._pending.clear()
         while it < max_iter:
             n = min(stop.every, max_iter - it)
             if n > 1:
                 state = eng.run(state, rhos, lams, it, n - 1)
-            resid = torch.zeros(1, B, 4, device=state[0].device, dtype=torch.float32)
+            resid = torch.empty(1, B, 4, device=dev, dtype=torch.float32)
             state = eng.run(state, rhos, lams, it + n - 1, 1, resid=resid)
+            sums = torch.empty(1, 4, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                cabi.check(cabi.lib().dpx_resid_reduce(cabi.ptr(resid), cabi.ptr(sums), 1, B, cabi.stream_ptr(dev)), "dpx_resid_reduce")
             it += n
-            if stop.converged(resid[-1].sum(dim=0), n_elems):
+            stop.submit(sums[0], n_elems)
+            if stop.poll():
                 break
+        else:
+            stop.poll(flush=True)
+        stop._pending.clear()
         self.iterations_run = it
         return state
 
@@ -413,13 +486,68 @@ def compile(prox_fns: List[ProxFn], method: str = "admm", device: Union[str, tor
     return solver.to(device)
 
 
+class UnrolledSolver(nn.Module):
+    """algo/specialization/unroll.py:20-58: one solver copy per unrolled iteration (`share=False`: deep copies, so trainable
+    denoisers / operator parameters are per-iteration) and, with `learned_params=True`, rho / lam schedules that are
+    nn.Parameters initialised to ones.  Like the reference it keys the per-iteration lam by `psi_fns[0]` of the copy, i.e. it
+    serves objectives with a single prox term."""
+
+    def __init__(self, solver: Algorithm, max_iter: int, share: bool = False, learned_params: bool = False):
+        super().__init__()
+        if share is False:
+            self.solvers = nn.ModuleList([_copy.deepcopy(solver) for _ in range(max_iter)])
+        else:
+            self.solver = solver
+            self.solvers = [solver for _ in range(max_iter)]
+        self.max_iter, self.share, self.learned_params = max_iter, share, learned_params
+        if learned_params:
+            self.rhos = nn.Parameter(torch.ones(max_iter))
+            self.lams = {}
+            for fn in solver.psi_fns:
+                lam = nn.Parameter(torch.ones(max_iter))
+                setattr(self, str(fn), lam)
+                self.lams[fn] = lam
+
+    def solve(self, x0=None, rhos=None, lams=None, max_iter=None):
+        first = self.solvers[0]
+        x0 = _to_tensor(x0, batch=True)
+        dev = first.device
+        if self.learned_params:
+            rhos, lams = self.rhos, self.lams
+        else:
+            rhos = _to_tensor(rhos).to(dev)
+            if not isinstance(lams, dict):
+                lams = {fn: lams for fn in first.psi_fns}
+            lams = {k: _to_tensor(v).to(dev) for k, v in lams.items()}
+        x0 = x0.to(dev, torch.complex64 if x0.is_complex() else torch.float32)
+        max_iter = self.max_iter if max_iter is None else max_iter
+        diff = first._wants_grad(x0, rhos, lams) or any(s._wants_grad() for s in self.solvers[1:max_iter])
+        if diff:
+            for s in {id(s): s for s in self.solvers[:max_iter]}.values():
+                s._diff_engine(x0).set_constants()                   # fresh tape from the measurements to K^T b
+        state = first.initialize(x0, _diff=diff)
+        for i in range(max_iter):
+            rho = rhos[..., i:i + 1]
+            lam = {self.solvers[i].psi_fns[0]: v[..., i:i + 1] for v in lams.values()}
+            state = self.solvers[i].iters(state, rho, lam, 1, False, _diff=diff)
+        return state[0]
+
+
+def build_unrolled_solver(solver: Algorithm, share: bool = True, **kwargs):
+    """unroll.py:14-18."""
+    if share is True:
+        solver.solve = partial(solver.solve, **kwargs)
+        return solver
+    return UnrolledSolver(solver, share=share, **kwargs)
+
+
 def specialize(solver: Algorithm, method: str = "unroll", device="cuda", **kwargs):
-    """algo/primitives.py:70-95 — only the shared-parameter unrolling (`partial`-bound solve kwargs, unroll.py:14-18)."""
-    if method != "unroll" or kwargs.get("share", True) is not True:
-        raise NotImplementedError("only specialize(..., method='unroll', share=True) is available in this backend")
-    kwargs.pop("share", None)
-    solver.solve = partial(solver.solve, **kwargs)
-    return solver
+    """algo/primitives.py:70-95; only the 'unroll' specialisation is part of this backend (DEQ / RL wrap training loops)."""
+    if method != "unroll":
+        raise NotImplementedError("only specialize(..., method='unroll') is available in this backend")
+    solver = build_unrolled_solver(solver, **kwargs)
+    device = torch.device(device) if isinstance(device, str) else device
+    return solver.to(device)
 
 
 class Problem:

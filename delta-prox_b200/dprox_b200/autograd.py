@@ -104,6 +104,37 @@ class Grad(torch.autograd.Function):
         return ops.grad(g.contiguous(), axis, not adjoint, scale), None, None, None
 
 
+class Pad2d(torch.autograd.Function):
+    """zero-pad / crop copy; its adjoint is the same copy with the offsets negated back to the input size"""
+
+    @staticmethod
+    def forward(ctx, x, out_hw, top, left):
+        from . import ops
+        ctx.cfg = (tuple(x.shape[-2:]), top, left)
+        return ops.pad2d(x, out_hw, top, left)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        in_hw, top, left = ctx.cfg
+        return ops.pad2d(g.contiguous(), in_hw, -top, -left), None, None, None
+
+
+class Augment(torch.autograd.Function):
+    """a pixel permutation: the adjoint is the inverse permutation"""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        from . import ops
+        ctx.mode = mode
+        return ops.augment(x, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        return ops.augment(g.contiguous(), ops.AUGMENT_INVERSE[ctx.mode]), None
+
+
 class SpectralFilter(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, otf, conj, plan):
@@ -162,7 +193,7 @@ class XSolve(torch.autograd.Function):
         with torch.cuda.device(t.device):
             cabi.check(cabi.lib().dpx_xsolve(plan.handle, cabi.ptr(t), cabi.ptr(rho), rho_stride, 0, cabi.ptr(x),
                                              cabi.stream_ptr(t.device)), "dpx_xsolve")
-        ctx.plan, ctx.rho_stride = plan, rho_stride
+        ctx.plan, ctx.rho_stride, ctx.const_version = plan, rho_stride, plan.const_version
         ctx.save_for_backward(x, rho)
         ctx.ktb_shape = None if ktb is None else ktb.shape
         return x
@@ -171,6 +202,12 @@ class XSolve(torch.autograd.Function):
     def backward(ctx, g):
         from . import ops
         x, rho = ctx.saved_tensors
+        if ctx.plan.const_version != ctx.const_version:
+            # the backward kernel reads F(K^T b) and the diagonals from the plan: a second forward with other measurements /
+            # operator parameters in between would silently give wrong rho gradients
+            raise RuntimeError("dprox_b200: the solver's constants (measurements / Placeholder values) changed between this "
+                               "forward pass and its backward; call backward() before the next solve(), or use one compiled "
+                               "solver per in-flight graph")
         g = cabi.require_cuda_f32(g, "grad")
         need_rho = ctx.needs_input_grad[2]
         gk = torch.empty_like(x)

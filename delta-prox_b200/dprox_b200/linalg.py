@@ -4,7 +4,7 @@ The operator `A` is any Python callable on CUDA tensors (the plugin surface: Lin
 BlackBoxes); everything *around* it — dot products, the x/r update, the direction update — runs in
 three fused sm_100a kernels (`dpx_cg_dot`, `dpx_cg_update`, `dpx_cg_direction`), so one CG step costs
 28 B/element of vector traffic instead of the reference's ~10 full-tensor passes, and there is no
-host synchronisation per step unless the stop test is asked for (`check_every`).
+host synchronisation per step: the stop test runs on the device (`dpx_cg_gate`).
 """
 from __future__ import annotations
 
@@ -29,34 +29,69 @@ class LinearSolveConfig:
     use_analytic_grad: bool = True
 
 
+class _StopPoll:
+    """Lagged, non-blocking read of the device-side `done` flag: every step queues a 4-byte copy into pinned memory behind
+    the step's kernels; the host only looks at copies whose event has already fired, so it never waits for the device and
+    simply stops enqueueing a couple of steps after the solve froze itself (extra steps are no-ops on x and r)."""
+
+    def __init__(self, device, depth=4):
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        self.slots = torch.zeros(depth, dtype=torch.int32).pin_memory()
+        self.events = [None] * depth
+        self.n = 0
+
+    def push(self):
+        k = self.n % len(self.events)
+        self.slots[k:k + 1].copy_(self.done, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        self.n += 1
+
+    def stopped(self) -> bool:
+        for k, ev in enumerate(self.events):
+            if ev is not None and ev.query() and int(self.slots[k]) != 0:
+                return True
+        return False
+
+
 def cg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: float = 1e-6, max_iters: int = 100,
-       verbose: bool = False, check_every: int = 1):
+       verbose: bool = False, check_every: Optional[int] = None):
     """Conjugate gradients, batched over dim 0 (linalg/solve/solver_cg.py:56-136).
 
     Stop test: per-sample ||r_b|| <= rtol * ||b_b|| for all b.  (The reference compares the *spectral*
     norm of the [B,n] residual matrix with the per-sample tolerances, solver_cg.py:103-104; for B == 1
-    the two coincide — SURVEY App. A-7.)  The test needs one 4*B-byte device->host read; set
-    `check_every=k` to do it only every k steps (0 = never, always run `max_iters`).
+    the two coincide — SURVEY App. A-7.)  The test runs ON THE DEVICE (`dpx_cg_gate`): once it holds the
+    iterate is frozen at exactly the iteration where the reference breaks, and the host -- which never
+    blocks on the device -- stops enqueueing steps as soon as a lagged copy of the flag tells it so.
+    `check_every=k > 0` restores a blocking host test every k steps; `check_every=0` never tests.
     """
     x = torch.zeros_like(b) if x0 is None else x0.clone()
     r = b.clone() if x0 is None else ops.axpby(1.0, b, -1.0, A(x))
     n_it = int(min(max_iters, int(np.prod(b.shape))))
     tol2 = None
-    if check_every:
+    poll = None
+    if check_every is None or check_every:
         bn2 = ops.dot(b, b)
-        tol2 = (rtol * rtol) * bn2
+        tol2 = (rtol * rtol) * bn2                               # B scalars (cold)
+        if check_every is None:
+            poll = _StopPoll(b.device)
     gamma = ops.dot(r, r)
     p = None
-    it = 0
     for it in range(n_it):
         if check_every and it % check_every == 0 and bool(torch.all(gamma <= tol2)):
             if verbose:
                 print("Converged at CG Iter %03d" % it)
             break
+        if poll is not None and poll.stopped():
+            break
         if it == 0:
             p = r.clone()
         q = A(p)
         pq = ops.dot(p, q)
+        if poll is not None:
+            ops.cg_gate(gamma, tol2, pq, poll.done)             # converged -> pq = inf -> the update below is a no-op
+            poll.push()
         gamma_new = ops.cg_update(x, r, p, q, gamma, pq)        # x += a p ; r -= a q ; <r,r>
         ops.cg_direction(p, r, gamma_new, gamma)                # p = r + (g'/g) p
         gamma = gamma_new
@@ -64,27 +99,38 @@ def cg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: fl
 
 
 def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: float = 1e-6, max_iters: int = 100,
-        verbose: bool = False, Minv: Optional[Callable] = None, check_every: int = 1):
+        verbose: bool = False, Minv: Optional[Callable] = None, check_every: Optional[int] = None):
     """Preconditioned CG with the reference's conventions (solver_cg.py:172-233): starts from ones,
-    whole-tensor dot products, absolute inf-norm stop `max|r| < rtol`.
+    whole-tensor dot products, absolute inf-norm stop `max|r| < rtol` -- tested on the device like `cg`'s.
 
     With `Minv=None` it is algebraically CG started at ones with global dots: the same three fused
     kernels are used with batch=1 (the residual tracked here is b - A x = -r_ref)."""
     x = torch.ones_like(b) if x0 is None else x0.clone()
     r = ops.axpby(1.0, b, -1.0, A(x))
+    poll = _StopPoll(b.device) if check_every is None else None
+    tol = torch.full((1,), rtol, device=b.device) if poll is not None else None
     if Minv is None:
         gamma = ops.dot(r, r, per_sample=False)
         p = r.clone()
+        rmax = None
         for it in range(max_iters):
+            if poll is not None and poll.stopped():
+                break
             q = A(p)
             pq = ops.dot(p, q, per_sample=False)
+            if poll is not None and rmax is not None:
+                ops.cg_gate(rmax, tol, pq, poll.done, strict=True)      # the reference breaks right after the update that met the test
+                poll.push()
             gamma_new = ops.cg_update(x, r, p, q, gamma, pq, per_sample=False)
             ops.cg_direction(p, r, gamma_new, gamma, per_sample=False)
             gamma = gamma_new
-            if check_every and (it + 1) % check_every == 0 and float(ops.absmax(r)) < rtol:
+            if poll is not None:
+                rmax = ops.absmax(r)
+            elif check_every and (it + 1) % check_every == 0 and float(ops.absmax(r)) < rtol:
                 break
         return x
-    # general preconditioner: y = Minv(r) is a user callable; dots/axpys stay native
+    # general preconditioner: y = Minv(r) is a user callable; dots/axpys stay native (host test: Minv is user code anyway)
+    check_every = 1 if check_every is None else check_every
     y = Minv(r)
     p = y.clone()
     ry = ops.dot(r, y, per_sample=False)

@@ -570,7 +570,7 @@ class conv(LinOp):
             return None
         if child.kind == "identity":
             return Lowered("spectral", child.scale, otf_fn=self._otf_half, gram_fn=self._gram_half)
-        if child.kind in ("spectral", "grad"):
+        if child.kind in ("spectral", "grad") and child.otf_fn is not None:
             c_otf, c_gram = child.otf_fn, child.gram_fn
             return Lowered("spectral", child.scale,
                            otf_fn=lambda s: self._otf_half(s) * _t(c_otf(s)),
@@ -603,22 +603,36 @@ class grad(conv):
         self.kernel = np.swapaxes(k, dim, -1)
         self.cache = {}
 
-    def _check(self):
-        if self.dim == 2:
-            raise NotImplementedError("grad along the channel axis (dim=2) has no native kernel yet")
+    def _chan_weight(self, input):
+        """dim=2: the kernel [1,-1] lies on the channel axis of the HWC kernel, and `conv` transforms the kernel over all three
+        axes but the image only over H, W (conv.py:31-41, psf2otf.py): channel c is multiplied by the complex constant FB[c],
+        and the real part is kept -- y[c] = Re(FB[c]) x[c] for forward AND adjoint.  Kept as the reference has it."""
+        shape = _shape4(input)
+        key = ("cw", shape[1], str(input.device))
+        if key not in self.cache:
+            fb = self._FB((1, shape[1], 8, 8))                     # constant over (h, w)
+            w = torch.real(fb[:, :, 0, 0]).float().reshape(1, shape[1], 1, 1)
+            self.cache[key] = w.to(input.device)
+        return self.cache[key].expand(1, shape[1], shape[2], shape[3]).contiguous()
 
     def forward(self, input, **kw):
-        self._check()
+        if self.dim == 2:
+            return ops.mul(input, self._chan_weight(input))
         return ops.grad(input, self.dim, adjoint=False)
 
     def adjoint(self, input, **kw):
-        self._check()
+        if self.dim == 2:
+            return ops.mul(input, self._chan_weight(input))
         return ops.grad(input, self.dim, adjoint=True)
 
     def lower(self):
         child = self.input_nodes[0].lower()
-        if child is None or child.const or self.dim == 2:
+        if child is None or child.const:
             return None
+        if self.dim == 2:
+            # Fourier-diagonalisable with the diagonal |FB[c]|^2 (what the reference's closed form divides by) while
+            # forward / adjoint apply Re(FB[c]): `otf_fn=None` keeps every application on this node's own forward/adjoint
+            return Lowered("spectral", child.scale, otf_fn=None, gram_fn=self._gram_half) if child.kind == "identity" else None
         if child.kind == "identity":
             return Lowered("grad", child.scale, axis=self.dim, otf_fn=self._otf_half, gram_fn=self._gram_half)
         return conv.lower(self)
@@ -658,58 +672,81 @@ class grad2d(LinOp):
         return Lowered("grad2d", child.scale, gram_fn=self._gram_half)
 
 
+def linear_conv_pads(H: int, W: int):
+    """zero padding of the `circular=False` mode (linop/conv.py:103-110): BOTH axes are padded towards 2 * H (the height),
+    ceil before / floor after -> (top, bottom, left, right)."""
+    target = 2 * H
+    hp, wp = (target - H) / 2, (target - W) / 2
+    return int(np.ceil(hp)), int(np.floor(hp)), int(np.ceil(wp)), int(np.floor(wp))
+
+
 class conv_doe(LinOp):
-    """Circular convolution with a (learnable / Placeholder-fed) PSF [1,C,h,w]  (linop/conv.py:83-156).
-    Only `circular=True` is lowered; gradients w.r.t. the PSF are not propagated by this backend."""
+    """Convolution with a (learnable / Placeholder-fed) PSF [1,C,h,w]  (linop/conv.py:83-156): circular, or -- `circular=False`
+    -- linear: zero-pad to twice the size, convolve circularly there, crop (:100-121).  As in the reference the linear mode
+    still reports the CIRCULAR |OTF|^2 at the image size as its Fourier diagonal (:143-152).  Gradients w.r.t. the PSF are
+    not propagated through this node (the reference re-wraps it as a fresh leaf, :91-96)."""
 
     def __init__(self, arg, psf, circular: bool = True):
         super().__init__([arg])
         self._psf = psf
         self.circular = circular
-        self._otf_cache = None
-        if not circular:
-            raise NotImplementedError("conv_doe(circular=False) (zero-padded linear convolution) is not lowered yet")
+        self._otf_cache = {}
         if isinstance(psf, Placeholder):
             def on_change(val):
                 self.psf = nn.Parameter(val, requires_grad=False)
-                self._otf_cache = None
+                self._otf_cache = {}
             psf.change(on_change)
             if psf._value is not None:
                 on_change(psf._value)
         else:
             self.psf = nn.Parameter(to_torch_tensor(psf, batch=True).float(), requires_grad=False)
 
-    def _otf_half(self, shape):
+    def _otf(self, shape):
         key = (tuple(shape), self.psf.data_ptr(), self.psf._version)
-        if self._otf_cache is None or self._otf_cache[0] != key:
+        hit = self._otf_cache.get(tuple(shape))
+        if hit is None or hit[0] != key:
             full = psf2otf2(self.psf.detach(), shape)
-            self._otf_cache = (key, full, _half(full))
-        return self._otf_cache[2]
+            hit = (key, full, _half(full))
+            self._otf_cache[tuple(shape)] = hit
+        return hit
+
+    def _otf_half(self, shape):
+        return self._otf(shape)[2]
 
     def _gram_half(self, shape):
         o = self._otf_half(shape)
         return (o.conj() * o).real.float().contiguous()
 
+    def _apply(self, img, conj):
+        if self.circular:
+            return ops.spectral_filter(img, self._otf_half(_shape4(img)), conj=conj)
+        B, Cc, H, W = _shape4(img)
+        pt, pb, pl, pr = linear_conv_pads(H, W)
+        big = ops.pad2d(img.reshape(B, Cc, H, W), (H + pt + pb, W + pl + pr), pt, pl)
+        out = ops.spectral_filter(big, self._otf_half(tuple(big.shape)), conj=conj)
+        # the reference crops with [pt:-pb, pl:-pr]
+        return ops.pad2d(out, (H, W), -pt, -pl).reshape(img.shape)
+
     def forward(self, img, **kw):
-        return ops.spectral_filter(img, self._otf_half(_shape4(img)), conj=False)
+        return self._apply(img, False)
 
     def adjoint(self, img, **kw):
-        return ops.spectral_filter(img, self._otf_half(_shape4(img)), conj=True)
+        return self._apply(img, True)
 
     def is_diag(self, freq=False):
         return freq and self.input_nodes[0].is_diag(freq)
 
     def get_diag(self, x, freq=False):
         assert freq
-        self._otf_half(_shape4(x))
-        full = self._otf_cache[1]
+        full = self._otf(_shape4(x))[1]
         return torch.abs(torch.conj(full) * full).to(self.device)
 
     def lower(self):
         child = self.input_nodes[0].lower()
         if child is None or child.const or child.kind != "identity":
             return None
-        return Lowered("spectral", child.scale, otf_fn=self._otf_half, gram_fn=self._gram_half)
+        # linear mode: K^T b must come from this node's own (padded) adjoint, so no OTF is offered for spectral shortcuts
+        return Lowered("spectral", child.scale, otf_fn=self._otf_half if self.circular else None, gram_fn=self._gram_half)
 
 
 def bayer_mask(H: int, W: int) -> torch.Tensor:

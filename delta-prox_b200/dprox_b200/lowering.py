@@ -103,6 +103,11 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
         if spec.xupdate == "freq" and not try_freq_diagonalize:
             spec.xupdate, spec.reason = "none", "frequency diagonalisation disabled"
             return spec
+        # The reference applies the prox to x itself and ignores the psi LINOP except for its constant (pgd.py:39-43): only
+        # an unscaled identity linop has that meaning in the fused plan; anything else takes the reference's literal step.
+        if psi[0].kind != "identity" or float(psi[0].scale) != 1.0 or (q.kind == "spectral" and q.low.otf_fn is None):
+            spec.xupdate, spec.reason = "none", "PGD with a non-identity psi linop: prox applied to x as in the reference"
+            return spec
         spec.tier = "native"
         return spec
 
@@ -120,9 +125,17 @@ def analyze(psi_fns, omega_fns, method: str, try_diagonalize=True, try_freq_diag
     if method in ("pc", "custom_admm"):
         spec.reason = f"{method} is composed node by node (closed-form x-update where diagonalisable)"
         return spec
+    if method == "admm_vxu" and spec.has_external:
+        spec.reason = "ADMM_vxu with an external prox: composed node by node (closed-form x-update)"
+        return spec
     # can the psi side be fused?
     for t in psi:
         if t.kind == "identity":
+            # LinearizedADMM forms b_i = x - K^T(Kx - v + u) = (1 - s^2) x + s (v - u): ADMM's v - u only for |s| = 1
+            # (algo/admm.py:82-90), so scaled identity terms keep the reference's literal update
+            if method == "ladmm" and abs(float(t.scale)) != 1.0:
+                spec.reason = "LADMM with a scaled identity psi linop: composed node by node"
+                return spec
             continue
         if t.kind in ("grad", "grad2d") and spec.xupdate == "freq" and method in ("admm", "hqs") \
                 and (t.kind == "grad" or t.prox_kind != cabi.PROX_EXTERNAL):
@@ -454,14 +467,16 @@ class GenericEngine(_EngineBase):
         self.ktb = None
         if spec.xupdate in ("freq", "spatial", "scalar"):
             B, Cc, H, W = self.shape4
-            if spec.xupdate != "freq":
-                # spatial: dq + rho * dpsi has no slot in the spatial kernel unless dpsi is a constant -> fold as wid
-                raise NotImplementedError("generic engine with a spatial-diagonal closed form")
             d = cabi.ProblemDesc()
             d.abi_version = cabi.ABI_VERSION
             d.batch, d.channels, d.height, d.width = B, Cc, H, W
             d.algo, d.n_psi, d.eps, d.fft_backend = cabi.ALGO_ADMM, 0, self.eps, cabi.FFT_AUTO     # fused x-update for 2^k sizes
-            d.xupdate, d.eps_delta = cabi.X_FREQ_DIAG, 0
+            if spec.xupdate == "freq":
+                d.xupdate, d.eps_delta = cabi.X_FREQ_DIAG, 0
+            else:
+                # spatial closed form (ktb + rho t) / (dq + rho dpsi + eps) (sum_square.py:142-148, 154); identity-only
+                # objectives take the reference's Fourier branch with a constant diagonal = the same quotient + eps * delta_0
+                d.xupdate, d.eps_delta = cabi.X_SPATIAL_DIAG, int(spec.xupdate == "scalar")
             self.plan = cabi.NativePlan(d, self.device)
         self.set_constants()
 
@@ -478,11 +493,21 @@ class GenericEngine(_EngineBase):
         if self.plan is None:
             return
         ktb4 = None if self.ktb is None else self._v(self.ktb.detach()).contiguous()
-        dq = _gram_diag(spec.quad, self.shape4, dev, True)
-        dpsi = _gram_diag(spec.psi, self.shape4, dev, True)        # identity contributions folded in (plan has wid = 0)
+        freq = spec.xupdate == "freq"
+        dq = _gram_diag(spec.quad, self.shape4, dev, freq)
+        dpsi = _gram_diag(spec.psi, self.shape4, dev, freq)        # identity contributions folded in (plan has wid = 0)
+        if dpsi is not None and dpsi.shape[0] != 1:
+            raise NotImplementedError("per-sample psi diagonals")
+        lib, s = cabi.lib(), cabi.stream_ptr(dev)
         with torch.cuda.device(dev):
-            cabi.check(cabi.lib().dpx_plan_set_freq_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0],
-                                                              cabi.ptr(dpsi), cabi.stream_ptr(dev)), "dpx_plan_set_freq_constants")
+            if freq:
+                cabi.check(lib.dpx_plan_set_freq_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0],
+                                                           cabi.ptr(dpsi), s), "dpx_plan_set_freq_constants")
+            else:
+                cabi.check(lib.dpx_plan_set_spatial_constants(self.plan.handle, cabi.ptr(ktb4), cabi.ptr(dq), dq.shape[0], s),
+                           "dpx_plan_set_spatial_constants")
+                cabi.check(lib.dpx_plan_set_spatial_psi_diag(self.plan.handle, cabi.ptr(dpsi), s), "dpx_plan_set_spatial_psi_diag")
+        self.plan.const_version += 1                               # autograd.XSolve refuses a backward across a constant change
         self._keep = (ktb4, dq, dpsi)
 
     # linop application through the tree -------------------------------------------------------------

@@ -97,6 +97,40 @@ def grad(x: torch.Tensor, axis: int, adjoint: bool = False, scale: float = 1.0) 
     return out
 
 
+def pad2d(x: torch.Tensor, out_hw, top: int, left: int) -> torch.Tensor:
+    """out[..., y, x] = in[..., y - top, x - left] inside the input, 0 elsewhere: zero padding (offsets >= 0) or cropping
+    (offsets < 0) of the last two axes -- the data movement of the `circular=False` convolutions (linop/conv.py:100-121)."""
+    if ag.needs_grad(x):
+        return ag.Pad2d.apply(x, tuple(out_hw), int(top), int(left))
+    x = cabi.require_cuda_f32(x, "x")
+    hi, wi = x.shape[-2:]
+    ho, wo = out_hw
+    out = torch.empty(*x.shape[:-2], ho, wo, device=x.device, dtype=torch.float32)
+    planes = x.numel() // (hi * wi)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_pad2d(cabi.ptr(x), cabi.ptr(out), planes, hi, wi, ho, wo, int(top), int(left), _s(x)), "dpx_pad2d")
+    return out
+
+
+def augment(x: torch.Tensor, mode: int) -> torch.Tensor:
+    """One of the 8 flips / rotations of the x8 test-time augmentation (pnp/denoisers/composite.py:30-47) of [B,C,H,W]."""
+    mode = int(mode) % 8
+    if mode == 0:
+        return x
+    if ag.needs_grad(x):
+        return ag.Augment.apply(x, mode)
+    x = cabi.require_cuda_f32(x, "x")
+    B, Cc, H, W = x.shape
+    tr = mode in (1, 3, 5, 7)
+    out = torch.empty(B, Cc, W if tr else H, H if tr else W, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().dpx_augment(cabi.ptr(x), cabi.ptr(out), B * Cc, H, W, mode, _s(x)), "dpx_augment")
+    return out
+
+
+AUGMENT_INVERSE = {0: 0, 1: 1, 2: 2, 3: 5, 4: 4, 5: 3, 6: 6, 7: 7}     # the transform that undoes mode m
+
+
 def prox(kind: int, v: torch.Tensor, lam: torch.Tensor, alpha=1.0, beta=1.0, lo=0.0, hi=0.0, offset=None, out=None):
     """ProxFn.prox with the wrapper chain for a native `_prox` body (proxfn/base.py:55-64)."""
     if out is None and ag.needs_grad(v, lam, offset):
@@ -193,6 +227,13 @@ def cg_update(x, r, p, q, gamma, pq, per_sample=True) -> torch.Tensor:
         cabi.check(cabi.lib().dpx_cg_update(cabi.ptr(x), cabi.ptr(r), cabi.ptr(p), cabi.ptr(q), cabi.ptr(gamma), cabi.ptr(pq),
                                             cabi.ptr(gn), B, x.numel() // B, _s(x)), "dpx_cg_update")
     return gn
+
+
+def cg_gate(val, tol, pq, done, strict=False):
+    """device-side stop test: done |= all(val <= tol) (strict: <); while done, pq := +inf so that the next cg_update is a no-op"""
+    with torch.cuda.device(val.device):
+        cabi.check(cabi.lib().dpx_cg_gate(cabi.ptr(val), cabi.ptr(tol), int(tol.numel()), int(strict), cabi.ptr(pq),
+                                          C.c_void_p(done.data_ptr()), int(val.numel()), _s(val)), "dpx_cg_gate")
 
 
 def cg_direction(p, r, gamma_new, gamma_old, per_sample=True):

@@ -212,15 +212,25 @@ def _padded_kernel(psf: torch.Tensor, out_shape) -> torch.Tensor:
 
 def img_psf_conv(img: torch.Tensor, psf: torch.Tensor, circular: bool = True) -> torch.Tensor:
     """Data formation `ifft2(fft2(img) * otf).real` (common.py:85-118), differentiable w.r.t. the image and the PSF."""
-    if not circular:
-        raise NotImplementedError("img_psf_conv(circular=False) (zero-padded linear convolution) is not lowered")
     img = cabi.require_cuda_f32(img, "img")
+    crop = None
+    if not circular:                                     # linear convolution: zero-pad to twice the size, crop (common.py:97-117)
+        from . import ops
+        from .linop import linear_conv_pads
+        H, W = img.shape[-2:]
+        pt, pb, pl, pr = linear_conv_pads(H, W)
+        img = ops.pad2d(img, (H + pt + pb, W + pl + pr), pt, pl)
+        crop = (H, W, pt, pl)
     kern = _padded_kernel(psf.to(img.device, torch.float32), img.shape)
     n = img.shape[-2] * img.shape[-1]
     X = C2C.apply(ToComplex.apply(img), False)
     K = C2C.apply(ToComplex.apply(kern), False)
     Y = C2C.apply(CMul.apply(X, K, 1.0 / n), True)
-    return RealPart.apply(Y)
+    out = RealPart.apply(Y)
+    if crop is not None:
+        from . import ops
+        out = ops.pad2d(out, crop[:2], -crop[2], -crop[3])
+    return out
 
 
 class FresnelPropagator(nn.Module):

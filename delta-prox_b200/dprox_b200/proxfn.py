@@ -234,6 +234,26 @@ class Denoiser(nn.Module):
         raise NotImplementedError
 
 
+class Augment(nn.Module):
+    """x8 test-time augmentation (pnp/denoisers/composite.py:6-28): call k denoises the image under flip / rotation k mod 8
+    and undoes it afterwards (native permutation kernels, `ops.augment`)."""
+
+    def __init__(self, base_denoiser):
+        super().__init__()
+        self.base_denoiser = base_denoiser
+        self.iter = 0
+
+    def denoise(self, x: torch.Tensor, sigma: torch.Tensor):
+        m = self.iter % 8
+        y = self.base_denoiser.denoise(ops.augment(x, m), sigma)
+        y = ops.augment(y.contiguous(), 8 - m if m in (3, 5) else m)
+        self.iter += 1
+        return y
+
+    def reset(self):
+        self.iter = 0
+
+
 class deep_prior(ProxFn):
     """Deep denoiser as a proximal operator (pnp/prior.py:42-89).  `denoiser` is a `Denoiser`
     instance (or any module with `.denoise(x, sigma)`); named pretrained models need their weight
@@ -246,8 +266,9 @@ class deep_prior(ProxFn):
         if isinstance(denoiser, str):
             from .denoisers import get_denoiser
             denoiser = get_denoiser(denoiser)
+        self.x8 = x8
         if x8:
-            raise NotImplementedError("x8 test-time augmentation is not part of the lowered path")
+            denoiser = Augment(denoiser)
         self.denoiser = denoiser
         self.clamp, self.sqrt = clamp, sqrt
         if not trainable:
@@ -257,6 +278,10 @@ class deep_prior(ProxFn):
         if self.unroll:
             import copy
             self.denoisers = nn.ModuleList([copy.deepcopy(self.denoiser) for _ in range(unroll_step)])
+
+    def _reload(self, shape=None):
+        if self.x8:
+            self.denoiser.reset()
 
     def eval(self, v):
         raise NotImplementedError("deep prior cannot be explictly evaluated")

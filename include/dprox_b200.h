@@ -138,6 +138,17 @@ int dpx_plan_set_rhs_spectral(dpx_plan* plan, const float* b, const float* otf, 
 /* SPATIAL_DIAG. ktb real [B,C,H,W]; dq real [dq_batch,C,H,W] (mask diagonal). */
 int dpx_plan_set_spatial_constants(dpx_plan* plan, const float* ktb, const float* dq, int dq_batch,
                                    void* stream);
+/* SPATIAL_DIAG, optional: dpsi real [C,H,W] = sum over psi terms of scale_i^2 * diag_i (mask-type psi linops such as
+ * norm1(mosaic(x)), or every psi term when the plan has n_psi = 0 and is driven through dpx_xsolve); the x-update divides by
+ * dq + rho (dpsi + wid) + eps (sum_square.py:142-148, 154).  NULL clears. */
+int dpx_plan_set_spatial_psi_diag(dpx_plan* plan, const float* dpsi, void* stream);
+/* Which transform engine the plan's last fused call ran on: introspection for tests and bench lines. */
+#define DPX_ENGINE_NONE (-1)        /* SPATIAL_DIAG plan: no transform */
+#define DPX_ENGINE_CUFFT 0          /* cuFFT R2C / C2R + element-wise kernels (any size) */
+#define DPX_ENGINE_FUSED_PLANES 1   /* fused sm_100a FFT kernels, half-spectrum planes */
+#define DPX_ENGINE_FUSED_PAIRS 2    /* fused kernels, two planes per complex transform (even batch) */
+#define DPX_ENGINE_FUSED_FLAT 3     /* fused kernels, planes paired across channels (+ odd last plane on the half-spectrum engine) */
+int dpx_plan_engine_mode(const dpx_plan* plan);
 /* Optional constant inside psi term i's linop (`norm1(x - c)`), real [B,C,H,W]; NULL clears. */
 int dpx_plan_set_psi_offset(dpx_plan* plan, int i, const float* c, void* stream);
 
@@ -170,12 +181,13 @@ int dpx_stage_prox(dpx_plan* plan, float* x, float* const* v, float* const* u,
  * SPATIAL: (ktb + rho t)/(dq + rho wid + eps).  Lets the host compose LADMM / ADMM_vxu / external-prox
  * variants from the stand-alone kernels below.  (sum_square.py:123-156) */
 int dpx_xsolve(dpx_plan* plan, const float* t, const float* rho, int rho_stride, int it, float* x, void* stream);
-/* Backward of dpx_xsolve (FREQ_DIAG), the closed form of what the reference obtains by autograd through
+/* Backward of dpx_xsolve, the closed form of what the reference obtains by autograd through
  * least_squares.solve_direct (sum_square.py:123-156; used by unrolled training, specialization/unroll.py:42-58):
  * given g = dL/dx and the forward output x,
  *   g_ktb = F^-1[F(g) / Dn]                 (= dL/d(sum_q A_q^T b_q);  dL/dt = rho * g_ktb)
  *   g_rho = sum_k Re(conj(F g)_k (F(t) - (dpsi+wid) F(x))_k / Dn_k) / (H W)      [B] if rho_stride != 0, else [1]
- * with Dn = dq + rho (dpsi + wid) + eps.  g_rho may be NULL.  x is only read when g_rho is requested. */
+ * with Dn = dq + rho (dpsi + wid) + eps.  g_rho may be NULL.  x is only read when g_rho is requested.
+ * SPATIAL_DIAG plans: g_ktb = g / D, g_rho = sum g_ktb (x (dq + eps) - ktb) / rho with the same D in pixel space. */
 int dpx_xsolve_backward(dpx_plan* plan, const float* g, const float* x, const float* rho, int rho_stride, int it,
                         float* g_ktb, float* g_rho, void* stream);
 /* v_i <- K_i x0 (affine: scale * A_i x0 - c_i), u_i <- 0.   ADMM.initialize / HQS.initialize
@@ -212,6 +224,14 @@ int dpx_axpby(float* out, float a, const float* x, float b, const float* y, size
 int dpx_grad_apply(const float* x, float* y, int planes, int height, int width, int axis, int adjoint,
                    float scale, void* stream);
 
+/* out[p][y][x] = in[p][y - top][x - left] where that lies inside the [h_in, w_in] input, else 0: the zero padding (top, left >= 0)
+ * and the crop (negative offsets) of the `circular=False` convolutions (linop/conv.py:100-121, contrib/optic/common.py:97-117). */
+int dpx_pad2d(const float* in, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int top, int left,
+              void* stream);
+/* the 8 flips / rotations of the x8 test-time augmentation, Augment.augment (proxfn/pnp/denoisers/composite.py:30-47);
+ * modes 1, 3, 5, 7 transpose: out is [planes, width, height]. */
+int dpx_augment(const float* in, float* out, int planes, int height, int width, int mode, void* stream);
+
 /* out = w * x — mosaic / mul_elementwise forward = adjoint (linop/subsample.py:18-31, linop/mul.py:59-65).
  * w: real [w_batch, per_sample], w_batch in {1, batch}. */
 int dpx_mul_apply(float* out, const float* x, const float* w, int w_batch, int batch, size_t per_sample,
@@ -228,6 +248,12 @@ int dpx_cg_update(float* x, float* r, const float* p, const float* q, const floa
 /* beta_b = gamma_new_b / gamma_old_b ; p = r + beta p    (cg :113-116) */
 int dpx_cg_direction(float* p, const float* r, const float* gamma_new, const float* gamma_old, int batch,
                      size_t per_sample, void* stream);
+
+/* Device-side stop test of cg / pcg (solver_cg.py:103-107, 225-229), no host round trip: *done (device int, zeroed by the
+ * caller before the solve) becomes and stays 1 once val[b] <= tol[b] (strict != 0: <) for every b in the batch; while it is
+ * set, pq[b] is overwritten with +inf, which makes the following dpx_cg_update a no-op (alpha = 0, x and r frozen).
+ * tol: device [tol_n], tol_n in {1, batch}. */
+int dpx_cg_gate(const float* val, const float* tol, int tol_n, int strict, float* pq, int* done, int batch, void* stream);
 
 /* ---- native deep-denoiser (FFDNet-color) on tcgen05 tensor cores ---------------------------------------------
  * deep_prior -> FFDNetColorDenoiser -> FFDNet.forward (proxfn/pnp/prior.py:73-86, denoisers/wrapper.py:38-48,

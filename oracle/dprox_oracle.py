@@ -466,6 +466,7 @@ class Term:
     sqrt: bool = False
     clamp: bool = False
     custom_prox: Optional[Callable] = None
+    box: tuple = (0.0, 1.0)
 
     # -- the affine linop and its constant part ------------------------------------------
     def K(self, x):
@@ -501,6 +502,8 @@ class Term:
             return out.to(v.dtype).reshape(v.shape)
         if self.kind == "iso_tv":
             return prox_iso_tv(v, lam)
+        if self.kind == "box":                           # NOT in the reference (north star): projection onto [lo, hi]
+            return torch.clamp(v, self.box[0], self.box[1])
         if self.kind == "custom":
             return self.custom_prox(v, lam)
         raise ValueError(self.kind)

@@ -49,6 +49,15 @@ def _worker(rank, world, port, q):
         dec = stop.converged(sums, n_elems=10)
         r, s = stop.history[-1]
         ok_stop = dec and abs(r - 2.0) < 1e-6 and abs(s - 2.0) < 1e-6          # sqrt(1+3) = 2 <= 0.5*sqrt(64)
+        # asynchronous form: decisions are consumed one check late, identically on every rank
+        lazy = ResidualStop(abstol=0.0, reltol=0.5, every=1, lag=1)
+        lazy.submit(sums * torch.tensor([100.0, 100.0, 1.0, 1.0]), n_elems=10)    # check 0: not converged
+        first = lazy.poll()                                                    # nothing old enough yet
+        lazy.submit(sums, n_elems=10)                                          # check 1: converged
+        second = lazy.poll()                                                   # consumes check 0
+        lazy.submit(sums, n_elems=10)
+        third = lazy.poll()                                                    # consumes check 1 -> stop
+        ok_stop = ok_stop and (first, second, third) == (False, False, True) and len(lazy.history) == 2
         # solve_sharded plumbing with a stand-in solver (no GPU here): each rank handles its shard only
         class Fake:
             def solve(self, x0, rhos, lams, **kw):

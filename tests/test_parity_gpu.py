@@ -342,10 +342,18 @@ def test_residual_stop_and_host_entry(dp):
     x = dp.Variable()
     b = T(g["b"])
     solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x), method="admm", device="cuda")
-    stop = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=5)
-    solver.solve(x0=b, max_iter=200, stop=stop)
-    assert solver.iterations_run < 200 and len(stop.history) == solver.iterations_run // 5
+    stop = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=5, lag=0)            # blocking variant
+    x_sync = solver.solve(x0=b, max_iter=200, stop=stop).clone()
+    n_sync = solver.iterations_run
+    assert n_sync < 200 and len(stop.history) == n_sync // 5
     assert stop.history[-1][0] < stop.history[0][0]
+    # asynchronous variant (side-stream reduction, decision consumed one check late): one extra block of iterations
+    lazy = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=5)
+    solver.solve(x0=b, max_iter=200, stop=lazy)
+    assert solver.iterations_run == n_sync + 5 and len(lazy.history) == n_sync // 5
+    assert lazy.history == stop.history or all(abs(a[0] - c[0]) <= 1e-6 * abs(c[0]) for a, c in zip(lazy.history, stop.history))
+    ref = solver.solve(x0=b, max_iter=n_sync)                                   # the rule stopped exactly where it said it did
+    assert rel(x_sync, ref) < 1e-6
     # host-buffer entry point (the e2e leg of bench.py): H2D + T iterations + D2H through one C-ABI call
     eng = solver.engine(b)
     x0h = torch.from_numpy(g["b"]).pin_memory()

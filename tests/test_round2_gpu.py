@@ -1,0 +1,398 @@
+"""Round-2 GPU parity tests (`pytest -m gpu`), all through Python host mirror -> ctypes -> libdprox_b200.so:
+
+ * the BENCH PATH at the headline configuration ([2,3,2048,2048], Placeholder-fed measurements -> dpx_plan_set_rhs_spectral
+   -> plane-pair engine k_rowz / k_col<2048> / k_rowz_mid_persist<2048>) against the oracle after 1, 5 and 50 iterations
+   (fp64 arbiter at 50) and the host-buffer entry point at that size;
+ * vectors produced by the UNMODIFIED reference at sizes the fused engine takes (BASELINE cfg1 [1,3,256,256] x 50, radix-12
+   and radix-10 rows), BASELINE cfg3 as stated (BlackBox + TV, LADMM, PCG), the `box` projection;
+ * the rows that were partial in round 1 (conv_doe / img_psf_conv circular=False, grad(dim=2), ADMM_vxu + external prox,
+   deep_prior(x8=True), UnrolledSolver(share=False, learned_params), spatial-diagonal closed form in the node-by-node /
+   differentiable engine) and the advisor's cases, each against a golden from the reference.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dprox_oracle as orc
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL_X, TOL_AUX = 1e-5, 5e-5
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import dprox_b200
+    from dprox_b200 import _cabi
+    _cabi.lib()
+    return dprox_b200
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def check_state(state, g, prefix="", tol_x=TOL_X, tol_aux=TOL_AUX):
+    for name, s in zip(["s0", "s1", "s2"], state):
+        if isinstance(s, (list, tuple)):
+            for i, e in enumerate(s):
+                r = rel(e, g[f"{prefix}{name}_{i}"])
+                assert r < tol_aux, (name, i, r)
+        else:
+            r = rel(s, g[prefix + name])
+            assert r < tol_x, (name, r)
+
+
+def run(dp, fns, method, x0, T_, rhos=None, lams=None, **kw):
+    solver = dp.compile(fns, method=method, device="cuda", **kw)
+    return solver, solver.solve(x0=x0, rhos=rhos, lams=lams, max_iter=T_, return_full_states=True)
+
+
+def engine_mode(solver):
+    return solver._engine.plan.engine_mode()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  1. the bench path at the headline configuration
+# ---------------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def headline():
+    """bench.py's workload at B = 2: img ~ U[-0.3, 0.7), b = blur(img) + 0.01 noise, PSF gaussian 15/5, rho = 1, lam = 0.02;
+    oracle states after 1, 5 and 50 ADMM iterations (fp32) and the fp64 run of sample 0 as the arbiter at 50."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)
+    B, Cc, H, W = 2, 3, 2048, 2048
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(15, 5)
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)
+    del img
+    snaps = {}
+
+    def grab(iter, state, rho, lam):
+        if iter + 1 in (1, 5, 50):
+            snaps[iter + 1] = (state[0].clone(), state[1][0].clone(), state[2][0].clone())
+
+    with torch.no_grad():
+        orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")], "admm").solve(
+            b.clone(), rhos=1.0, lams=0.02, max_iter=50, callback=grab)
+        b0 = b[:1].double()
+        x64 = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b0), orc.Term("nonneg")], "admm",
+                         dtype=torch.float64).solve(b0.clone(), rhos=1.0, lams=0.02, max_iter=50)
+    return dict(b=b, psf=psf, snaps=snaps, x64=x64)
+
+
+def test_bench_path_headline_vs_oracle(dp, headline):
+    from dprox_b200 import _cabi as cabi
+    b = headline["b"].cuda()
+    x, y = dp.Variable(), dp.Placeholder()
+    solver = dp.compile(dp.sum_squares(dp.conv(x, headline["psf"]) - y) + dp.nonneg(x), method="admm", device="cuda")
+    y.value = (0.5 * b).contiguous()                 # a first batch of measurements builds the plan ...
+    solver.solve(x0=b, rhos=1.0, lams=0.02, max_iter=1)
+    eng = solver._engine
+    y.value = b                                      # ... the bench's batch only re-hoists F(K^T b): dpx_plan_set_rhs_spectral
+    for T_ in (1, 5, 50):
+        rhos = torch.full((T_,), 1.0, device="cuda")             # device-resident schedules, as bench.py passes them
+        lams = torch.full((T_,), 0.02, device="cuda")
+        st = solver.solve(x0=b, rhos=rhos, lams=lams, max_iter=T_, return_full_states=True)
+        assert solver._engine is eng and engine_mode(solver) == cabi.ENGINE_FUSED_PAIRS
+        wx, wv, wu = headline["snaps"][T_]
+        tx = TOL_X if T_ < 50 else 1.5e-5            # the fp32 reference itself carries ~8e-6 of round-off at 50 iterations
+        assert rel(st[0], wx) < tx, (T_, "x", rel(st[0], wx))
+        assert rel(st[1][0], wv) < TOL_AUX and rel(st[2][0], wu) < TOL_AUX, (T_, rel(st[1][0], wv), rel(st[2][0], wu))
+        if T_ == 50:
+            ours, ref = rel(st[0][:1], headline["x64"]), rel(wx[:1], headline["x64"])
+            assert ours < 1e-5 and ours < 2 * ref + 1e-6, (ours, ref)
+
+
+def test_solve_host_headline_size(dp, headline):
+    """the e2e leg's C entry (H2D + init + iterations + D2H in one call) at [2,3,2048,2048], against the oracle at 5 iterations"""
+    from dprox_b200 import _cabi as cabi
+    b = headline["b"].cuda()
+    x = dp.Variable()
+    solver = dp.compile(dp.sum_squares(dp.conv(x, headline["psf"]) - b) + dp.nonneg(x), method="admm", device="cuda")
+    eng = solver.engine(b)
+    out = eng.solve_host(headline["b"].pin_memory(), torch.full((5,), 1.0), torch.full((5,), 0.02), 5)
+    assert eng.plan.engine_mode() == cabi.ENGINE_FUSED_PAIRS
+    assert rel(out, headline["snaps"][5][0]) < TOL_X
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  2. reference vectors through the fused engine: cfg1, radix-12 / radix-10 rows; cfg3 as stated; box
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_cfg1_256_reference_golden(dp):
+    """BASELINE configs[0]: [1,3,256,256], sum_squares(conv)+nonneg, ADMM x 50 -- a single RGB image rides the FLAT pairing
+    (two channels on the pair engine, the third on the half-spectrum engine)."""
+    from dprox_b200 import _cabi as cabi
+    g = load("cfg1_admm_256_50it")
+    x = dp.Variable()
+    b = T(g["b"])
+    solver, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x), "admm", b, 50, rhos=1.0, lams=0.02)
+    assert engine_mode(solver) == cabi.ENGINE_FUSED_FLAT
+    b64 = torch.from_numpy(g["b"]).double()
+    x64 = orc.Solver([orc.Term("sum_squares", orc.Conv(g["psf"], orc.Identity()), c=b64), orc.Term("nonneg")], "admm",
+                     dtype=torch.float64).solve(b64.clone(), rhos=1.0, lams=0.02, max_iter=50)
+    ours, ref = rel(st[0], x64), rel(g["s0"], x64)
+    assert rel(st[0], g["s0"]) < 2e-5 and ours < 1e-5 and ours < 2 * ref + 1e-6, (rel(st[0], g["s0"]), ours, ref)
+
+
+@pytest.mark.parametrize("case,method", [("admm_fused_128x192", "admm"), ("hqs_fused_64x320", "hqs")])
+def test_fused_radix12_radix10_reference_goldens(dp, case, method):
+    from dprox_b200 import _cabi as cabi
+    g = load(case)
+    x = dp.Variable()
+    b = T(g["b"])
+    solver, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.nonneg(x), method, b, int(g["T"]), rhos=float(g["rho"]),
+                     lams=0.02)
+    assert engine_mode(solver) == cabi.ENGINE_FUSED_PAIRS
+    check_state(st, g)
+
+
+def test_cfg3_blackbox_tv_ladmm_pcg(dp):
+    """BASELINE configs[2] as stated: subsampled-FFT BlackBox + TV, LADMM, PCG inner solve (3 iterations)."""
+    g = load("ladmm_csmri_blackbox_3it")
+    mask = T(g["mask"])
+    fwd = lambda x, step=0: mask * torch.fft.fft2(x, norm="ortho")
+    adj = lambda y, step=0: torch.real(torch.fft.ifft2(mask * y, norm="ortho")).contiguous()
+    y0 = torch.complex(T(g["y0_re"]), T(g["y0_im"]))
+    x = dp.Variable()
+    A = dp.LinOpFactory(fwd, adj)
+    fns = dp.sum_squares(A(x), y0) + dp.norm1(dp.grad(x, dim=0)) + dp.norm1(dp.grad(x, dim=1))
+    cfg = dp.LinearSolveConfig(rtol=1e-6, max_iters=int(g["cg_iters"]), solver_type="pcg")
+    s, st = run(dp, fns, "ladmm", T(g["x0"]), int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]), linear_solve_config=cfg)
+    assert s.spec.tier == "generic" and s.spec.xupdate == "cg"
+    check_state(st, g, tol_x=3e-5, tol_aux=2e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (2, 3, 24, 40)])        # fused engine / cuFFT engine
+def test_box_projection(dp, shape):
+    """`box` (north star; absent from the reference): exact projection, and inside ADMM against the oracle restatement."""
+    gen = torch.Generator().manual_seed(5)
+    v = torch.randn(*shape, generator=gen)
+    f = dp.box(dp.Variable(), lo=-0.1, hi=0.4)
+    assert torch.equal(f.prox(v.cuda(), torch.tensor(0.3)).cpu(), v.clamp(-0.1, 0.4))
+    img = torch.rand(*shape, generator=gen) - 0.3
+    psf = orc.point_spread_function(7, 2.0)
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(*shape, generator=gen)
+    ob = orc.Term("box", box=(0.05, 0.5))
+    want = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), ob], "admm").solve(
+        b.clone(), rhos=0.8, lams=0.02, max_iter=8, return_full_states=True)
+    x = dp.Variable()
+    bd = b.cuda()
+    s, st = run(dp, dp.sum_squares(dp.conv(x, psf) - bd) + dp.box(x, lo=0.05, hi=0.5), "admm", bd, 8, rhos=0.8, lams=0.02)
+    assert s.spec.tier == "native"
+    assert rel(st[0], want[0]) < TOL_X and rel(st[1][0], want[1][0]) < TOL_AUX and rel(st[2][0], want[2][0]) < TOL_AUX
+    assert float(st[1][0].min()) >= 0.05 and float(st[1][0].max()) <= 0.5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  3. formerly partial rows
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_conv_doe_linear_mode(dp):
+    g = load("conv_doe_linear")
+    for tag in ("even", "small", "odd"):
+        psf, t, b = T(g[f"{tag}_psf"]), T(g[f"{tag}_t"]), T(g[f"{tag}_b"])
+        x = dp.Variable()
+        op = dp.conv_doe(x, psf, circular=False)
+        assert rel(op.forward(t), g[f"{tag}_fwd"]) < 2e-6 and rel(op.adjoint(t), g[f"{tag}_adj"]) < 2e-6, tag
+        s, st = run(dp, dp.sum_squares(dp.conv_doe(x, psf, circular=False) - b) + dp.nonneg(x), "hqs", b, int(g["T"]),
+                    rhos=float(g["rho"]))
+        check_state(st, g, prefix=tag + "_")
+
+
+def test_img_psf_conv_linear_mode(dp):
+    from dprox_b200.optics import img_psf_conv
+    g = load("img_psf_conv_linear")
+    for tag in ("same", "small"):
+        img = T(g[f"{tag}_img"]).requires_grad_(True)
+        psf = T(g[f"{tag}_psf"]).requires_grad_(True)
+        y = img_psf_conv(img, psf, circular=False)
+        (y * T(g[f"{tag}_w"])).sum().backward()
+        assert rel(y, g[f"{tag}_y"]) < 1e-5, tag
+        assert rel(img.grad, g[f"{tag}_g_img"]) < 1e-5 and rel(psf.grad, g[f"{tag}_g_psf"]) < 1e-5, tag
+
+
+def test_grad_channel_axis(dp):
+    gl = load("linops")
+    t = T(gl["t"])
+    x = dp.Variable()
+    op = dp.grad(x, dim=2)
+    assert rel(op.forward(t), gl["grad2_fwd"]) < 2e-6 and rel(op.adjoint(t), gl["grad2_adj"]) < 2e-6
+    assert np.abs(op.get_diag(t, freq=True).cpu().numpy() - gl["grad2_diag"]).max() < 1e-5
+    g = load("admm_grad_dim2")
+    b = T(g["b"])
+    fns = dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(dp.grad(x, dim=2)) + dp.norm1(dp.grad(x, dim=1))
+    s, st = run(dp, fns, "admm", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert s.spec.xupdate == "freq"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+
+
+def test_vxu_external_prox_and_x8(dp):
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    den = FFDNetColorDenoiser(seed=4).cuda()
+    g = load("vxu_deep_prior")
+    x = dp.Variable()
+    b = T(g["b"])
+    prior, nn_ = dp.deep_prior(x, denoiser=den), dp.nonneg(x)
+    s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + prior + nn_, "admm_vxu", b, int(g["T"]), rhos=float(g["rho"]),
+                lams={prior: T(g["sigmas"], "cpu"), nn_: 0.02})
+    assert s.spec.tier == "generic" and s.spec.xupdate == "freq"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+    g = load("deep_prior_x8")
+    x = dp.Variable()
+    b = T(g["b"])
+    prior, nn_ = dp.deep_prior(x, denoiser=FFDNetColorDenoiser(seed=4).cuda(), x8=True), dp.nonneg(x)
+    s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + prior + nn_, "admm", b, int(g["T"]), rhos=float(g["rho"]),
+                lams={prior: T(g["sigmas"], "cpu"), nn_: 0.02})
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+    # the permutation kernels against torch's flips / rotations, and their inverse table
+    from dprox_b200 import ops
+    t = torch.rand(2, 3, 10, 14, device="cuda")
+    for m in range(8):
+        assert torch.equal(ops.augment(t, m).cpu(), orc.augment(t.cpu(), m)), m
+        assert torch.equal(ops.augment(ops.augment(t, m), ops.AUGMENT_INVERSE[m]), t), m
+
+
+def test_unrolled_solver_share_false(dp):
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    g = load("unrolled_share_false")
+    b, wgt = T(g["b"]), T(g["wgt"])
+    x = dp.Variable()
+    f1 = dp.norm1(x)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - b) + f1, method="admm", device="cuda")
+    us = dp.specialize(solver, method="unroll", share=False, max_iter=3, learned_params=True)
+    assert isinstance(us, dp.UnrolledSolver) and len({id(s) for s in us.solvers}) == 3
+    assert torch.equal(us.rhos.detach().cpu(), torch.ones(3)) and sorted(n for n, _ in us.named_parameters() if "solvers" not in n) == ["norm1", "rhos"]
+    with torch.no_grad():
+        us.rhos.copy_(torch.tensor([0.6, 0.9, 1.3]))
+        us.lams[f1].copy_(torch.tensor([0.05, 0.03, 0.02]))
+    y = us.solve(x0=b, rhos=1.0, lams={f1: 1.0})
+    (y * wgt).sum().backward()
+    assert rel(y, g["lp_out"]) < 1e-5
+    assert rel(us.rhos.grad, g["lp_g_rhos"]) < 1e-4 and rel(us.lams[f1].grad, g["lp_g_lam"]) < 1e-4
+    # per-iteration trainable denoiser copies
+    den = FFDNetColorDenoiser(seed=int(g["seed"])).cuda()
+    x = dp.Variable()
+    prior = dp.deep_prior(x, denoiser=den, trainable=True)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - b) + prior, method="admm", device="cuda")
+    us = dp.build_unrolled_solver(solver, share=False, max_iter=3)
+    y = us.solve(x0=b, rhos=torch.tensor([0.6, 0.9, 1.3]), lams={prior: T(g["sig"], "cpu")})
+    (y * wgt).sum().backward()
+    assert rel(y, g["dn_out"]) < 2e-5
+    w0 = us.solvers[0].psi_fns[0].denoiser.model.model[0].weight
+    w1 = us.solvers[1].psi_fns[0].denoiser.model.model[0].weight
+    assert w0 is not w1 and rel(w0.grad, g["dn_g_w0"]) < 2e-3 and rel(w1.grad, g["dn_g_w1"]) < 2e-3
+    assert us.solvers[2].psi_fns[0].denoiser.model.model[0].weight.grad is None      # the last prox never reaches x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  4. advisor findings
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_spatial_and_scalar_closed_forms_in_the_generic_engine(dp):
+    g = load("pc_identity")
+    x = dp.Variable()
+    b = T(g["b"])
+    s, st = run(dp, dp.sum_squares(x - b) + dp.norm1(x), "pc", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert s.spec.tier == "generic" and s.spec.xupdate == "scalar"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+    g = load("admm_mask_psi")
+    x = dp.Variable()
+    b = T(g["b"])
+    s, st = run(dp, dp.sum_squares(x - b) + dp.norm1(dp.mosaic(x)), "admm", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+    assert s.spec.tier == "generic" and s.spec.xupdate == "spatial"
+    check_state(st, g)
+
+
+def test_ladmm_scaled_identity_and_pgd_psi_linop(dp):
+    g = load("ladmm_scaled_identity")
+    x = dp.Variable()
+    b = T(g["b"])
+    s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(2 * x), "ladmm", b, int(g["T"]), rhos=float(g["rho"]),
+                lams=float(g["lam"]))
+    assert s.spec.tier == "generic"
+    check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+    g = load("pgd_psi_linop")
+    b = T(g["b"])
+    for fn, key in ((lambda v: dp.norm1(dp.grad(v, dim=1)), "s0"), (lambda v: dp.norm1(2 * v), "scaled_s0")):
+        x = dp.Variable()
+        s, st = run(dp, dp.sum_squares(dp.conv(x, g["psf"]), b) + fn(x), "pgd", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
+        assert s.spec.tier == "generic"
+        assert rel(st[0], g[key]) < TOL_X, key
+
+
+def test_unrolled_gradients_spatial_diag(dp):
+    """unrolled training of a demosaicking objective: the differentiable engine with the spatial closed form + its backward"""
+    g = load("unrolled_grads_mosaic")
+    b = T(g["b"]).requires_grad_(True)
+    x0 = T(g["x0"]).requires_grad_(True)
+    rhos = T(g["rhos"]).requires_grad_(True)
+    lam1 = T(g["lam1"]).requires_grad_(True)
+    x = dp.Variable()
+    f1 = dp.norm1(x)
+    solver = dp.compile(dp.sum_squares(dp.mosaic(x) - b) + f1, method="admm", device="cuda")
+    out = solver.solve(x0=x0, rhos=rhos, lams={f1: lam1}, max_iter=int(g["T"]))
+    (out * T(g["wgt"])).sum().backward()
+    assert rel(out, g["out"]) < 1e-5
+    for name, t in (("g_b", b), ("g_x0", x0), ("g_rhos", rhos), ("g_lam1", lam1)):
+        assert rel(t.grad, g[name]) < 1e-4, (name, rel(t.grad, g[name]))
+
+
+def test_solve_host_with_stacked_gradient_state(dp):
+    """dpx_solve_host with an iso_tv term ([B,2C,H,W] state): same answer as the device entry (was an out-of-bounds write)"""
+    gen = torch.Generator().manual_seed(3)
+    b = torch.rand(2, 3, 32, 48, generator=gen)
+    psf = orc.point_spread_function(5, 1.5)
+    x = dp.Variable()
+    bd = b.cuda()
+    f1 = dp.iso_tv(x)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - bd) + f1, method="admm", device="cuda")
+    want = solver.solve(x0=bd, rhos=1.5, lams=0.03, max_iter=6).clone()
+    out = solver.engine(bd).solve_host(b.pin_memory(), torch.full((6,), 1.5), torch.full((6,), 0.03), 6)
+    assert rel(out, want) < 1e-6
+    torch.cuda.synchronize()
+
+
+def test_xsolve_backward_refuses_stale_constants(dp):
+    g = load("unrolled_grads_native")
+    b1 = T(g["b"]).requires_grad_(True)
+    x = dp.Variable()
+    y = dp.Placeholder()
+    f = dp.nonneg(x)
+    solver = dp.compile(dp.sum_squares(dp.conv(x, g["psf"]) - y) + f, method="admm", device="cuda")
+    rhos = torch.tensor([0.7, 0.9], device="cuda", requires_grad=True)
+    y.value = b1
+    out1 = solver.solve(x0=b1.detach(), rhos=rhos, lams=0.02, max_iter=2)
+    y.value = (b1.detach() * 0.5).requires_grad_(True)
+    out2 = solver.solve(x0=b1.detach(), rhos=rhos, lams=0.02, max_iter=2)
+    out2.sum().backward()                                    # the most recent graph is fine
+    with pytest.raises(RuntimeError, match="constants"):
+        out1.sum().backward()
+
+
+def test_cg_device_side_stop_matches_host_test(dp):
+    g = load("linear_solvers")
+    x = dp.Variable()
+    cv = dp.conv(x, g["psf"])
+    rhs = T(g["rhs"])
+    Aop = lambda v: dp.linalg.ops.axpby(1.0, v, 0.5, cv.adjoint(cv.forward(v)))
+    for fn in (dp.linalg.cg, dp.linalg.pcg):
+        a = fn(Aop, rhs, rtol=1e-4, max_iters=60)                       # device-side gate, host never blocks
+        c = fn(Aop, rhs, rtol=1e-4, max_iters=60, check_every=1)        # blocking host test every step
+        assert rel(a, c) < 1e-5, fn.__name__                            # (dot products use atomics: last-bit differences)
+        assert rel(Aop(a), rhs) < 1e-3
