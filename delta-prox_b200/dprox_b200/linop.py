@@ -717,7 +717,7 @@ class conv_doe(LinOp):
         o = self._otf_half(shape)
         return (o.conj() * o).real.float().contiguous()
 
-    def _apply(self, img, conj):
+    def _conv(self, img, conj):
         if self.circular:
             return ops.spectral_filter(img, self._otf_half(_shape4(img)), conj=conj)
         B, Cc, H, W = _shape4(img)
@@ -728,10 +728,10 @@ class conv_doe(LinOp):
         return ops.pad2d(out, (H, W), -pt, -pl).reshape(img.shape)
 
     def forward(self, img, **kw):
-        return self._apply(img, False)
+        return self._conv(img, False)
 
     def adjoint(self, img, **kw):
-        return self._apply(img, True)
+        return self._conv(img, True)
 
     def is_diag(self, freq=False):
         return freq and self.input_nodes[0].is_diag(freq)

@@ -771,11 +771,13 @@ def img_psf_conv_linear():
 
 @case
 def admm_grad_dim2():
-    """grad(x, dim=2) (channel axis, linop/grad.py:14-23) as a psi linop next to the H/W gradients."""
+    """grad(x, dim=2) (channel axis, linop/grad.py:14-23) as a psi linop next to the H and W gradients (all three, so that
+    the closed-form denominator has no near-null frequencies: the reference solves this in float64 -- int64 kernel -- and an
+    ill-conditioned case would measure precision, not the operator)."""
     img, psf, b = _deconv_inputs(2, 3, 32, 48, lo=0.0)
     x = dp.Variable()
-    f1, f2 = dp.norm1(dp.grad(x, dim=2)), dp.norm1(dp.grad(x, dim=1))
-    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2, "admm", b, 6, rhos=1.5, lams=0.02)
+    f1, f2, f3 = dp.norm1(dp.grad(x, dim=2)), dp.norm1(dp.grad(x, dim=1)), dp.norm1(dp.grad(x, dim=0))
+    out = _run(dp.sum_squares(dp.conv(x, psf) - b) + f1 + f2 + f3, "admm", b, 6, rhos=1.5, lams=0.02)
     return dict(psf=psf, b=_np(b), T=6, rho=1.5, lam=0.02, **out)
 
 

@@ -326,7 +326,7 @@ def test_img_psf_conv_linear():
 
 def test_grad_channel_axis():
     g = load("admm_grad_dim2")
-    psi = [orc.Term("norm1", orc.Grad(2, orc.Identity())), orc.Term("norm1", orc.Grad(1, orc.Identity()))]
+    psi = [orc.Term("norm1", orc.Grad(d, orc.Identity())) for d in (2, 1, 0)]
     st = orc.Solver(deconv_terms(g, psi), "admm").solve(T(g["b"]), rhos=float(g["rho"]), lams=float(g["lam"]),
                                                         max_iter=int(g["T"]), return_full_states=True)
     check_state(st, g, 3e-6)

@@ -86,13 +86,15 @@ def headline():
         if iter + 1 in (1, 5, 50):
             snaps[iter + 1] = (state[0].clone(), state[1][0].clone(), state[2][0].clone())
 
+    s64 = []
+
     with torch.no_grad():
         orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")], "admm").solve(
             b.clone(), rhos=1.0, lams=0.02, max_iter=50, callback=grab)
         b0 = b[:1].double()
-        x64 = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b0), orc.Term("nonneg")], "admm",
-                         dtype=torch.float64).solve(b0.clone(), rhos=1.0, lams=0.02, max_iter=50)
-    return dict(b=b, psf=psf, snaps=snaps, x64=x64)
+        s64 = orc.Solver([orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b0), orc.Term("nonneg")], "admm",
+                         dtype=torch.float64).solve(b0.clone(), rhos=1.0, lams=0.02, max_iter=50, return_full_states=True)
+    return dict(b=b, psf=psf, snaps=snaps, x64=s64[0], v64=s64[1][0], u64=s64[2][0])
 
 
 def test_bench_path_headline_vs_oracle(dp, headline):
@@ -110,12 +112,20 @@ def test_bench_path_headline_vs_oracle(dp, headline):
         st = solver.solve(x0=b, rhos=rhos, lams=lams, max_iter=T_, return_full_states=True)
         assert solver._engine is eng and engine_mode(solver) == cabi.ENGINE_FUSED_PAIRS
         wx, wv, wu = headline["snaps"][T_]
-        tx = TOL_X if T_ < 50 else 1.5e-5            # the fp32 reference itself carries ~8e-6 of round-off at 50 iterations
-        assert rel(st[0], wx) < tx, (T_, "x", rel(st[0], wx))
-        assert rel(st[1][0], wv) < TOL_AUX and rel(st[2][0], wu) < TOL_AUX, (T_, rel(st[1][0], wv), rel(st[2][0], wu))
-        if T_ == 50:
-            ours, ref = rel(st[0][:1], headline["x64"]), rel(wx[:1], headline["x64"])
-            assert ours < 1e-5 and ours < 2 * ref + 1e-6, (ours, ref)
+        errs = (rel(st[0], wx), rel(st[1][0], wv), rel(st[2][0], wu))
+        print(f"headline T={T_}: rel-L2 vs oracle fp32  x {errs[0]:.2e}  v {errs[1]:.2e}  u {errs[2]:.2e}")
+        if T_ < 50:
+            assert errs[0] < TOL_X and errs[1] < TOL_AUX and errs[2] < TOL_AUX, (T_, errs)
+            continue
+        # 50 iterations: the fp32 reference path itself carries ~1e-5 of accumulated round-off (and the dual variable, a
+        # running sum of 50 residuals over the ~30 % of pixels where the constraint is active, several times that), so both
+        # fp32 results are held to the fp64 run of the same algorithm
+        assert errs[0] < 1.5e-5, errs
+        for name, ours_t, ref_t, t64, cap in (("x", st[0], wx, headline["x64"], 1e-5), ("v", st[1][0], wv, headline["v64"], 2e-5),
+                                              ("u", st[2][0], wu, headline["u64"], 2e-4)):
+            ours, ref = rel(ours_t[:1], t64), rel(ref_t[:1], t64)
+            print(f"headline T=50 vs fp64: {name} ours {ours:.2e} oracle-fp32 {ref:.2e}")
+            assert ours < cap and ours < 2 * ref + 1e-6, (name, ours, ref)
 
 
 def test_solve_host_headline_size(dp, headline):
@@ -236,7 +246,7 @@ def test_grad_channel_axis(dp):
     assert np.abs(op.get_diag(t, freq=True).cpu().numpy() - gl["grad2_diag"]).max() < 1e-5
     g = load("admm_grad_dim2")
     b = T(g["b"])
-    fns = dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(dp.grad(x, dim=2)) + dp.norm1(dp.grad(x, dim=1))
+    fns = dp.sum_squares(dp.conv(x, g["psf"]) - b) + dp.norm1(dp.grad(x, dim=2)) + dp.norm1(dp.grad(x, dim=1)) + dp.norm1(dp.grad(x, dim=0))
     s, st = run(dp, fns, "admm", b, int(g["T"]), rhos=float(g["rho"]), lams=float(g["lam"]))
     assert s.spec.xupdate == "freq"
     check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
