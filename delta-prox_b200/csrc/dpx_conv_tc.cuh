@@ -1,0 +1,335 @@
+// dpx_conv_tc.cuh — hand-written 3x3 / stride 1 / pad 1 convolution on the 5th-generation tensor cores (sm_100a):
+// the FFDNet layers behind `deep_prior` (proxfn/pnp/denoisers/models/network_ffdnet.py:27-68), forward and data gradient.
+//
+// Formulation.  Implicit GEMM  D[pixel, cout] = sum_{tap, cin} A_tap[pixel, cin] * W_tap[cout, cin]  with
+//   * activations in HBM as channel-group-major bf16 with one explicit zero column on either side of every row,
+//       X[n][cg][h][W + 2][8]   (cg = channel / 8: 16 bytes per pixel and group; image pixel x lives at index x + 1),
+//   * one MMA = 2 x 128 pixels of one image row each, issued for a CTA PAIR (tcgen05 cta_group::2, M = 256, N = cout): each
+//     CTA owns 128 pixels (its TMEM lanes) and HALF of the filter bank (N/2 output channels), so the whole 3x3xCinxCout
+//     filter (162 KB for 96 -> 96) stays RESIDENT in shared memory for the lifetime of the kernel,
+//   * the activation rows a tile needs (y-1, y, y+1; 130 pixels each = 128 + halo) live in a ring of row slots filled by
+//     TMA (cp.async.bulk.tensor.5d; rows above / below the image = out-of-bounds zero fill, the left / right padding = the
+//     zero columns of the layout) and are REUSED for all nine taps and by three consecutive output rows: a tap is nothing
+//     but a different start address of the same shared-memory tile in the MMA's matrix descriptor (K-major, no swizzle:
+//     pixel stride 16 B, channel-group stride 130 * 16 B), so every activation is fetched from L2 once per row block
+//     (+ 2/16 halo) instead of once per tap.  (A TMA box dimension is limited to 256 elements and short inner runs are an
+//     order of magnitude slower, so the 130-pixel run of one channel group is described as 2 x 65 pixels of 8-byte
+//     elements with a separate unit-stride "start pixel" dimension.)
+//   * fp32 accumulators in TMEM, three stages (the MMAs of rows y+1, y+2 overlap the epilogue of row y),
+//   * epilogue (8 warps: two per TMEM lane quadrant, 48 channels each): tcgen05.ld x3 -> + bias -> ReLU (or the ReLU mask of
+//     the saved forward activation: data gradient) -> bf16 -> coalesced 16-byte stores in the same layout (the next
+//     layer's input).
+// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + (leader CTA) MMA issue,
+// warps 2..9 = epilogue.  Persistent: a cluster walks over pairs of (image, 128-pixel column tile, 16-row block) work units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpx {
+namespace convtc {
+
+constexpr int TILE_PX = 128;             // output pixels per CTA and tile row (= UMMA M per CTA)
+constexpr int HALO_PX = TILE_PX + 2;     // staged pixels per row
+constexpr int ROW_BLOCK = 16;            // output rows per work unit
+constexpr int NSLOT = 5;                 // activation row slots in the ring (3 live + 2 in flight)
+constexpr int N_EPI_WARPS = 8;
+constexpr int NTHREADS = 64 + 32 * N_EPI_WARPS;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
+
+template <int CGIN, int COUT>
+struct Cfg {
+  static constexpr int NH = COUT / 2;                                   // output channels held by one CTA of the pair
+  static constexpr int KSTEPS = CGIN / 2;                               // UMMA_K = 16 bf16 = 2 channel groups
+  static constexpr uint32_t ROW_BYTES = CGIN * HALO_PX * 16;            // one staged activation row
+  static constexpr uint32_t SLOT_BYTES = (ROW_BYTES + 127) / 128 * 128;  // ring-slot stride (TMA destinations are 128-byte aligned)
+  static constexpr uint32_t W_TAP_BYTES = CGIN * NH * 16;               // one tap of this CTA's filter half
+  static constexpr uint32_t W_BYTES = 9 * W_TAP_BYTES;
+  static constexpr uint32_t A_LBO = HALO_PX * 16, B_LBO = NH * 16;      // byte distance of the two K halves of one MMA
+  static constexpr int ACC_STRIDE = COUT <= 32 ? 32 : 128;              // TMEM columns per accumulator stage
+  static constexpr int NACC = 3;                                        // accumulator stages
+  static constexpr int TMEM_COLS = COUT <= 32 ? 128 : 512;              // power of two >= NACC * ACC_STRIDE
+  static constexpr int EPI_COLS = COUT / 2 >= 16 ? COUT / 2 : COUT;     // channels per epilogue warp (two warps per lane quadrant)
+  static constexpr int EPI_SPLIT = COUT / EPI_COLS;                     // 2, or 1 when the layer is too narrow to split
+  static constexpr size_t SMEM = 1024 + (W_BYTES + 127) / 128 * 128 + (size_t)NSLOT * SLOT_BYTES + 256;
+  static_assert(CGIN % 2 == 0 && COUT % 16 == 0 && COUT <= 128, "shape");
+  static_assert(W_TAP_BYTES % 16 == 0, "alignment");
+};
+
+struct Params {
+  const __nv_bfloat16* wpack;      // [2 halves][9 taps][CGIN][NH][8]
+  float bias[96];                  // per output channel (kernel-parameter constant bank: free operands in the epilogue)
+  __nv_bfloat16* out;              // [N][COUT/8][H][W+2][8]
+  const __nv_bfloat16* mask;       // optional, same layout as out: result is zeroed where mask <= 0 (ReLU backward)
+  int N, H, W;
+  int relu;
+  int n_tiles, x_tiles, row_blocks;   // CTA work units: (image, 128-pixel column tile, 16-row block)
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n"
+      "D_%=:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (same offset in its shared memory)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* b) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(s2u(b) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(dst)), "l"(src),
+               "r"(bytes), "r"(s2u(bar)) : "memory");
+}
+// one staged activation row of this CTA: tensor dims {130 x 8 B = 65 px, 2 halves, start pixel, row, plane = image * CG + cg},
+// box {130, 2, 1, 1, CGIN} at (0, 0, xs, y, plane0); completion bytes are counted on the LEADER's barrier (cta_group::2 form),
+// which the single MMA-issuing thread of the pair waits on
+__device__ __forceinline__ void tma_row(void* dst, const CUtensorMap* map, uint64_t* bar, int xs, int y, int plane0) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar) & PEER_MASK), "r"(0), "r"(0), "r"(xs), "r"(y),
+      "r"(plane0)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, int cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(dst_smem)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_free(uint32_t addr, int cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], M = 256 over the CTA pair, K = 16 bf16
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+      "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive on barrier `b` of BOTH CTAs once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit_both(uint64_t* b) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s2u(b)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: rows (pixels / output channels) 16 B apart, 8-row groups `sbo` bytes
+// apart, the two 8-element K halves `lbo` bytes apart (cute/arch/mma_sm100_desc.hpp: bits [0,14) addr >> 4, [16,30) LBO >> 4,
+// [32,46) SBO >> 4, [46,48) version = 1, [61,64) layout = 0)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor of kind::f16: fp32 accumulate, bf16 x bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Unit { int n, x0, y0; };
+// CTA `rank` of cluster-level work item `u` takes CTA tile 2u + rank; tiles beyond the end are dummies (n = N: every load is out
+// of bounds = zeros, nothing is stored), which keeps the two CTAs of a pair in lockstep
+__device__ __forceinline__ Unit unit_of(const Params& P, int u, int rank) {
+  Unit t;
+  const int tile = 2 * u + rank;
+  const int xt = tile % P.x_tiles;
+  const int rb = (tile / P.x_tiles) % P.row_blocks;
+  t.n = tile / (P.x_tiles * P.row_blocks);
+  t.x0 = xt * TILE_PX;
+  t.y0 = rb * ROW_BLOCK;
+  return t;
+}
+
+template <int CGIN, int COUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+    k_conv3x3_tc(const __grid_constant__ CUtensorMap in_map, Params P) {
+  using C = Cfg<CGIN, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm_w = base;                                       // this CTA's filter half: [9][CGIN][NH][8] bf16
+  uint8_t* sm_a = base + (C::W_BYTES + 127) / 128 * 128;      // ring: [NSLOT][CGIN][130][8] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_a + (size_t)NSLOT * C::SLOT_BYTES);
+  uint64_t* full = bars;                                      // [NSLOT]  (leader's copy is the live one)
+  uint64_t* empty = bars + NSLOT;                             // [NSLOT]  per CTA
+  uint64_t* tfull = bars + 2 * NSLOT;                         // [NACC]   per CTA
+  uint64_t* tempty = bars + 2 * NSLOT + C::NACC;              // [NACC]   leader's copy
+  uint64_t* wbar = bars + 2 * NSLOT + 2 * C::NACC;            // filter bank landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * C::NACC + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int n_units = (P.n_tiles + 1) / 2;
+  constexpr int EPI_WARPS_USED = 4 * C::EPI_SPLIT;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < C::NACC; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 2 * EPI_WARPS_USED); }
+    mbar_init(wbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == 0 && lane == 0) {                               // resident filter half of this CTA
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+    mbar_expect_tx(wbar, C::W_BYTES);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(P.wpack) + (size_t)rank * C::W_BYTES;
+    for (int t = 0; t < 9; ++t) bulk_g2s(sm_w + t * C::W_TAP_BYTES, src + (size_t)t * C::W_TAP_BYTES, C::W_TAP_BYTES, wbar);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  mbar_wait(wbar, 0);
+  tc_fence_before();
+  cluster_sync_all();                                         // barriers initialised, both filter halves resident, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: one activation row per step into the next ring slot ===========================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const Unit t = unit_of(P, u, rank);
+        for (int r = 0; r < ROW_BLOCK + 2; ++r, ++it) {
+          const uint32_t s = it % NSLOT, ph = (it / NSLOT) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          if (leader) mbar_expect_tx(full + s, 2 * C::ROW_BYTES);
+          // padded index of image pixel x0 - 1 is x0
+          tma_row(sm_a + (size_t)s * C::SLOT_BYTES, &in_map, full + s, t.x0, t.y0 - 1 + r, t.n * CGIN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA, one thread): 9 taps x KSTEPS k-steps per output row ====================================
+    if (leader && lane == 0) {
+      constexpr uint32_t IDESC = instr_desc(2 * TILE_PX, COUT);
+      const uint32_t a0 = s2u(sm_a), w0 = s2u(sm_w);
+      uint32_t it_base = 0, acc_it = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        int waited = 0;
+        for (int j = 0; j < ROW_BLOCK; ++j, ++acc_it) {
+          const uint32_t a = acc_it % C::NACC, aph = (acc_it / C::NACC) & 1;
+          mbar_wait(tempty + a, aph ^ 1);
+          while (waited < j + 3) {
+            const uint32_t i = it_base + waited;
+            mbar_wait(full + (i % NSLOT), (i / NSLOT) & 1);
+            ++waited;
+          }
+          tc_fence_after();
+          const uint32_t d = tmem_base + a * C::ACC_STRIDE;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t slot = (it_base + j + dy) % NSLOT;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint32_t arow = a0 + slot * C::SLOT_BYTES + dx * 16;
+              const uint32_t wtap = w0 + (dy * 3 + dx) * C::W_TAP_BYTES;
+#pragma unroll
+              for (int k = 0; k < C::KSTEPS; ++k) {
+                umma_2sm(d, smem_desc(arow + 2 * k * C::A_LBO, C::A_LBO, 128), smem_desc(wtap + 2 * k * C::B_LBO, C::B_LBO, 128), IDESC, acc);
+                acc = 1;
+              }
+            }
+          }
+          umma_commit_both(tfull + a);                                         // accumulator ready -> both epilogues
+          umma_commit_both(empty + (it_base + j) % NSLOT);                     // input row j is dead
+          if (j == ROW_BLOCK - 1) {
+            umma_commit_both(empty + (it_base + ROW_BLOCK) % NSLOT);
+            umma_commit_both(empty + (it_base + ROW_BLOCK + 1) % NSLOT);
+          }
+        }
+        it_base += ROW_BLOCK + 2;
+      }
+    }
+  } else if (warp - 2 < EPI_WARPS_USED) {
+    // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> bf16 -> global (channel-group-major, padded rows) ==========
+    const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
+    const int part = (warp - 2) >> 2;                          // which half of the output channels
+    const int m = quad * 32 + lane;                            // pixel of the tile
+    const int cbase = part * C::EPI_COLS;
+    const int Wp = P.W + 2;
+    uint32_t acc_it = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      const Unit t = unit_of(P, u, rank);
+      const int x = t.x0 + m;
+      for (int j = 0; j < ROW_BLOCK; ++j, ++acc_it) {
+        const uint32_t a = acc_it % C::NACC, aph = (acc_it / C::NACC) & 1;
+        const int y = t.y0 + j;
+        mbar_wait(tfull + a, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + a * C::ACC_STRIDE + cbase + ((uint32_t)(quad * 32) << 16);
+        uint32_t v[C::EPI_COLS];
+#pragma unroll
+        for (int c0 = 0; c0 < C::EPI_COLS; c0 += 16) tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty + a);         // accumulator `a` is in registers: the MMA thread may reuse it
+        if (t.n < P.N && x < P.W && y < P.H) {
+#pragma unroll
+          for (int g = 0; g < C::EPI_COLS / 8; ++g) {          // channel groups of 8
+            const int cg = cbase / 8 + g;
+            const size_t o = ((((size_t)t.n * (COUT / 8) + cg) * P.H + y) * Wp + x + 1) * 8;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = __uint_as_float(v[g * 8 + e]) + P.bias[cbase + g * 8 + e];
+              if (P.relu) f[e] = fmaxf(f[e], 0.f);
+            }
+            if (P.mask) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(P.mask + o);
+              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (!(__bfloat162float(mb[e]) > 0.f)) f[e] = 0.f;
+            }
+            uint4 pk;
+            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pb[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            *reinterpret_cast<uint4*>(P.out + o) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown: nobody may free TMEM (or exit: the peer's MMAs read our shared memory) before both CTAs are done ----------
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_free(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace convtc
+}  // namespace dpx

@@ -1,56 +1,90 @@
-// dpx_ffdnet.cu — native FFDNet-color forward (the denoiser behind deep_prior):
+// dpx_ffdnet.cu — native FFDNet-color (the denoiser behind deep_prior): forward and data gradient.
 //   PixelUnshuffle(2) + sigma map -> conv3x3(13->96)+ReLU -> 10 x [conv3x3(96->96)+ReLU] -> conv3x3(96->12) -> PixelShuffle(2)
 //   (proxfn/pnp/denoisers/models/network_ffdnet.py:44-68)
-// Activations live in HBM as NHWC bf16 (channels padded to 16 / 96), the twelve convolutions run as implicit GEMMs on
-// tcgen05 tensor cores with fp32 accumulation in TMEM (conv/dpx_conv_umma.cuh); the unshuffle/sigma prologue and the
-// shuffle/crop epilogue are fused layout kernels.  bf16 operands => ~1e-2 relative accuracy: this is the opt-in FAST
-// denoiser; the fp32 parity path keeps the framework convolution (dprox_b200/denoisers.py).
+// Activations live in HBM as channel-group-major bf16 [N][C/8][h][w][8]; the twelve convolutions run on tcgen05 tensor
+// cores through the hand-written kernel of dpx_conv_tc.cuh (CTA pairs, TMEM accumulators, TMA-staged activation rows reused
+// for all nine taps, filter bank resident in shared memory).  The data gradient (unrolled training with a frozen denoiser,
+// BASELINE config 5) reuses the SAME kernel: d/d(input) of a 3x3 convolution is a 3x3 convolution with the transposed,
+// spatially flipped filter, and the ReLU mask of the saved forward activation is applied in its epilogue.
+// bf16 operands, fp32 accumulation => ~1e-2 relative accuracy: this is the FAST denoiser; the fp32 parity path keeps the
+// framework convolution (dprox_b200/denoisers.py).
 #include <cuda_bf16.h>
 
 #include <new>
 
 #include "dpx_common.cuh"
-#ifndef DPX_NO_UMMA_CONV
-#include "conv/dpx_conv_api.h"
-#endif
+#include "dpx_conv_tc.cuh"
 
 using namespace dpx;
 
-struct dpx_ffdnet {
-  int nb = 0, nc = 0;
-  __nv_bfloat16* w[32] = {nullptr};      // KRSC, channels padded
-  float* bias[32] = {nullptr};
-  bool set[32] = {false};
-  __nv_bfloat16 *act0 = nullptr, *act1 = nullptr, *io16 = nullptr, *out16 = nullptr;
-  void* ws = nullptr;
-  size_t ws_bytes = 0, act_cap = 0, io_cap = 0;
-};
-
 namespace {
 
-constexpr int CIN_PAD = 16, COUT_TAIL_PAD = 16;
+constexpr int MAXL = 32;
 
-// [Cout,Cin,3,3] fp32 -> [Cout_pad,3,3,Cin_pad] bf16 (zero padded)
-__global__ void k_pack_filter(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int cout_pad,
-                              int cin_pad) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map of a padded channel-group-major activation tensor [N][CG][H][W+2][8] bf16.  One staged row of one channel group
+// is 130 px x 16 B = 2080 contiguous bytes starting at ANY pixel; a box dimension is limited to 256 elements, so the run is
+// described as {130 x 8-byte elements (65 px), 2 halves 1040 B apart} and the start pixel gets its own unit-stride (16 B)
+// dimension -- the dimensions deliberately overlap in memory.  dims {130, 2, W+2, H, N*CG}, box {130, 2, 1, 1, CG}.
+int make_row_map(CUtensorMap* map, const __nv_bfloat16* ptr, int N, int CG, int H, int W) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DPX_ERR_CUDA; }
+  const cuuint64_t Wp = (cuuint64_t)W + 2;
+  const cuuint64_t dims[5] = {(cuuint64_t)convtc::HALO_PX, 2, Wp, (cuuint64_t)H, (cuuint64_t)N * CG};
+  const cuuint64_t strides[4] = {(cuuint64_t)convtc::HALO_PX * 8, 16, Wp * 16, (cuuint64_t)H * Wp * 16};
+  const cuuint32_t box[5] = {(cuuint32_t)convtc::HALO_PX, 2, 1, 1, (cuuint32_t)CG};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (N=%d CG=%d H=%d W=%d)", (int)r, N, CG, H, W); return DPX_ERR_CUDA; }
+  return DPX_OK;
+}
+
+// elements of a padded activation buffer: rows of W + 2 pixels, plus slack for the last tile's overhang (a 130-pixel run that
+// starts inside the last row may end up to 129 pixels past it)
+inline size_t padded_elems(int N, int C, int H, int W) { return ((size_t)N * (C / 8) * H * (W + 2) + 256) * 8; }
+
+// nn.Conv2d weight [Cout,Cin,3,3] fp32 -> the shared-memory image of the kernel: [half][tap][cg][n][8] bf16, zero padded.
+// transpose = 1 builds the data-gradient filter  Wd[ci][co][ky][kx] = W[co][ci][2-ky][2-kx]  (roles of cin / cout swapped).
+__global__ void k_pack_filter_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int cgin_pad,
+                                 int cout_pad, int transpose) {
+  const int nh = cout_pad / 2;
+  const int total = 2 * 9 * cgin_pad * nh * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = cout_pad * 9 * cin_pad;
   if (i >= total) return;
-  const int c = i % cin_pad, rs = (i / cin_pad) % 9, k = i / (cin_pad * 9);
-  const float v = (k < cout && c < cin) ? w[((size_t)k * cin + c) * 9 + rs] : 0.f;
+  const int c8 = i % 8, n = (i / 8) % nh, cg = (i / (8 * nh)) % cgin_pad, tap = (i / (8 * nh * cgin_pad)) % 9, half = i / (8 * nh * cgin_pad * 9);
+  const int ko = half * nh + n, ki = cg * 8 + c8;            // output / input channel of the (possibly transposed) filter
+  const int ky = tap / 3, kx = tap % 3;
+  float v = 0.f;
+  if (!transpose) {
+    if (ko < cout && ki < cin) v = w[(((size_t)ko * cin + ki) * 3 + ky) * 3 + kx];
+  } else {
+    // filter of the data gradient: its outputs are the ORIGINAL inputs (cin of them), its inputs the original outputs
+    if (ko < cin && ki < cout) v = w[(((size_t)ki * cin + ko) * 3 + (2 - ky)) * 3 + (2 - kx)];
+  }
   out[i] = __float2bfloat16(v);
 }
 
-__global__ void k_pad_bias(const float* __restrict__ b, float* __restrict__ out, int cout, int cout_pad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cout_pad) out[i] = i < cout ? b[i] : 0.f;
-}
-
-// x [B,3,H,W] fp32 -> NHWC bf16 [B,h2,w2,16]: channel c*4+dy*2+dx = x[b,c,2h+dy,2w+dx] (replicate-padded to even sizes),
+// x [B,3,H,W] fp32 -> [B][2][h2][w2][8] bf16: channel c*4+dy*2+dx = x[b,c,2h+dy,2w+dx] (replicate-padded to even sizes),
 // channel 12 = sigma_b, channels 13..15 = 0                                         network_ffdnet.py:54-64
 __global__ void k_unshuffle_in(const float* __restrict__ x, const float* __restrict__ sigma, int sigma_per_sample,
                                __nv_bfloat16* __restrict__ out, int B, int H, int W, int h2, int w2) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per output pixel
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per quarter-resolution pixel
   const size_t total = (size_t)B * h2 * w2;
   if (i >= total) return;
   const int w = (int)(i % w2), h = (int)((i / w2) % h2), b = (int)(i / ((size_t)w2 * h2));
@@ -66,20 +100,23 @@ __global__ void k_unshuffle_in(const float* __restrict__ x, const float* __restr
       }
   v[12] = __float2bfloat16(sigma[sigma_per_sample ? b : 0]);
   v[13] = v[14] = v[15] = __float2bfloat16(0.f);
-  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
-  dst[0] = reinterpret_cast<const uint4*>(v)[0];
-  dst[1] = reinterpret_cast<const uint4*>(v)[1];
+  const size_t plane = (size_t)h2 * (w2 + 2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(v)[0];
+  *reinterpret_cast<uint4*>(out + o + plane * 8) = reinterpret_cast<const uint4*>(v)[1];
 }
 
-// NHWC bf16 [B,h2,w2,16] -> y [B,3,H,W] fp32 (PixelShuffle(2) + crop)              network_ffdnet.py:65-68
+// [B][2][h2][w2+2][8] bf16 -> y [B,3,H,W] fp32 (PixelShuffle(2) + crop)              network_ffdnet.py:65-68
 __global__ void k_shuffle_out(const __nv_bfloat16* __restrict__ in, float* __restrict__ y, int B, int H, int W, int h2, int w2) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * h2 * w2;
   if (i >= total) return;
   const int w = (int)(i % w2), h = (int)((i / w2) % h2), b = (int)(i / ((size_t)w2 * h2));
+  const size_t plane = (size_t)h2 * (w2 + 2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
   __align__(16) __nv_bfloat16 v[16];
-  reinterpret_cast<uint4*>(v)[0] = reinterpret_cast<const uint4*>(in + i * 16)[0];
-  reinterpret_cast<uint4*>(v)[1] = reinterpret_cast<const uint4*>(in + i * 16)[1];
+  reinterpret_cast<uint4*>(v)[0] = *reinterpret_cast<const uint4*>(in + o);
+  reinterpret_cast<uint4*>(v)[1] = *reinterpret_cast<const uint4*>(in + o + plane * 8);
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -91,38 +128,224 @@ __global__ void k_shuffle_out(const __nv_bfloat16* __restrict__ in, float* __res
       }
 }
 
+// adjoint of k_shuffle_out: g_y [B,3,H,W] fp32 -> [B][2][h2][w2][8] bf16 (cropped positions and the 4 padding channels get 0)
+__global__ void k_shuffle_out_bwd(const float* __restrict__ gy, __nv_bfloat16* __restrict__ out, int B, int H, int W, int h2, int w2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * h2 * w2;
+  if (i >= total) return;
+  const int w = (int)(i % w2), h = (int)((i / w2) % h2), b = (int)(i / ((size_t)w2 * h2));
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * h + dy, xx = 2 * w + dx;
+        v[c * 4 + dy * 2 + dx] = __float2bfloat16((yy < H && xx < W) ? gy[(((size_t)b * 3 + c) * H + yy) * W + xx] : 0.f);
+      }
+  v[12] = v[13] = v[14] = v[15] = __float2bfloat16(0.f);
+  const size_t plane = (size_t)h2 * (w2 + 2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(v)[0];
+  *reinterpret_cast<uint4*>(out + o + plane * 8) = reinterpret_cast<const uint4*>(v)[1];
+}
+
+// adjoint of k_unshuffle_in: g16 [B][2][h2][w2][8] bf16 -> g_x [B,3,H,W] fp32 (a replicate-padded border pixel collects the
+// gradients of its copies) and g_sigma[b] += sum of channel 12 (warp-shuffle + atomics)
+__global__ void k_unshuffle_in_bwd(const __nv_bfloat16* __restrict__ g16, float* __restrict__ gx, float* __restrict__ gsigma,
+                                   int sigma_per_sample, int B, int H, int W, int h2, int w2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * h2 * w2;
+  float gs = 0.f;
+  int b = 0;
+  if (i < total) {
+    const int w = (int)(i % w2), h = (int)((i / w2) % h2);
+    b = (int)(i / ((size_t)w2 * h2));
+    const size_t plane = (size_t)h2 * (w2 + 2);
+    const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+    __align__(16) __nv_bfloat16 v[16];
+    reinterpret_cast<uint4*>(v)[0] = *reinterpret_cast<const uint4*>(g16 + o);
+    reinterpret_cast<uint4*>(v)[1] = *reinterpret_cast<const uint4*>(g16 + o + plane * 8);
+    gs = __bfloat162float(v[12]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g[2][2];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) g[dy][dx] = __bfloat162float(v[c * 4 + dy * 2 + dx]);
+      // clamp-duplicated positions (odd H / W, last quarter-resolution row / column) fold onto the border pixel
+      const bool fold_y = 2 * h + 1 >= H, fold_x = 2 * w + 1 >= W;
+      if (fold_y) { g[0][0] += g[1][0]; g[0][1] += g[1][1]; }
+      if (fold_x) { g[0][0] += g[0][1]; if (!fold_y) g[1][0] += g[1][1]; }
+      float* dst = gx + (((size_t)b * 3 + c) * H + 2 * h) * W + 2 * w;
+      dst[0] = g[0][0];
+      if (!fold_x) dst[1] = g[0][1];
+      if (!fold_y) { dst[W] = g[1][0]; if (!fold_x) dst[W + 1] = g[1][1]; }
+    }
+  }
+  if (gsigma) {
+    // blocks never straddle... they may: reduce per warp only where the whole warp shares b, else fall back to per-thread atomics
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool uniform = __all_sync(0xffffffffu, b == b0 || i >= total);
+    if (uniform) {
+      const float s = warp_sum(i < total ? gs : 0.f);
+      if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(gsigma + (sigma_per_sample ? b0 : 0), s);
+    } else if (i < total) {
+      atomicAdd(gsigma + (sigma_per_sample ? b : 0), gs);
+    }
+  }
+}
+
+// fp32 NCHW <-> channel-group-major bf16 (per-layer debug entry)
+__global__ void k_nchw_to_c8(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cc, int CG, int H, int W) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * CG * H * W * 8;
+  if (i >= total) return;
+  const int c8 = (int)(i % 8);
+  size_t r = i / 8;
+  const int w = (int)(r % W); r /= W;
+  const int h = (int)(r % H); r /= H;
+  const int cg = (int)(r % CG);
+  const int b = (int)(r / CG);
+  const int c = cg * 8 + c8;
+  out[((((size_t)b * CG + cg) * H + h) * (W + 2) + w + 1) * 8 + c8] = __float2bfloat16(c < Cc ? x[(((size_t)b * Cc + c) * H + h) * W + w] : 0.f);
+}
+__global__ void k_c8_to_nchw(const __nv_bfloat16* __restrict__ in, float* __restrict__ y, int B, int Cc, int CG, int H, int W) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * Cc * H * W;
+  if (i >= total) return;
+  const int w = (int)(i % W);
+  size_t r = i / W;
+  const int h = (int)(r % H); r /= H;
+  const int c = (int)(r % Cc);
+  const int b = (int)(r / Cc);
+  y[i] = __bfloat162float(in[((((size_t)b * CG + c / 8) * H + h) * (W + 2) + w + 1) * 8 + c % 8]);
+}
+
+template <int CGIN, int COUT>
+int launch_conv(const __nv_bfloat16* in, const __nv_bfloat16* wpack, const float* bias, __nv_bfloat16* out, const __nv_bfloat16* mask,
+                int relu, int N, int H, int W, cudaStream_t s) {
+  using C = convtc::Cfg<CGIN, COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPX_CUDA(cudaFuncSetAttribute(convtc::k_conv3x3_tc<CGIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap map;
+  int rc = make_row_map(&map, in, N, CGIN, H, W);
+  if (rc) return rc;
+  convtc::Params P;
+  P.wpack = wpack; P.out = out; P.mask = mask; P.N = N; P.H = H; P.W = W; P.relu = relu;
+  for (int i = 0; i < 96; ++i) P.bias[i] = (bias && i < COUT) ? bias[i] : 0.f;
+  P.x_tiles = (W + convtc::TILE_PX - 1) / convtc::TILE_PX;
+  P.row_blocks = (H + convtc::ROW_BLOCK - 1) / convtc::ROW_BLOCK;
+  P.n_tiles = N * P.x_tiles * P.row_blocks;
+  int dev = 0, sms = 0;
+  DPX_CUDA(cudaGetDevice(&dev));
+  DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int units = (P.n_tiles + 1) / 2;
+  const int clusters = units < sms / 2 ? units : sms / 2;
+  convtc::k_conv3x3_tc<CGIN, COUT><<<2 * clusters, convtc::NTHREADS, C::SMEM, s>>>(map, P);
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
+}  // namespace
+
+struct dpx_ffdnet {
+  int nb = 0, nc = 0;
+  __nv_bfloat16* w[MAXL] = {nullptr};       // forward filter, kernel image
+  __nv_bfloat16* wd[MAXL] = {nullptr};      // data-gradient filter (transposed + flipped), kernel image
+  float bias[MAXL][96] = {{0.f}};           // host copies: passed to the kernels as parameter constants
+  bool set[MAXL] = {false};
+  __nv_bfloat16 *io16 = nullptr, *out16 = nullptr;
+  __nv_bfloat16* act[MAXL] = {nullptr};     // act[l] = output of layer l (l < nb - 1); two ping-pong buffers unless training
+  __nv_bfloat16 *ga = nullptr, *gb = nullptr;
+  size_t act_cap = 0;                       // elements per 96-channel buffer
+  int n_act = 0;
+  int buf_B = 0, buf_h2 = 0, buf_w2 = 0;    // shape the zero borders of the buffers were laid out for
+  int saved_B = 0, saved_h2 = 0, saved_w2 = 0;
+  bool saved = false;
+};
+
+namespace {
+
+// (re)allocates the activation buffers for a [B, ., h2, w2] problem; every buffer is zero-filled whenever the shape changes,
+// because the kernels rely on (and never write) the zero columns left and right of every row
+int ensure_buffers(dpx_ffdnet* n, int B, int h2, int w2, bool train, cudaStream_t s) {
+  const int want = train ? n->nb - 1 : 2;
+  const size_t e96 = padded_elems(B, 96, h2, w2), e16 = padded_elems(B, 16, h2, w2);
+  const bool shape_changed = n->buf_B != B || n->buf_h2 != h2 || n->buf_w2 != w2;
+  if (n->act_cap < e96 || n->n_act < want) {
+    for (int i = 0; i < MAXL; ++i) { cudaFree(n->act[i]); n->act[i] = nullptr; }
+    cudaFree(n->io16); cudaFree(n->out16); cudaFree(n->ga); cudaFree(n->gb);
+    n->io16 = n->out16 = n->ga = n->gb = nullptr;
+    const size_t cap = e96 > n->act_cap ? e96 : n->act_cap;
+    for (int i = 0; i < want; ++i) DPX_CUDA(cudaMalloc(&n->act[i], sizeof(__nv_bfloat16) * cap));
+    DPX_CUDA(cudaMalloc(&n->io16, sizeof(__nv_bfloat16) * (cap / 6 + 4096)));
+    DPX_CUDA(cudaMalloc(&n->out16, sizeof(__nv_bfloat16) * (cap / 6 + 4096)));
+    n->act_cap = cap;
+    n->n_act = want;
+  } else if (!shape_changed) {
+    return DPX_OK;
+  }
+  for (int i = 0; i < n->n_act; ++i) DPX_CUDA(cudaMemsetAsync(n->act[i], 0, sizeof(__nv_bfloat16) * e96, s));
+  DPX_CUDA(cudaMemsetAsync(n->io16, 0, sizeof(__nv_bfloat16) * e16, s));
+  DPX_CUDA(cudaMemsetAsync(n->out16, 0, sizeof(__nv_bfloat16) * e16, s));
+  if (n->ga) {
+    DPX_CUDA(cudaMemsetAsync(n->ga, 0, sizeof(__nv_bfloat16) * e96, s));
+    DPX_CUDA(cudaMemsetAsync(n->gb, 0, sizeof(__nv_bfloat16) * e96, s));
+  }
+  n->buf_B = B; n->buf_h2 = h2; n->buf_w2 = w2;
+  n->saved = false;
+  return DPX_OK;
+}
+
+int run_forward(dpx_ffdnet* n, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H, int W, bool train,
+                cudaStream_t s) {
+  for (int i = 0; i < n->nb; ++i) DPX_REQUIRE(n->set[i], "layer %d has no weights", i);
+  const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+  const size_t pix = (size_t)B * h2 * w2;
+  int rc = ensure_buffers(n, B, h2, w2, train, s);
+  if (rc) return rc;
+  k_unshuffle_in<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(x, sigma, sigma_per_sample, n->io16, B, H, W, h2, w2);
+  DPX_LAUNCH_CHECK();
+  // act[l] receives the output of layer l; without saving, two buffers alternate
+  auto buf = [&](int l) { return train ? n->act[l] : n->act[l & 1]; };
+  rc = launch_conv<2, 96>(n->io16, n->w[0], n->bias[0], buf(0), nullptr, 1, B, h2, w2, s);
+  for (int l = 1; l < n->nb - 1 && !rc; ++l) rc = launch_conv<12, 96>(buf(l - 1), n->w[l], n->bias[l], buf(l), nullptr, 1, B, h2, w2, s);
+  if (!rc) rc = launch_conv<12, 16>(buf(n->nb - 2), n->w[n->nb - 1], n->bias[n->nb - 1], n->out16, nullptr, 0, B, h2, w2, s);
+  if (rc) return rc;
+  k_shuffle_out<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(n->out16, y, B, H, W, h2, w2);
+  DPX_LAUNCH_CHECK();
+  n->saved = train;
+  n->saved_B = B; n->saved_h2 = h2; n->saved_w2 = w2;
+  return DPX_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int dpx_ffdnet_available(void) {
-#ifdef DPX_NO_UMMA_CONV
-  return 0;
-#else
-  return 1;
-#endif
-}
+int dpx_ffdnet_available(void) { return 1; }
 
 int dpx_ffdnet_create(int nb, int nc, dpx_ffdnet** out) {
   DPX_REQUIRE(out, "null argument");
   *out = nullptr;
-#ifdef DPX_NO_UMMA_CONV
-  set_error("library built without the tcgen05 convolution (CUTLASS headers not found at build time)");
-  return DPX_ERR_STATE;
-#else
-  DPX_REQUIRE(nc == 96 && nb >= 3 && nb <= 32, "native FFDNet supports nc=96 (FFDNet-color), 3 <= nb <= 32");
+  DPX_REQUIRE(nc == 96 && nb >= 3 && nb <= MAXL, "native FFDNet supports nc=96 (FFDNet-color), 3 <= nb <= 32");
   dpx_ffdnet* n = new (std::nothrow) dpx_ffdnet();
   if (!n) { set_error("out of host memory"); return DPX_ERR_NOMEM; }
   n->nb = nb; n->nc = nc;
   *out = n;
   return DPX_OK;
-#endif
 }
 
 void dpx_ffdnet_destroy(dpx_ffdnet* n) {
   if (!n) return;
-  for (int i = 0; i < 32; ++i) { cudaFree(n->w[i]); cudaFree(n->bias[i]); }
-  cudaFree(n->act0); cudaFree(n->act1); cudaFree(n->io16); cudaFree(n->out16); cudaFree(n->ws);
+  for (int i = 0; i < MAXL; ++i) { cudaFree(n->w[i]); cudaFree(n->wd[i]); cudaFree(n->act[i]); }
+  cudaFree(n->io16); cudaFree(n->out16); cudaFree(n->ga); cudaFree(n->gb);
   delete n;
 }
 
@@ -131,16 +354,20 @@ int dpx_ffdnet_set_layer(dpx_ffdnet* n, int layer, const float* w, const float* 
   DPX_REQUIRE(n && w && bias, "null argument");
   DPX_REQUIRE(layer >= 0 && layer < n->nb, "layer %d out of range", layer);
   const bool head = layer == 0, tail = layer == n->nb - 1;
-  const int cin_pad = head ? CIN_PAD : n->nc, cout_pad = tail ? COUT_TAIL_PAD : n->nc;
+  const int cin_pad = head ? 16 : n->nc, cout_pad = tail ? 16 : n->nc;
   DPX_REQUIRE(cin <= cin_pad && cout <= cout_pad, "layer %d: shape [%d,%d,3,3] does not fit [%d,%d]", layer, cout, cin, cout_pad, cin_pad);
   cudaStream_t s = (cudaStream_t)stream;
-  const int total = cout_pad * 9 * cin_pad;
+  const int total = 9 * cin_pad * cout_pad;                    // both halves together
   if (!n->w[layer]) DPX_CUDA(cudaMalloc(&n->w[layer], sizeof(__nv_bfloat16) * total));
-  if (!n->bias[layer]) DPX_CUDA(cudaMalloc(&n->bias[layer], sizeof(float) * cout_pad));
-  k_pack_filter<<<(total + 255) / 256, 256, 0, s>>>(w, n->w[layer], cout, cin, cout_pad, cin_pad);
+  if (!n->wd[layer]) DPX_CUDA(cudaMalloc(&n->wd[layer], sizeof(__nv_bfloat16) * total));
+  k_pack_filter_tc<<<(total + 255) / 256, 256, 0, s>>>(w, n->w[layer], cout, cin, cin_pad / 8, cout_pad, 0);
   DPX_LAUNCH_CHECK();
-  k_pad_bias<<<1, 128, 0, s>>>(bias, n->bias[layer], cout, cout_pad);
+  // data-gradient filter: inputs = this layer's outputs (cout_pad channels), outputs = this layer's inputs (cin_pad channels)
+  k_pack_filter_tc<<<(total + 255) / 256, 256, 0, s>>>(w, n->wd[layer], cout, cin, cout_pad / 8, cin_pad, 1);
   DPX_LAUNCH_CHECK();
+  for (int i = 0; i < 96; ++i) n->bias[layer][i] = 0.f;
+  DPX_CUDA(cudaMemcpyAsync(n->bias[layer], bias, sizeof(float) * cout, cudaMemcpyDeviceToHost, s));      // cold path: once per weight load
+  DPX_CUDA(cudaStreamSynchronize(s));
   n->set[layer] = true;
   return DPX_OK;
 }
@@ -148,49 +375,81 @@ int dpx_ffdnet_set_layer(dpx_ffdnet* n, int layer, const float* w, const float* 
 // y = FFDNet(x, sigma): x, y [B,3,H,W] fp32 device; sigma device [B] (sigma_per_sample) or [1]
 int dpx_ffdnet_forward(dpx_ffdnet* n, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H, int W,
                        void* stream) {
-#ifdef DPX_NO_UMMA_CONV
-  set_error("library built without the tcgen05 convolution");
-  return DPX_ERR_STATE;
-#else
   DPX_REQUIRE(n && x && sigma && y, "null argument");
-  for (int i = 0; i < n->nb; ++i) DPX_REQUIRE(n->set[i], "layer %d has no weights", i);
-  cudaStream_t s = (cudaStream_t)stream;
+  return run_forward(n, x, sigma, sigma_per_sample, y, B, H, W, false, (cudaStream_t)stream);
+}
+
+int dpx_ffdnet_forward_train(dpx_ffdnet* n, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H, int W,
+                             void* stream) {
+  DPX_REQUIRE(n && x && sigma && y, "null argument");
+  return run_forward(n, x, sigma, sigma_per_sample, y, B, H, W, true, (cudaStream_t)stream);
+}
+
+int dpx_ffdnet_backward(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, int B, int H, int W,
+                        void* stream) {
+  DPX_REQUIRE(n && g_y && g_x, "null argument");
   const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+  DPX_REQUIRE(n->saved && n->saved_B == B && n->saved_h2 == h2 && n->saved_w2 == w2,
+              "dpx_ffdnet_backward needs the activations of a matching dpx_ffdnet_forward_train call");
+  cudaStream_t s = (cudaStream_t)stream;
   const size_t pix = (size_t)B * h2 * w2;
-  if (n->act_cap < pix) {
-    cudaFree(n->act0); cudaFree(n->act1); cudaFree(n->io16); cudaFree(n->out16);
-    n->act0 = n->act1 = n->io16 = n->out16 = nullptr;
-    DPX_CUDA(cudaMalloc(&n->act0, sizeof(__nv_bfloat16) * pix * n->nc));
-    DPX_CUDA(cudaMalloc(&n->act1, sizeof(__nv_bfloat16) * pix * n->nc));
-    DPX_CUDA(cudaMalloc(&n->io16, sizeof(__nv_bfloat16) * pix * 16));
-    DPX_CUDA(cudaMalloc(&n->out16, sizeof(__nv_bfloat16) * pix * 16));
-    n->act_cap = pix;
+  if (!n->ga) {
+    DPX_CUDA(cudaMalloc(&n->ga, sizeof(__nv_bfloat16) * n->act_cap));
+    DPX_CUDA(cudaMalloc(&n->gb, sizeof(__nv_bfloat16) * n->act_cap));
+    DPX_CUDA(cudaMemsetAsync(n->ga, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
+    DPX_CUDA(cudaMemsetAsync(n->gb, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
   }
-  const size_t need = conv::conv_workspace(B, h2, w2);
-  if (n->ws_bytes < need) {
-    cudaFree(n->ws); n->ws = nullptr;
-    DPX_CUDA(cudaMalloc(&n->ws, need));
-    n->ws_bytes = need;
-  }
-  k_unshuffle_in<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(x, sigma, sigma_per_sample, n->io16, B, H, W, h2, w2);
+  // g wrt the tail's output (16 channels, 12 real)
+  k_shuffle_out_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(g_y, n->out16, B, H, W, h2, w2);
   DPX_LAUNCH_CHECK();
-  int rc = conv::conv_head(n->io16, n->w[0], n->bias[0], n->act0, B, h2, w2, n->ws, n->ws_bytes, s);
-  if (rc) { set_error("tcgen05 conv (head) failed with status %d", rc); return DPX_ERR_CUDA; }
-  ++g_launches;
-  __nv_bfloat16 *cur = n->act0, *nxt = n->act1;
-  for (int l = 1; l < n->nb - 1; ++l) {
-    rc = conv::conv_body(cur, n->w[l], n->bias[l], nxt, B, h2, w2, n->ws, n->ws_bytes, s);
-    if (rc) { set_error("tcgen05 conv (body %d) failed with status %d", l, rc); return DPX_ERR_CUDA; }
-    ++g_launches;
+  // tail: g wrt its input a_{nb-2}, masked by the ReLU of the layer that produced it -> g wrt that layer's pre-activation
+  __nv_bfloat16 *cur = n->ga, *nxt = n->gb;
+  int rc = launch_conv<2, 96>(n->out16, n->wd[n->nb - 1], nullptr, cur, n->act[n->nb - 2], 0, B, h2, w2, s);
+  for (int l = n->nb - 2; l >= 1 && !rc; --l) {
+    rc = launch_conv<12, 96>(cur, n->wd[l], nullptr, nxt, n->act[l - 1], 0, B, h2, w2, s);
     __nv_bfloat16* t = cur; cur = nxt; nxt = t;
   }
-  rc = conv::conv_tail(cur, n->w[n->nb - 1], n->bias[n->nb - 1], n->out16, B, h2, w2, n->ws, n->ws_bytes, s);
-  if (rc) { set_error("tcgen05 conv (tail) failed with status %d", rc); return DPX_ERR_CUDA; }
-  ++g_launches;
-  k_shuffle_out<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(n->out16, y, B, H, W, h2, w2);
+  if (!rc) rc = launch_conv<12, 16>(cur, n->wd[0], nullptr, n->io16, nullptr, 0, B, h2, w2, s);     // g wrt the 16-channel input
+  if (rc) return rc;
+  if (g_sigma) DPX_CUDA(cudaMemsetAsync(g_sigma, 0, sizeof(float) * (sigma_per_sample ? B : 1), s));
+  k_unshuffle_in_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(n->io16, g_x, g_sigma, sigma_per_sample, B, H, W, h2, w2);
   DPX_LAUNCH_CHECK();
+  n->saved = false;                                             // io16 was reused: the saved input is gone
   return DPX_OK;
-#endif
+}
+
+// one convolution layer on fp32 NCHW tensors (debug / per-layer parity tests): direction 0 = forward (bias, optional ReLU),
+// 1 = data gradient (no bias).  x [B,cin,H,W] -> y [B,cout,H,W] with (cin, cout) the layer's logical channel counts in that
+// direction.
+int dpx_ffdnet_conv_layer(dpx_ffdnet* n, int layer, int direction, int relu, const float* x, float* y, int B, int H, int W, void* stream) {
+  DPX_REQUIRE(n && x && y, "null argument");
+  DPX_REQUIRE(layer >= 0 && layer < n->nb && n->set[layer], "layer %d out of range or without weights", layer);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool head = layer == 0, tail = layer == n->nb - 1;
+  int cin = head ? 13 : 96, cout = tail ? 12 : 96;
+  int cin_pad = head ? 16 : 96, cout_pad = tail ? 16 : 96;
+  if (direction) { int t = cin; cin = cout; cout = t; t = cin_pad; cin_pad = cout_pad; cout_pad = t; }
+  const size_t pix = (size_t)B * H * W;
+  __nv_bfloat16 *a = nullptr, *o = nullptr;
+  DPX_CUDA(cudaMalloc(&a, sizeof(__nv_bfloat16) * padded_elems(B, cin_pad, H, W)));
+  DPX_CUDA(cudaMalloc(&o, sizeof(__nv_bfloat16) * padded_elems(B, cout_pad, H, W)));
+  DPX_CUDA(cudaMemsetAsync(a, 0, sizeof(__nv_bfloat16) * padded_elems(B, cin_pad, H, W), s));
+  DPX_CUDA(cudaMemsetAsync(o, 0, sizeof(__nv_bfloat16) * padded_elems(B, cout_pad, H, W), s));
+  k_nchw_to_c8<<<(unsigned)((pix * cin_pad + 255) / 256), 256, 0, s>>>(x, a, B, cin, cin_pad / 8, H, W);
+  DPX_LAUNCH_CHECK();
+  const __nv_bfloat16* wp = direction ? n->wd[layer] : n->w[layer];
+  const float* bp = direction ? nullptr : n->bias[layer];
+  int rc;
+  if (cin_pad == 16) rc = launch_conv<2, 96>(a, wp, bp, o, nullptr, relu, B, H, W, s);
+  else if (cout_pad == 16) rc = launch_conv<12, 16>(a, wp, bp, o, nullptr, relu, B, H, W, s);
+  else rc = launch_conv<12, 96>(a, wp, bp, o, nullptr, relu, B, H, W, s);
+  if (!rc) {
+    k_c8_to_nchw<<<(unsigned)((pix * cout + 255) / 256), 256, 0, s>>>(o, y, B, cout, cout_pad / 8, H, W);
+    ++g_launches;
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(a); cudaFree(o);
+  return rc;
 }
 
 }  // extern "C"

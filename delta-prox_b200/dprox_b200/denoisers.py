@@ -4,8 +4,9 @@
 (pnp/denoisers/models/network_ffdnet.py:27-68: PixelUnshuffle(2) -> conv3x3(13->96)+ReLU ->
 10 x [conv3x3(96->96)+ReLU] -> conv3x3(96->12) -> PixelShuffle(2)), so the published
 `ffdnet_color.pth` loads unchanged.  It is launched as an *external* prox between two native
-stages on the same CUDA stream; its 3x3 convolutions currently run through the library conv
-(cuDNN) — a hand-written tcgen05 implicit-GEMM path is the §8f follow-up.
+stages on the same CUDA stream.  `precision="bf16"` runs the hand-written tcgen05 kernels of
+csrc/dpx_conv_tc.cuh (forward and data gradient); `precision="fp32"` keeps fp32 library
+convolutions for 1e-5-class parity with the reference.
 """
 from __future__ import annotations
 
@@ -38,18 +39,18 @@ class FFDNet(nn.Module):
 
 
 class NativeFFDNet:
-    """FFDNet-color forward on tcgen05 tensor cores through the C-ABI (`dpx_ffdnet_*`, csrc/dpx_ffdnet.cu): NHWC bf16
-    activations, implicit-GEMM 3x3 convolutions with fp32 TMEM accumulation, fused bias+ReLU, fused
-    unshuffle/sigma prologue and shuffle/crop epilogue.  bf16 operands: ~1e-2 relative to the fp32 network."""
+    """FFDNet-color on tcgen05 tensor cores through the C-ABI (`dpx_ffdnet_*`, csrc/dpx_conv_tc.cuh): channel-group-major
+    bf16 activations, hand-written implicit-GEMM 3x3 convolutions (CTA pairs, TMEM accumulators, TMA-staged rows reused for all
+    nine taps, resident filter bank), fused bias+ReLU, fused unshuffle/sigma prologue and shuffle/crop epilogue; the data
+    gradient runs on the same kernel.  bf16 operands: ~1e-2 relative to the fp32 network."""
 
     def __init__(self, model: "FFDNet", device):
         import ctypes as C
         from . import _cabi as cabi
         self._cabi, self.device = cabi, torch.device(device)
         lib = cabi.lib()
-        if not lib.dpx_ffdnet_available():
-            raise RuntimeError("libdprox_b200 was built without the tcgen05 convolution (CUTLASS headers missing)")
         convs = [m for m in model.model if isinstance(m, nn.Conv2d)]
+        self.n_layers = len(convs)
         self._h = C.c_void_p()
         cabi.check(lib.dpx_ffdnet_create(len(convs), convs[1].out_channels, C.byref(self._h)), "dpx_ffdnet_create")
         with torch.cuda.device(self.device):
@@ -60,7 +61,7 @@ class NativeFFDNet:
                                                     cabi.stream_ptr(self.device)), "dpx_ffdnet_set_layer")
             torch.cuda.current_stream(self.device).synchronize()
 
-    def __call__(self, x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    def _args(self, x, sigma):
         cabi = self._cabi
         x = cabi.require_cuda_f32(x, "x")
         B, Cc, H, W = x.shape
@@ -69,11 +70,49 @@ class NativeFFDNet:
         sigma = cabi.require_cuda_f32(sigma.to(x.device, torch.float32).reshape(-1), "sigma")
         if sigma.numel() not in (1, B):
             raise ValueError(f"sigma must have 1 or {B} entries")
+        return x, sigma, B, H, W
+
+    def __call__(self, x: torch.Tensor, sigma: torch.Tensor, train: bool = False) -> torch.Tensor:
+        cabi = self._cabi
+        x, sigma, B, H, W = self._args(x, sigma)
         y = torch.empty_like(x)
+        fn = cabi.lib().dpx_ffdnet_forward_train if train else cabi.lib().dpx_ffdnet_forward
         with torch.cuda.device(x.device):
-            cabi.check(cabi.lib().dpx_ffdnet_forward(self._h, cabi.ptr(x), cabi.ptr(sigma), int(sigma.numel() > 1), cabi.ptr(y),
-                                                     B, H, W, cabi.stream_ptr(x.device)), "dpx_ffdnet_forward")
+            cabi.check(fn(self._h, cabi.ptr(x), cabi.ptr(sigma), int(sigma.numel() > 1), cabi.ptr(y), B, H, W,
+                          cabi.stream_ptr(x.device)), "dpx_ffdnet_forward")
         return y
+
+    def backward(self, g_y: torch.Tensor, n_sigma: int):
+        """(dL/dx, dL/dsigma) of the last `train=True` call."""
+        cabi = self._cabi
+        g_y = cabi.require_cuda_f32(g_y, "g_y")
+        B, _, H, W = g_y.shape
+        g_x = torch.empty_like(g_y)
+        g_s = torch.empty(n_sigma, device=g_y.device, dtype=torch.float32)
+        with torch.cuda.device(g_y.device):
+            cabi.check(cabi.lib().dpx_ffdnet_backward(self._h, cabi.ptr(g_y), cabi.ptr(g_x), cabi.ptr(g_s), int(n_sigma > 1), B, H, W,
+                                                      cabi.stream_ptr(g_y.device)), "dpx_ffdnet_backward")
+        return g_x, g_s
+
+    def conv_layer(self, layer: int, x: torch.Tensor, direction: int = 0, relu: bool = False) -> torch.Tensor:
+        """one convolution of the network on fp32 NCHW tensors (per-layer parity tests)"""
+        cabi = self._cabi
+        x = cabi.require_cuda_f32(x, "x")
+        B, Cc, H, W = x.shape
+        head, tail = layer == 0, layer == self.n_layers - 1
+        cin, cout = (13 if head else 96), (12 if tail else 96)
+        if direction:
+            cin, cout = cout, cin
+        if Cc != cin:
+            raise ValueError(f"layer {layer} expects {cin} channels in this direction, got {Cc}")
+        y = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            cabi.check(cabi.lib().dpx_ffdnet_conv_layer(self._h, layer, int(direction), int(relu), cabi.ptr(x), cabi.ptr(y), B, H, W,
+                                                        cabi.stream_ptr(x.device)), "dpx_ffdnet_conv_layer")
+        return y
+
+    def __deepcopy__(self, memo):
+        raise TypeError("NativeFFDNet owns device filter banks; copy the owning denoiser instead (it rebuilds them lazily)")
 
     def __del__(self):
         try:
@@ -81,6 +120,32 @@ class NativeFFDNet:
                 self._cabi.lib().dpx_ffdnet_destroy(self._h)
         except Exception:
             pass
+
+
+class _NativeFFDNetFn(torch.autograd.Function):
+    """y = FFDNet(x, sigma) with frozen weights: forward and data gradient on the tensor-core kernels."""
+
+    @staticmethod
+    def forward(ctx, x, sigma, net):
+        ctx.net, ctx.sigma_shape = net, sigma.shape
+        ctx.n_sigma = int(sigma.numel())
+        net._graph_id = getattr(net, "_graph_id", 0) + 1
+        ctx.graph_id = net._graph_id
+        ctx.save_for_backward(x.detach(), sigma.detach())
+        return net(x.detach(), sigma.detach(), train=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        if ctx.graph_id != net._graph_id:
+            # another forward ran in between (an unrolled solver calls the denoiser once per iteration and backpropagates
+            # in reverse order): the saved activations were overwritten -> recompute this call's forward
+            x, sigma = ctx.saved_tensors
+            net(x, sigma, train=True)
+            net._graph_id = ctx.graph_id
+        g_x, g_s = net.backward(g.contiguous(), ctx.n_sigma)
+        net._graph_id = -1                                        # the saved state is consumed
+        return g_x, g_s.reshape(ctx.sigma_shape), None
 
 
 class FFDNetColorDenoiser(Denoiser):
@@ -98,6 +163,14 @@ class FFDNetColorDenoiser(Denoiser):
         elif seed is not None:
             self.load_seeded(seed)
 
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_native" else copy.deepcopy(v, memo)      # filter banks are rebuilt lazily
+        return new
+
     def load_seeded(self, seed: int):
         """Deterministic random weights (nn.Conv2d's default init bounds) — what the parity tests use, because the
         pretrained file needs a download (pnp/prior.py:14-35)."""
@@ -113,9 +186,15 @@ class FFDNetColorDenoiser(Denoiser):
     def _denoise(self, x, sigma):
         wants_grad = torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad
                                                    or any(p.requires_grad for p in self.model.parameters()))
+        if self.precision == "bf16" and wants_grad and not any(p.requires_grad for p in self.model.parameters()):
+            # unrolled training with a frozen denoiser (BASELINE config 5, e2e_optics_dprox.py:34): forward and data gradient
+            # both run on the native tensor-core kernels (activation recomputation when several calls are in flight)
+            if self._native is None or self._native.device != x.device:
+                self._native = NativeFFDNet(self.model, x.device)
+            return _NativeFFDNetFn.apply(x.contiguous(), sigma, self._native)
         if self.precision == "bf16" and wants_grad:
-            # training (unrolled solver, BASELINE config 5): the tcgen05 forward has no backward yet, so the tape runs
-            # through the framework's convolutions with bf16 operands / fp32 accumulation
+            # trainable denoiser weights: the weight gradient has no native kernel, so the tape runs through the framework's
+            # convolutions with bf16 operands / fp32 accumulation
             if not getattr(self, "_nhwc", False):          # NHWC weights: cuDNN's tensor-core kernels for forward, dgrad and wgrad
                 self.model.to(memory_format=torch.channels_last)
                 self._nhwc = True
@@ -191,6 +270,14 @@ class DRUNetDenoiser(Denoiser):
         self.model = UNetRes(in_nc=n_channels + 1, out_nc=n_channels)
         if model_path is not None:
             self.model.load_state_dict(torch.load(model_path, map_location="cpu"), strict=True)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_native" else copy.deepcopy(v, memo)      # filter banks are rebuilt lazily
+        return new
 
     def load_seeded(self, seed: int):
         """Deterministic random weights in state_dict order (U(-b, b), b = 1/sqrt(fan_in)) for the parity tests."""

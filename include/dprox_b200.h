@@ -257,9 +257,11 @@ int dpx_cg_gate(const float* val, const float* tol, int tol_n, int strict, float
 
 /* ---- native deep-denoiser (FFDNet-color) on tcgen05 tensor cores ---------------------------------------------
  * deep_prior -> FFDNetColorDenoiser -> FFDNet.forward (proxfn/pnp/prior.py:73-86, denoisers/wrapper.py:38-48,
- * models/network_ffdnet.py:44-68).  bf16 operands, fp32 accumulation: the opt-in fast denoiser (~1e-2 relative). */
+ * models/network_ffdnet.py:44-68).  Hand-written sm_100a kernel (csrc/dpx_conv_tc.cuh): tcgen05.mma cta_group::2, TMEM
+ * accumulators, TMA-staged activation rows reused for all nine taps, filter bank resident in shared memory.
+ * bf16 operands, fp32 accumulation: the fast denoiser (~1e-2 relative to the fp32 network). */
 typedef struct dpx_ffdnet dpx_ffdnet;
-int dpx_ffdnet_available(void);                       /* 0 when built without the CUTLASS header tree */
+int dpx_ffdnet_available(void);                       /* 1: the tensor-core path is always built */
 int dpx_ffdnet_create(int nb, int nc, dpx_ffdnet** out);          /* nb conv layers, nc = 96 channels */
 void dpx_ffdnet_destroy(dpx_ffdnet* net);
 /* layer 0 = head [nc,13,3,3], 1..nb-2 = body [nc,nc,3,3], nb-1 = tail [12,nc,3,3]; w/bias: device fp32, nn.Conv2d layout */
@@ -267,6 +269,19 @@ int dpx_ffdnet_set_layer(dpx_ffdnet* net, int layer, const float* w, const float
 /* y = FFDNet(x, sigma); x, y device fp32 [B,3,H,W]; sigma device [B] (sigma_per_sample=1) or [1] */
 int dpx_ffdnet_forward(dpx_ffdnet* net, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H,
                        int W, void* stream);
+/* Same, keeping every layer's activation for dpx_ffdnet_backward (unrolled training with a frozen denoiser: what the
+ * reference obtains by autograd through FFDNet.forward, e2e_optics_dprox.py:34-58). */
+int dpx_ffdnet_forward_train(dpx_ffdnet* net, const float* x, const float* sigma, int sigma_per_sample, float* y, int B, int H,
+                             int W, void* stream);
+/* Data gradient of the last dpx_ffdnet_forward_train call: g_x [B,3,H,W] = dL/dx and g_sigma ([B] or [1], may be NULL) =
+ * dL/dsigma given g_y = dL/dy.  Every layer's input gradient is again a 3x3 convolution (transposed, flipped filter) on the
+ * same tensor-core kernel, with the ReLU mask of the saved activation applied in its epilogue.  Consumes the saved state. */
+int dpx_ffdnet_backward(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, int B, int H,
+                        int W, void* stream);
+/* One convolution layer on fp32 NCHW tensors (per-layer parity tests): direction 0 = forward (+bias, optional ReLU),
+ * 1 = data gradient.  x [B,cin,H,W] -> y [B,cout,H,W], (cin, cout) = the layer's channel counts in that direction. */
+int dpx_ffdnet_conv_layer(dpx_ffdnet* net, int layer, int direction, int relu, const float* x, float* y, int B, int H, int W,
+                          void* stream);
 
 /* ---- CS-MRI closed-form data term on complex iterates (proxfn/fast/csmri.py:14-25; the ext_sum_squares hook,
  * proxfn/sum_square.py:44-48).  v, y, out: complex64 [B,C,H,W] (interleaved re,im); mask: fp32 0/1 [mask_batch,C,H,W],
