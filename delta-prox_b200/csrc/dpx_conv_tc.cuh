@@ -92,9 +92,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "bra W_%=;\n"
       "D_%=:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
 }
-// arrive on the LEADER CTA's copy of a barrier (same offset in its shared memory)
+// arrive on the LEADER CTA's copy of a barrier (same offset in its shared memory).  RELAXED: the only thing the arrival publishes
+// is "this warp's tcgen05.ld of the accumulator has completed", which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already
+// order; a release at cluster scope would also wait for the warp's outstanding global stores (MEMBAR.ALL.GPU: it was 55 % of all
+// stall samples of the first version)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* b) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(s2u(b) & PEER_MASK) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(s2u(b) & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(dst)), "l"(src),
@@ -231,10 +234,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA, one thread): 9 taps x KSTEPS k-steps per output row ====================================
-    if (leader && lane == 0) {
+    // ===== MMA issuer (leader CTA): 9 taps x KSTEPS k-steps per output row.  The WHOLE warp runs the loop so that addresses and
+    // descriptors stay in uniform registers; only the tcgen05 instructions themselves are predicated on one elected lane (a
+    // single-lane branch made every operand a per-thread value and cost a ~20-instruction uniform-broadcast loop per MMA:
+    // 91 cycles per MMA instead of the tensor pipe's 48) =====
+    if (leader) {
       constexpr uint32_t IDESC = instr_desc(2 * TILE_PX, COUT);
-      const uint32_t a0 = s2u(sm_a), w0 = s2u(sm_w);
+      const uint32_t a0 = s2u(sm_a);
+      const uint64_t bd0 = smem_desc(s2u(sm_w), C::B_LBO, 128);
       uint32_t it_base = 0, acc_it = 0;
       for (int u = cluster_id; u < n_units; u += n_clusters) {
         int waited = 0;
@@ -248,27 +255,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           }
           tc_fence_after();
           const uint32_t d = tmem_base + a * C::ACC_STRIDE;
-          uint32_t acc = 0;
+          // descriptors differ from a per-slot / per-bank base only in the 14-bit start-address field (bytes >> 4; shared
+          // memory addresses stay below 2^18, so the field never carries): one add per operand and MMA
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const uint32_t slot = (it_base + j + dy) % NSLOT;
+            const uint64_t ad0 = smem_desc(a0 + slot * C::SLOT_BYTES, C::A_LBO, 128);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t arow = a0 + slot * C::SLOT_BYTES + dx * 16;
-              const uint32_t wtap = w0 + (dy * 3 + dx) * C::W_TAP_BYTES;
 #pragma unroll
               for (int k = 0; k < C::KSTEPS; ++k) {
-                umma_2sm(d, smem_desc(arow + 2 * k * C::A_LBO, C::A_LBO, 128), smem_desc(wtap + 2 * k * C::B_LBO, C::B_LBO, 128), IDESC, acc);
-                acc = 1;
+                const uint64_t ad = ad0 + (uint64_t)((dx * 16 + 2 * k * C::A_LBO) >> 4);
+                const uint64_t bd = bd0 + (uint64_t)(((dy * 3 + dx) * C::W_TAP_BYTES + 2 * k * C::B_LBO) >> 4);
+                if (elect_one()) umma_2sm(d, ad, bd, IDESC, (dy | dx | k) != 0);
               }
             }
           }
-          umma_commit_both(tfull + a);                                         // accumulator ready -> both epilogues
-          umma_commit_both(empty + (it_base + j) % NSLOT);                     // input row j is dead
-          if (j == ROW_BLOCK - 1) {
-            umma_commit_both(empty + (it_base + ROW_BLOCK) % NSLOT);
-            umma_commit_both(empty + (it_base + ROW_BLOCK + 1) % NSLOT);
+          __syncwarp();
+          if (elect_one()) {
+            umma_commit_both(tfull + a);                                         // accumulator ready -> both epilogues
+            umma_commit_both(empty + (it_base + j) % NSLOT);                     // input row j is dead
+            if (j == ROW_BLOCK - 1) {
+              umma_commit_both(empty + (it_base + ROW_BLOCK) % NSLOT);
+              umma_commit_both(empty + (it_base + ROW_BLOCK + 1) % NSLOT);
+            }
           }
+          __syncwarp();
         }
         it_base += ROW_BLOCK + 2;
       }
