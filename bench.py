@@ -426,8 +426,24 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")
     ap.add_argument("--e2e-wave", type=int, default=0, help="max sub-batches iterating concurrently (0 = all)")
     ap.add_argument("--e2e-priority", type=int, default=0, help="1: earlier sub-batches on higher-priority streams (measured: no gain)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs: headline = configs[1]-shape batch (default); cfg1 = single 256x256 ADMM x 50; cfg2 = PnP "
+                         "deconv with the deep denoiser; cfg3 = CS-MRI + TV with PCG; cfg4 = HQS 8 x 1024^2 per GPU; cfg5 = unrolled training step")
     args = ap.parse_args()
-    if args.impl == "reference":
+    given = set(a.split("=")[0] for a in sys.argv[1:] if a.startswith("--"))
+    args.batch_set, args.iters_set, args.size_set = "--batch" in given, "--iters" in given, "--size" in given
+    if args.workload == "cfg1":                            # BASELINE configs[0]: single [3,256,256] image, ADMM x 50
+        args.batch = args.batch if args.batch_set else 1
+        args.size = args.size if args.size_set else 256
+    elif args.workload == "cfg4":                          # BASELINE configs[3]: 64 x [3,1024,1024] over 8 GPUs, HQS x 24
+        args.method = "hqs"
+        args.batch = args.batch if args.batch_set else 8
+        args.size = args.size if args.size_set else 1024
+        args.iters = args.iters if args.iters_set else 24
+    if args.workload in ("cfg2", "cfg3", "cfg5"):
+        import bench_workloads
+        bench_workloads.run(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

@@ -48,6 +48,7 @@ class NativeFFDNet:
         import ctypes as C
         from . import _cabi as cabi
         self._cabi, self.device = cabi, torch.device(device)
+        self.profile = None            # set to a list to collect (kind, start event, end event, pixels) per call (bench.py)
         lib = cabi.lib()
         convs = [m for m in model.model if isinstance(m, nn.Conv2d)]
         self.n_layers = len(convs)
@@ -77,10 +78,21 @@ class NativeFFDNet:
         x, sigma, B, H, W = self._args(x, sigma)
         y = torch.empty_like(x)
         fn = cabi.lib().dpx_ffdnet_forward_train if train else cabi.lib().dpx_ffdnet_forward
+        ev = self._mark()
         with torch.cuda.device(x.device):
             cabi.check(fn(self._h, cabi.ptr(x), cabi.ptr(sigma), int(sigma.numel() > 1), cabi.ptr(y), B, H, W,
                           cabi.stream_ptr(x.device)), "dpx_ffdnet_forward")
+        self._mark(ev, "fwd", B * H * W)
         return y
+
+    def _mark(self, start=None, kind=None, pixels=0):
+        if self.profile is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if start is not None:
+            self.profile.append((kind, start, e, pixels))
+        return e
 
     def backward(self, g_y: torch.Tensor, n_sigma: int):
         """(dL/dx, dL/dsigma) of the last `train=True` call."""
@@ -89,9 +101,11 @@ class NativeFFDNet:
         B, _, H, W = g_y.shape
         g_x = torch.empty_like(g_y)
         g_s = torch.empty(n_sigma, device=g_y.device, dtype=torch.float32)
+        ev = self._mark()
         with torch.cuda.device(g_y.device):
             cabi.check(cabi.lib().dpx_ffdnet_backward(self._h, cabi.ptr(g_y), cabi.ptr(g_x), cabi.ptr(g_s), int(n_sigma > 1), B, H, W,
                                                       cabi.stream_ptr(g_y.device)), "dpx_ffdnet_backward")
+        self._mark(ev, "bwd", B * H * W)
         return g_x, g_s
 
     def conv_layer(self, layer: int, x: torch.Tensor, direction: int = 0, relu: bool = False) -> torch.Tensor:
@@ -124,13 +138,14 @@ class NativeFFDNet:
 
 class _NativeFFDNetFn(torch.autograd.Function):
     """y = FFDNet(x, sigma) with frozen weights: forward and data gradient on the tensor-core kernels."""
+    _calls = 0
 
     @staticmethod
     def forward(ctx, x, sigma, net):
         ctx.net, ctx.sigma_shape = net, sigma.shape
         ctx.n_sigma = int(sigma.numel())
-        net._graph_id = getattr(net, "_graph_id", 0) + 1
-        ctx.graph_id = net._graph_id
+        _NativeFFDNetFn._calls += 1                                # process-wide, never reused
+        ctx.graph_id = net._graph_id = _NativeFFDNetFn._calls
         ctx.save_for_backward(x.detach(), sigma.detach())
         return net(x.detach(), sigma.detach(), train=True)
 

@@ -465,21 +465,55 @@ def test_iso_tv_group_shrink(dp, method):
     assert dp.CompGraph(dp.grad2d(x)).sanity_check(shape=(1, 3, 32, 48))
 
 
-# ---- native FFDNet-color on tcgen05 tensor cores (bf16 fast mode) -----------------------------------------------
+# ---- native FFDNet-color on tcgen05 tensor cores (hand-written kernel, csrc/dpx_conv_tc.cuh; bf16 fast mode) --------------
+
+def test_tcgen05_conv_layers_match_torch_conv2d(dp):
+    """every layer shape of the network (13->96, 96->96, 96->12), forward (+bias, ReLU) and data gradient, against torch's
+    conv2d / conv_transpose2d in fp32 on the SAME bf16-rounded operands: the only differences left are the fp32 summation
+    order and the bf16 rounding of the stored result (2^-9 relative: tolerance 4e-3 in relative L2, 1 bf16 ulp per element)."""
+    import torch.nn.functional as F
+    from dprox_b200.denoisers import FFDNetColorDenoiser, NativeFFDNet
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        den = FFDNetColorDenoiser(seed=4).cuda()
+        net = NativeFFDNet(den.model, torch.device("cuda"))
+        convs = [m for m in den.model.model if isinstance(m, torch.nn.Conv2d)]
+        bf = lambda t: t.to(torch.bfloat16).float()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for (B, H, W) in ((1, 5, 7), (2, 37, 300), (1, 40, 129)):       # single tile, odd sizes, a 1-pixel second column tile
+            for layer in (0, 1, 11):
+                c = convs[layer]
+                x = torch.randn(B, c.in_channels, H, W, device="cuda", generator=g)
+                ref = F.conv2d(bf(x), bf(c.weight), c.bias, padding=1)
+                ref = ref.relu() if layer != 11 else ref
+                y = net.conv_layer(layer, x, 0, relu=(layer != 11))
+                assert rel(y, ref) < 4e-3, (layer, B, H, W, rel(y, ref))
+                assert float(((y - ref).abs() / ref.abs().clamp_min(1e-2)).max()) < 1.2e-2
+                gy = torch.randn(B, c.out_channels, H, W, device="cuda", generator=g)
+                gx = net.conv_layer(layer, gy, 1)
+                assert rel(gx, F.conv_transpose2d(bf(gy), bf(c.weight), padding=1)) < 4e-3, (layer, "dgrad")
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
 
 def test_native_ffdnet_tcgen05_matches_fp32_network(dp):
     from dprox_b200.denoisers import FFDNetColorDenoiser
     g = torch.Generator().manual_seed(8)
     ref = FFDNetColorDenoiser(seed=4).cuda()
-    fast = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
-    for shape in ((2, 3, 64, 96), (1, 3, 45, 70)):                       # even sizes and odd sizes (replicate pad + crop)
+    fast = FFDNetColorDenoiser(seed=4, precision="bf16").cuda().requires_grad_(False)
+    for shape in ((2, 3, 64, 96), (1, 3, 45, 70), (1, 3, 300, 520)):     # even sizes, odd sizes (replicate pad + crop), 2 x 3 tiles
         x = torch.rand(*shape, generator=g).cuda()
         sig = (0.02 + 0.1 * torch.rand(shape[0], generator=g)).cuda()
         y_ref = ref.denoise(x, sig)
         y = fast.denoise(x, sig)
         assert y.shape == x.shape and torch.isfinite(y).all()
         r = rel(y, y_ref)
-        assert r < 2e-2, (shape, r)                                      # bf16 operands, fp32 accumulation
+        assert r < 1e-2, (shape, r)                                      # bf16 operands, fp32 accumulation: measured 3e-3
+    # against the UNMODIFIED reference's output (golden) at the stated bf16 tolerance
+    gold = load("ffdnet_forward")
+    y = fast.denoise(T(gold["x"]), T(gold["sigma"]))
+    assert rel(y, gold["y"]) < 1e-2, rel(y, gold["y"])
     # inside the ADMM loop as an external prox
     gold = load("admm_deep_prior_wellcond")
     xv = dp.Variable()
@@ -488,6 +522,42 @@ def test_native_ffdnet_tcgen05_matches_fp32_network(dp):
     _, st = run(dp, dp.sum_squares(dp.conv(xv, gold["psf"]) - b) + prior + nn_, "admm", b, int(gold["T"]), rhos=float(gold["rho"]),
                 lams={prior: T(gold["sigmas"], "cpu"), nn_: 0.02})
     assert rel(st[0], gold["s0"]) < 3e-2
+
+
+def test_native_ffdnet_data_gradient(dp):
+    """frozen denoiser under autograd (unrolled training, BASELINE cfg5): forward AND backward on the tensor-core kernels.
+    A bf16 ReLU network's input gradient is noisy by nature (units whose pre-activation flips sign under rounding switch their
+    whole path on or off): torch's own bf16 autocast backward is 0.10 away from the fp32 gradient on this network, so the native
+    backward is required to be no worse than that, and the smooth quantities (d/d sigma, the loss) to agree to 2e-2."""
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ref = FFDNetColorDenoiser(seed=4).cuda()
+    fast = FFDNetColorDenoiser(seed=4, precision="bf16").cuda().requires_grad_(False)
+    for shape in ((2, 3, 64, 96), (1, 3, 45, 71)):
+        x = torch.rand(*shape, device="cuda", generator=g)
+        sig = 0.02 + 0.1 * torch.rand(shape[0], device="cuda", generator=g)
+        w = torch.rand(*shape, device="cuda", generator=g)
+        xa, sa = x.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+        la = (fast.denoise(xa, sa) * w).sum()
+        la.backward()
+        xr, sr = x.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+        lr = (ref.denoise(xr, sr) * w).sum()
+        lr.backward()
+        xt = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yt = ref.model(xt, sig)
+        (yt.float() * w).sum().backward()
+        ours, torch16 = rel(xa.grad, xr.grad), rel(xt.grad, xr.grad)
+        assert ours < 1.15 * torch16 + 1e-2 and ours < 0.2, (shape, ours, torch16)
+        assert rel(sa.grad, sr.grad) < 2e-2 and abs(float(la) - float(lr)) < 1e-2 * abs(float(lr))
+    # two calls in flight (an unrolled solver calls the denoiser once per iteration): the earlier one is recomputed in backward
+    x1 = torch.rand(1, 3, 32, 48, device="cuda", generator=g).requires_grad_(True)
+    s1 = torch.tensor([0.05], device="cuda")
+    y2 = fast.denoise(fast.denoise(x1, s1), s1)
+    y2.sum().backward()
+    xr = x1.detach().clone().requires_grad_(True)
+    ref.denoise(ref.denoise(xr, s1), s1).sum().backward()
+    assert rel(x1.grad, xr.grad) < 0.3 and torch.isfinite(x1.grad).all()
 
 
 # ---- more fused-engine coverage: single-term fast paths (persistent row kernel), HQS, largest size, per-iteration calls ----
