@@ -363,6 +363,31 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(ems_t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * T * e_steps / (float(ems_t) * 1e-3)
+    e2e_ms_per_step = float(ems_t) / e_steps
+
+    # ---- the path's only collective: the opt-in residual stop rule, all-reduced over the ranks -------------
+    # per-sample sums reduced on the device, NCCL all-reduce + host copy on a side stream, decision consumed one check later
+    stop_leg = None
+    if args.stop_leg:
+        sc0, yc0 = chunks[0][0], chunks[0][1]
+        bd0 = b_host[:Bc].to(dev)
+        yc0.value = bd0
+        stop = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=10)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        sc0.solve(x0=bd0, rhos=1.0, lams=0.02, max_iter=200, stop=stop)
+        s1.record()
+        barrier()
+        its = torch.tensor([sc0.iterations_run], device=dev)
+        gathered = [torch.zeros_like(its) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(gathered, its)
+        else:
+            gathered = [its]
+        stop_leg = {"iterations_run": int(its), "same_on_every_rank": len({int(t) for t in gathered}) == 1, "checks": len(stop.history),
+                    "every": 10, "ms": s0.elapsed_time(s1), "ranks": world,
+                    "how": "dpx_resid_reduce on the device, all-reduce of 5 doubles over NCCL on a side stream, decision consumed one check late"}
 
     if rank != 0:
         if world > 1:
@@ -401,8 +426,10 @@ def run_native(args):
         "config": workload_config(args, world),
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4),
-                "steps": e_steps, "pipeline": f"{n_chunks} sub-batches of {Bc} problems on {n_chunks} CUDA streams "
-                                               f"(H2D / iterations / D2H overlapped, consecutive steps pipelined)"},
+                "steps": e_steps, "ms_per_step": e2e_ms_per_step,
+                "pipeline": f"{n_chunks} sub-batches of {Bc} problems on {n_chunks} CUDA streams "
+                            f"(H2D / iterations / D2H overlapped, consecutive steps pipelined)"},
+        "stop_leg": stop_leg,
         "gpu_launches": int(launches), "clocks": clk.summary(),
     }))
     if world > 1:
@@ -426,6 +453,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches (streams) of the end-to-end pipeline")
     ap.add_argument("--e2e-wave", type=int, default=0, help="max sub-batches iterating concurrently (0 = all)")
     ap.add_argument("--e2e-priority", type=int, default=0, help="1: earlier sub-batches on higher-priority streams (measured: no gain)")
+    ap.add_argument("--stop-leg", type=int, default=1, help="0: skip the residual-stop leg (the path's only collective, untimed extra)")
     ap.add_argument("--workload", default="headline", choices=["headline", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json configs: headline = configs[1]-shape batch (default); cfg1 = single 256x256 ADMM x 50; cfg2 = PnP "
                          "deconv with the deep denoiser; cfg3 = CS-MRI + TV with PCG; cfg4 = HQS 8 x 1024^2 per GPU; cfg5 = unrolled training step")
