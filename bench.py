@@ -372,7 +372,7 @@ def run_native(args):
         sc0, yc0 = chunks[0][0], chunks[0][1]
         bd0 = b_host[:Bc].to(dev)
         yc0.value = bd0
-        stop = dp.ResidualStop(abstol=1e-3, reltol=1e-2, every=10)
+        stop = dp.ResidualStop(abstol=1e-4, reltol=1e-3, every=10)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
