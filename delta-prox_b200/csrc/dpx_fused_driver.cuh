@@ -43,6 +43,10 @@ inline bool size_supported(int n) {
 template <class F>
 inline bool dispatch_size(int n, F&& f) {
   switch (n) {
+#ifdef DPX_EXP_SIZES                                   // experiment builds: only the headline size (compile time)
+    case 2048: f(std::integral_constant<int, 2048>{}); return true;
+    default: return false;
+#else
     case 64: f(std::integral_constant<int, 64>{}); return true;
     case 128: f(std::integral_constant<int, 128>{}); return true;
     case 256: f(std::integral_constant<int, 256>{}); return true;
@@ -60,6 +64,7 @@ inline bool dispatch_size(int n, F&& f) {
     case 1280: f(std::integral_constant<int, 1280>{}); return true;
     case 2560: f(std::integral_constant<int, 2560>{}); return true;
     default: return false;
+#endif
   }
 }
 

@@ -4,6 +4,7 @@
 // Generic transforms (constant hoisting, stand-alone spectral filters, algorithms the fused kernels do not
 // cover) are delegated to an embedded cuFFT engine, so this engine is a strict superset of it.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -62,11 +63,17 @@ struct CudaBackend {
     k_col_tma<TH><<<grid, ColTmaCfg<TH>::NT, smem, s>>>(p, n_tiles, nb);
     after();
   }
+  static constexpr int kRowCtrs = 4096;                 // dynamic-tile counters: one per persistent row launch of a call (zeroed per call)
+  int* row_ctr = nullptr;
+  int row_ctr_next = 0, row_dyn = 1;
+  unsigned long long *trace_col = nullptr, *trace_row = nullptr;
   template <class TH>
   void col(dim3 grid, size_t smem, const ColParams& p) {
     if (rc) return;
+    ColParams q = p;
+    q.trace = trace_col;
     prep(k_col<TH>, smem);
-    k_col<TH><<<grid, kThreads, smem, s>>>(p);
+    k_col<TH><<<grid, kThreads, smem, s>>>(q);
     after();
   }
   template <class TW, int MODE, bool SINGLE>
@@ -80,7 +87,10 @@ struct CudaBackend {
   void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
     prep(k_rowz_mid_persist<TW>, smem);
-    k_rowz_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
+    RowParams q = p;
+    q.trace = trace_row;
+    if (row_ctr && row_dyn) { q.ctr = row_ctr + (row_ctr_next++ % kRowCtrs); }
+    k_rowz_mid_persist<TW><<<grid, kThreads, smem, s>>>(q, n_tiles);
     after();
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, const PackGeom& q) {
@@ -126,6 +136,16 @@ class FusedEngine final : public FftEngine {
       col_tma_sms_ = (te && te[0] == '1') ? sms : 0;          // opt-in: measured slower than 3 co-resident k_col CTAs (profiles/README.md)
       const char* pe = getenv("DPX_PAIRS");                   // 0 disables the plane-pair engine (for A/B runs)
       pairs_enabled_ = !(pe && pe[0] == '0');
+      DPX_CUDA(cudaMalloc(&row_ctr_, sizeof(int) * CudaBackend::kRowCtrs));
+      const char* de = getenv("DPX_ROW_DYN");                 // 0 = static round-robin tiles in the persistent pair kernel
+      row_dyn_ = !(de && de[0] == '0');
+      trace_path_ = getenv("DPX_TRACE");
+      if (trace_path_) {
+        DPX_CUDA(cudaMalloc(&trace_col_, kTraceRecs * 16 * sizeof(unsigned long long)));
+        DPX_CUDA(cudaMalloc(&trace_row_, kTraceRecs * 16 * sizeof(unsigned long long)));
+        DPX_CUDA(cudaMemset(trace_col_, 0, kTraceRecs * 16 * sizeof(unsigned long long)));
+        DPX_CUDA(cudaMemset(trace_row_, 0, kTraceRecs * 16 * sizeof(unsigned long long)));
+      }
     }
     rc = upload_twiddles(g.H, &tw_h_);
     if (!rc) rc = upload_twiddles(g.W, &tw_w_);
@@ -134,10 +154,20 @@ class FusedEngine final : public FftEngine {
   int r2c(const float* in, float2* out, cudaStream_t s) override { return inner_->r2c(in, out, s); }
   int c2r(float2* in, float* out, cudaStream_t s) override { return inner_->c2r(in, out, s); }
   size_t workspace_bytes() const override { return bytes_ + (inner_ ? inner_->workspace_bytes() : 0); }
+  void dump_trace() {
+    if (!trace_path_ || !trace_col_) return;
+    std::vector<unsigned long long> h(2 * kTraceRecs * 16);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h.data(), trace_col_, kTraceRecs * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data() + kTraceRecs * 16, trace_row_, kTraceRecs * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path_, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+    cudaFree(trace_col_); cudaFree(trace_row_); trace_col_ = trace_row_ = nullptr;
+  }
   void destroy() override {
+    dump_trace();
     if (inner_) inner_->destroy();
     cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(dpsp_); cudaFree(S1_); cudaFree(fbp1_); cudaFree(dqp1_);
-    cudaFree(tw_h_); cudaFree(tw_w_);
+    cudaFree(tw_h_); cudaFree(tw_w_); cudaFree(row_ctr_);
     if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_join_); }
     delete this;
   }
@@ -257,6 +287,9 @@ class FusedEngine final : public FftEngine {
     CudaBackend be{s};
     be.n_persist = persist_ctas_;
     be.n_sm = col_tma_sms_;
+    be.trace_col = trace_col_; be.trace_row = trace_row_;
+    be.row_ctr = row_ctr_; be.row_dyn = row_dyn_ && n_iters <= CudaBackend::kRowCtrs;   // one zeroed counter per launch
+    if (row_ctr_ && be.row_dyn) DPX_CUDA(cudaMemsetAsync(row_ctr_, 0, sizeof(int) * std::min(n_iters, (int)CudaBackend::kRowCtrs), s));
     Mode mode = PLANES;
     int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
@@ -322,6 +355,11 @@ class FusedEngine final : public FftEngine {
   int dq_batch_ = 1;
   int persist_ctas_ = 0;
   int col_tma_sms_ = 0;
+  int* row_ctr_ = nullptr;
+  int row_dyn_ = 1;
+  static constexpr size_t kTraceRecs = 16384;          // >= CTAs of k_col / tiles of the row kernel at the traced batch
+  const char* trace_path_ = nullptr;
+  unsigned long long *trace_col_ = nullptr, *trace_row_ = nullptr;
   const float2* fb_std_ = nullptr;
   const float* dq_std_ = nullptr;
   const float* dpsi_std_ = nullptr;

@@ -46,6 +46,8 @@ struct RowParams {
   int it;                        // schedule column for lam
   float* x;                      // ROW_LAST: receives x
   const float2* tw;              // twiddle records of the W-tile (fft::TwiddleLayout)
+  int* ctr = nullptr;            // persistent pair kernel: dynamic tile counter of this launch (zeroed), or nullptr = static round robin
+  unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
 };
 
 struct ColParams {
@@ -61,6 +63,7 @@ struct ColParams {
   float wid, eps, inv_n;
   RhoRef rho;
   const float2* tw;              // twiddle records of the H-tile
+  unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
 };
 
 DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
@@ -74,7 +77,16 @@ DPX_HD float fast_div(float a, float b) { return a / b; }
 DPX_HD float2 ld_stream2(const float2* p) { return *p; }
 DPX_HD float4 ld_stream4(const float4* p) { return *p; }
 DPX_HD void prefetch_l2(const void*) {}
+DPX_HD void trace_stamp(unsigned long long*, int, int) {}
 #else
+DPX_HD void trace_stamp(unsigned long long* tr, int rec, int slot) {
+  if (tr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[(size_t)rec * 16 + slot] = t;
+    if (slot == 1) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tr[(size_t)rec * 16] = sm; }
+  }
+}
 // pull one 128-byte line into L2 ahead of the CTA that will stream it (software pipelining across CTAs)
 DPX_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 DPX_HD float fast_div(float a, float b) { return __fdividef(a, b); }
@@ -121,7 +133,12 @@ DPX_HD void bulk_commit() {}
 DPX_HD void bulk_wait_read_all() {}
 DPX_HD void bulk_wait_all() {}
 DPX_HD void fence_async_smem() {}
+DPX_HD void bulk_prefetch_l2(const void*, unsigned) {}
 #else
+// one instruction pulls a whole run into L2 (TMA engine); unlike prefetch.global.L2 it is not dropped under load
+DPX_HD void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 #define DPX_MBAR_ALL_WAIT 0
 typedef unsigned long long mbar_t;
 DPX_HD unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -580,8 +597,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
 // ------------------------------------------------------------------------------------------------
 //  Column kernel
 // ------------------------------------------------------------------------------------------------
-template <class TH>
-__global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
+// STAGE: the tile is brought in by cp.async straight to its padded shared-memory positions -- the whole 64 KB tile is in
+// flight at once without holding registers or L1 lines -- and pass A runs in place (measured +2.8 % on the headline workload
+// against register-fed 2 x 16 loads per thread, +6.5 % at 4096 points; -1.4 ... -4 % for tiles of 1024 points and fewer, whose
+// CTAs are short enough for their co-resident siblings to cover the load; profiles/README.md round 2) -- hence by tile size.
+template <class TH, bool STAGE = (TH::N >= 2048)>
+__global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 3 <= 225 * 1024) ? 3 : 1) k_col(ColParams P) {
   static_assert(TH::COLS == CG, "column tile holds CG columns");
   constexpr int H = TH::N, RA = TH::RA, RC = TH::RC, MA = TH::MA;
   DPX_DYN_SMEM(float2, sm);
@@ -592,31 +613,50 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
   const int p = blockIdx.x * P.C + blockIdx.z;
   const int b = blockIdx.x * P.bmul;
   const int NG = P.groups;
+  const int rec = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tid == 0) trace_stamp(P.trace, rec, 1);
   float2* tile = P.S + ((size_t)p * NG + g) * H * CG;
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
+  if (STAGE) {
+    // 16-byte pieces = columns (0,1) / (2,3) of one row, contiguous both in global memory and at the padded position
+    for (int i = tid; i < H * CG / 2; i += kThreads) {
+      const int n = i >> 1, c2 = (i & 1) * 2;
+      cp_async16(sm + TH::phys(n, c2), tile + (size_t)n * CG + c2);
+    }
+    cp_async_commit();
+  }
   {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
     const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * NG + g) * H * CG);
     for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) prefetch_l2(nf + o);
   }
 
-  // ---- pass A of the forward FFT, fed straight from global memory ---------------------------------------------
-  for (int t = tid; t < CG * MA; t += kThreads) {
-    const int c = t % CG, j = t / CG;
-    const int p0 = TH::phys(j, c);
-    float2 a[RA], w[RA];
+  // ---- pass A of the forward FFT: in place on the staged tile, or fed straight from global memory ---------------------
+  if (STAGE) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid == 0) trace_stamp(P.trace, rec, 2);
+    fft::smem_pass<TH, RA, H, false, true>(sm, twA, tid, kThreads);
+  } else {
+    for (int t = tid; t < CG * MA; t += kThreads) {
+      const int c = t % CG, j = t / CG;
+      const int p0 = TH::phys(j, c);
+      float2 a[RA], w[RA];
 #pragma unroll
-    for (int m = 0; m < RA; ++m) a[m] = ld_stream2(tile + (size_t)(j + m * MA) * CG + c);   // streamed: the small L1 next to
-    fft::Dft<RA, false>::run(a);                                                              // 217 KB of tiles is kept for twiddles
-    fft::load_twiddles<RA, MA>(twA, j, w);
+      for (int m = 0; m < RA; ++m) a[m] = ld_stream2(tile + (size_t)(j + m * MA) * CG + c);   // streamed: the small L1 next to
+      fft::Dft<RA, false>::run(a);                                                              // 217 KB of tiles is kept for twiddles
+      fft::load_twiddles<RA, MA>(twA, j, w);
 #pragma unroll
-    for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
+      for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);
 #pragma unroll
-    for (int m = 0; m < RA; ++m) sm[p0 + TH::template delta<MA>(m) * CG] = a[m];
+      for (int m = 0; m < RA; ++m) sm[p0 + TH::template delta<MA>(m) * CG] = a[m];
+    }
   }
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, rec, 3);
   fft::smem_pass<TH, TH::RB, TH::MA, false, true>(sm, twB, tid, kThreads);
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, rec, 4);
 
   // ---- pass C, spectral solve, inverse pass C — all on a thread-private block of RC positions ------------------------
   const float rho = P.rho.p[(size_t)b * P.rho.stride + P.rho.it];
@@ -666,8 +706,10 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
     for (int m = 0; m < RC; ++m) sm[p0 + TH::template delta<1>(m) * CG] = a[m];
   }
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, rec, 5);
   fft::smem_pass<TH, TH::RB, TH::MA, true, true>(sm, twB, tid, kThreads);
   __syncthreads();
+  if (tid == 0) trace_stamp(P.trace, rec, 6);
 
   // ---- inverse pass A, written straight to global memory ------------------------------------------------------------------
   for (int t = tid; t < CG * MA; t += kThreads) {
@@ -683,6 +725,7 @@ __global__ void __launch_bounds__(kThreads) k_col(ColParams P) {
 #pragma unroll
     for (int m = 0; m < RA; ++m) tile[(size_t)(j + m * MA) * CG + c] = a[m];
   }
+  if (tid == 0) trace_stamp(P.trace, rec, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -978,15 +1021,18 @@ struct RowZPersistSmem {
   static constexpr int G = TW::N / CG;
   static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
   static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
-  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t);
+  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t) + 16;   // + next-tile slot
   // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
   static constexpr int CTAS_PER_SM = (TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2;
 };
 
 struct RowZTile { int pp, h0, pA, pB; };
-DPX_HD RowZTile rowz_tile(const RowParams& P, int tile, int tiles_per_pair) {
+DPX_HD RowZTile rowz_tile(const RowParams& P, int tile, int tiles_per_pair, int n_tiles) {
   RowZTile t;
-  t.pp = tile / tiles_per_pair; t.h0 = (tile - t.pp * tiles_per_pair) * ZR;
+  const int seq = tile / tiles_per_pair;
+  t.h0 = (tile - seq * tiles_per_pair) * ZR;
+  t.pp = seq;
+  (void)n_tiles;
   const int bq = t.pp / P.C;
   t.pA = 2 * bq * P.C + (t.pp - bq * P.C); t.pB = t.pA + P.C;
   return t;
@@ -1039,7 +1085,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   }
   __syncthreads();
   int tile = blockIdx.x;
-  RowZTile cur = rowz_tile(P, tile < n_tiles ? tile : 0, tpp);
+  RowZTile cur = rowz_tile(P, tile < n_tiles ? tile : 0, tpp, n_tiles);
   if (tile < n_tiles) {
     if (tid == 0 && !hqs) mbar_expect_tx(bars + 1, U_BYTES);
     __syncthreads();
@@ -1048,15 +1094,28 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   }
   cp_async_commit();
 
+  // tiles after the first come from a device counter when one is given: SMs differ by ~13 % in per-tile time (distance to
+  // the L2 slices), and a static round robin leaves the fast ones idle for the last 10 % of the kernel (DPX_TRACE timeline)
+  volatile int* s_next = reinterpret_cast<volatile int*>(bars + 2);
   unsigned phase = 0;
-  for (; tile < n_tiles; tile += gridDim.x, phase ^= 1u) {
+  int next = tile + gridDim.x;
+  for (; tile < n_tiles; tile = next, phase ^= 1u) {
     const int pp = cur.pp, h0 = cur.h0, pA = cur.pA, pB = cur.pB;
     const int b = 2 * (pp / P.C);
-    const int next = tile + gridDim.x;
-    const RowZTile nxt = rowz_tile(P, next < n_tiles ? next : tile, tpp);
+    if (tid == 0) {
+      trace_stamp(P.trace, tile, 1);
+#ifndef DPX_EMU
+      if (P.ctr) *s_next = (int)gridDim.x + atomicAdd(P.ctr, 1);
+      else
+#endif
+        *s_next = tile + (int)gridDim.x;
+    }
     cp_async_wait_all();
     if (DPX_MBAR_ALL_WAIT || tid == 0) { if (!hqs) mbar_wait(bars + 1, phase); }   // one poller; the barrier below publishes it
     __syncthreads();                                   // staged inputs are visible; the tile buffer is free
+    next = *s_next;
+    const RowZTile nxt = rowz_tile(P, next < n_tiles ? next : tile, tpp, n_tiles);
+    if (tid == 0) trace_stamp(P.trace, tile, 2);
     if (tid == 0 && next < n_tiles && !hqs) mbar_expect_tx(bars + 1, U_BYTES);   // copies are issued behind later barriers
 
     // ---- 1. inverse pass C out of the staged spectrum rows (column storage order: see k_rowz) ----------------------------
@@ -1073,10 +1132,12 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       for (int m = 0; m < RC; ++m) sm[p0 + TW::template delta<1>(m) * NSEQ] = a[m];
     }
     __syncthreads();                                   // stS consumed
+    if (tid == 0) trace_stamp(P.trace, tile, 3);
     if (next < n_tiles) rowz_stage_S<TW>(P, nxt, stS, tid);
     cp_async_commit();
     fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
     __syncthreads();
+    if (tid == 0) trace_stamp(P.trace, tile, 4);
 
     // ---- 2. last inverse pass -> (x_A, x_B);  prox / dual / next rhs in registers (dual rows from the stage);  first forward pass
     {
@@ -1128,11 +1189,13 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       }
     }
     __syncthreads();                                   // stU consumed, tile holds pass-A output
+    if (tid == 0) trace_stamp(P.trace, tile, 5);
     if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, nxt, stU, bars + 1, tid);
 
     // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
     fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
     __syncthreads();
+    if (tid == 0) trace_stamp(P.trace, tile, 6);
     for (int t = tid; t < NT1; t += kThreads) {
       const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
       const int blk = gq * CG + cc;
@@ -1146,6 +1209,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
     }
     cur = nxt;
+    if (tid == 0) trace_stamp(P.trace, tile, 7);
   }
   cp_async_wait_all();
 }
