@@ -19,11 +19,21 @@
 //   * epilogue (8 warps: two per TMEM lane quadrant, 48 channels each): tcgen05.ld x3 -> + bias -> ReLU (or the ReLU mask of
 //     the saved forward activation: data gradient) -> bf16 -> coalesced 16-byte stores in the same layout (the next
 //     layer's input).
+// SPLIT (fp32-class accuracy on the same tensor cores, `precision="fp32"` of the denoiser): every operand is the sum of two fp16
+// numbers, v = hi + 2^-11 lo' (hi = fp16(v), lo' = fp16((v - hi) 2^11): 22 mantissa bits), and the product is formed as
+//     main = a_hi w_hi            corr = a_lo' w_hi + a_hi w_lo'            result = main + 2^-11 corr
+// in TWO TMEM accumulators per stage (the lo' lo' term is 2^-22 relative and dropped; fp16 x fp16 products are exact in the
+// fp32 accumulator).  Three MMAs per k-step instead of one.  Both operand pieces of a layer do not fit shared memory next to
+// each other for 96 -> 96 channels, so such a layer runs as TWO launches over one half of the input channels each (ring slot =
+// hi + lo' pieces of 48 channels = the same 12 planes as the bf16 kernel; filter image = hi + lo' pieces of that half = the same
+// 83 KB), handing an fp32 partial sum from the first to the second launch, which finalises (bias, ReLU / mask, re-split).
+// Activation tensors of this mode: fp16 [N][khalf][piece][kp][H][W+2][8] with kp = channel groups per K-half.
 // Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + (leader CTA) MMA issue,
 // warps 2..9 = epilogue.  Persistent: a cluster walks over pairs of (image, 128-pixel column tile, 16-row block) work units.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,7 +48,7 @@ constexpr int N_EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + 32 * N_EPI_WARPS;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
 
-template <int CGIN, int COUT>
+template <int CGIN, int COUT, bool SPLIT = false>
 struct Cfg {
   static constexpr int NH = COUT / 2;                                   // output channels held by one CTA of the pair
   static constexpr int KSTEPS = CGIN / 2;                               // UMMA_K = 16 bf16 = 2 channel groups
@@ -47,9 +57,14 @@ struct Cfg {
   static constexpr uint32_t W_TAP_BYTES = CGIN * NH * 16;               // one tap of this CTA's filter half
   static constexpr uint32_t W_BYTES = 9 * W_TAP_BYTES;
   static constexpr uint32_t A_LBO = HALO_PX * 16, B_LBO = NH * 16;      // byte distance of the two K halves of one MMA
-  static constexpr int ACC_STRIDE = COUT <= 32 ? 32 : 128;              // TMEM columns per accumulator stage
-  static constexpr int NACC = 3;                                        // accumulator stages
-  static constexpr int TMEM_COLS = COUT <= 32 ? 128 : 512;              // power of two >= NACC * ACC_STRIDE
+  static constexpr int CORR_OFF = COUT <= 32 ? 32 : 128;                // SPLIT: TMEM column offset of the correction accumulator
+  static constexpr int ACC_STRIDE = (SPLIT ? 2 : 1) * CORR_OFF;         // TMEM columns per accumulator stage
+  static constexpr int NACC = (SPLIT && COUT > 32) ? 2 : 3;             // accumulator stages
+  static constexpr int TMEM_COLS = COUT <= 32 ? (SPLIT ? 256 : 128) : 512;   // power of two >= NACC * ACC_STRIDE
+  static constexpr int KP = CGIN / 2;                                   // SPLIT: channel groups per operand piece
+  static constexpr int OUT_KP = COUT >= 96 ? 6 : COUT / 8;              // SPLIT: groups per piece and K-half of the OUTPUT tensor (a
+                                                                        // 96-channel tensor is consumed in two K-halves of 6 groups)
+  static_assert(!SPLIT || CGIN % 4 == 0, "SPLIT: hi and lo' pieces of an even number of channel groups");
   static constexpr int EPI_COLS = COUT / 2 >= 16 ? COUT / 2 : COUT;     // channels per epilogue warp (two warps per lane quadrant)
   static constexpr int EPI_SPLIT = COUT / EPI_COLS;                     // 2, or 1 when the layer is too narrow to split
   static constexpr size_t SMEM = 1024 + (W_BYTES + 127) / 128 * 128 + (size_t)NSLOT * SLOT_BYTES + 256;
@@ -58,13 +73,21 @@ struct Cfg {
 };
 
 struct Params {
-  const __nv_bfloat16* wpack;      // [2 halves][9 taps][CGIN][NH][8]
+  const void* wpack;               // [2 halves][9 taps][CGIN][NH][8] bf16 (SPLIT: fp16, groups = hi piece then lo' piece)
   float bias[96];                  // per output channel (kernel-parameter constant bank: free operands in the epilogue)
   __nv_bfloat16* out;              // [N][COUT/8][H][W+2][8]
   const __nv_bfloat16* mask;       // optional, same layout as out: result is zeroed where mask <= 0 (ReLU backward)
   int N, H, W;
   int relu;
   int n_tiles, x_tiles, row_blocks;   // CTA work units: (image, 128-pixel column tile, 16-row block)
+  int in_planes, in_plane_off;     // planes per image of the input tensor; first plane of this launch (SPLIT: khalf * CGIN)
+  // ---- SPLIT mode ----
+  __half* out16;                   // output pieces [N][khalf][piece][out_kp][H][W+2][8] (next layer's input / saved activation)
+  const __half* mask16;            // optional: saved forward activation in the out16 layout; zero the result where its hi piece <= 0
+  int out_kp;                      // channel groups per piece and K-half of the output tensor (6 for 96 channels, 2 for 16)
+  const float* pin;                // fp32 partial sum of the previous K-half [N][COUT/8][H][W+2][8], or nullptr
+  float* pout;                     // if set: write the fp32 partial sum there and do not finalise
+  float* out32;                    // if set (last layer): fp32 result [N][COUT/8][H][W+2][8] instead of pieces
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------------
@@ -144,6 +167,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
 }
+// (lo, hi) fp32 -> packed fp16, round to nearest even, saturating to the largest finite value
+__device__ __forceinline__ __half2 cvt_sat_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle: rows (pixels / output channels) 16 B apart, 8-row groups `sbo` bytes
@@ -154,8 +183,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
          ((uint64_t)1 << 46);
 }
 // instruction descriptor of kind::f16: fp32 accumulate, bf16 x bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool fp16 = false) {
+  // a_format [7,10) / b_format [10,13): 0 = fp16, 1 = bf16
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct Unit { int n, x0, y0; };
@@ -172,10 +202,10 @@ __device__ __forceinline__ Unit unit_of(const Params& P, int u, int rank) {
   return t;
 }
 
-template <int CGIN, int COUT>
+template <int CGIN, int COUT, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     k_conv3x3_tc(const __grid_constant__ CUtensorMap in_map, Params P) {
-  using C = Cfg<CGIN, COUT>;
+  using C = Cfg<CGIN, COUT, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sm_w = base;                                       // this CTA's filter half: [9][CGIN][NH][8] bf16
@@ -229,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           mbar_wait(empty + s, ph ^ 1);
           if (leader) mbar_expect_tx(full + s, 2 * C::ROW_BYTES);
           // padded index of image pixel x0 - 1 is x0
-          tma_row(sm_a + (size_t)s * C::SLOT_BYTES, &in_map, full + s, t.x0, t.y0 - 1 + r, t.n * CGIN);
+          tma_row(sm_a + (size_t)s * C::SLOT_BYTES, &in_map, full + s, t.x0, t.y0 - 1 + r, t.n * P.in_planes + P.in_plane_off);
         }
       }
     }
@@ -239,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     // single-lane branch made every operand a per-thread value and cost a ~20-instruction uniform-broadcast loop per MMA:
     // 91 cycles per MMA instead of the tensor pipe's 48) =====
     if (leader) {
-      constexpr uint32_t IDESC = instr_desc(2 * TILE_PX, COUT);
+      constexpr uint32_t IDESC = instr_desc(2 * TILE_PX, COUT, SPLIT);
       const uint32_t a0 = s2u(sm_a);
       const uint64_t bd0 = smem_desc(s2u(sm_w), C::B_LBO, 128);
       uint32_t it_base = 0, acc_it = 0;
@@ -263,11 +293,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             const uint64_t ad0 = smem_desc(a0 + slot * C::SLOT_BYTES, C::A_LBO, 128);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
+              if constexpr (!SPLIT) {
 #pragma unroll
-              for (int k = 0; k < C::KSTEPS; ++k) {
-                const uint64_t ad = ad0 + (uint64_t)((dx * 16 + 2 * k * C::A_LBO) >> 4);
-                const uint64_t bd = bd0 + (uint64_t)(((dy * 3 + dx) * C::W_TAP_BYTES + 2 * k * C::B_LBO) >> 4);
-                if (elect_one()) umma_2sm(d, ad, bd, IDESC, (dy | dx | k) != 0);
+                for (int k = 0; k < C::KSTEPS; ++k) {
+                  const uint64_t ad = ad0 + (uint64_t)((dx * 16 + 2 * k * C::A_LBO) >> 4);
+                  const uint64_t bd = bd0 + (uint64_t)(((dy * 3 + dx) * C::W_TAP_BYTES + 2 * k * C::B_LBO) >> 4);
+                  if (elect_one()) umma_2sm(d, ad, bd, IDESC, (dy | dx | k) != 0);
+                }
+              } else {
+                // groups [0, KP) = hi piece, [KP, 2 KP) = lo' piece, of the activations (ring slot) and of the filter image alike
+#pragma unroll
+                for (int k = 0; k < C::KP / 2; ++k) {
+                  const uint64_t ah = ad0 + (uint64_t)((dx * 16 + 2 * k * C::A_LBO) >> 4);
+                  const uint64_t al = ah + (uint64_t)((C::KP * C::A_LBO) >> 4);
+                  const uint64_t bh = bd0 + (uint64_t)(((dy * 3 + dx) * C::W_TAP_BYTES + 2 * k * C::B_LBO) >> 4);
+                  const uint64_t bl = bh + (uint64_t)((C::KP * C::B_LBO) >> 4);
+                  if (elect_one()) {
+                    umma_2sm(d, ah, bh, IDESC, (dy | dx | k) != 0);
+                    umma_2sm(d + C::CORR_OFF, al, bh, IDESC, (dy | dx | k) != 0);
+                    umma_2sm(d + C::CORR_OFF, ah, bl, IDESC, 1);
+                  }
+                }
               }
             }
           }
@@ -299,38 +345,114 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       for (int j = 0; j < ROW_BLOCK; ++j, ++acc_it) {
         const uint32_t a = acc_it % C::NACC, aph = (acc_it / C::NACC) & 1;
         const int y = t.y0 + j;
+        [[maybe_unused]] float pv[SPLIT ? C::EPI_COLS : 1];
+        if constexpr (SPLIT) {
+          // the previous K-half's partial sums of this row are requested BEFORE the wait for the accumulator: their DRAM latency
+          // hides behind the row's MMAs
+          if (P.pin && t.n < P.N && x < P.W && y < P.H) {
+#pragma unroll
+            for (int g = 0; g < C::EPI_COLS / 8; ++g) {
+              const size_t o32 = ((((size_t)t.n * (COUT / 8) + cbase / 8 + g) * P.H + y) * Wp + x + 1) * 8;
+              *reinterpret_cast<float4*>(&pv[g * 8]) = *reinterpret_cast<const float4*>(P.pin + o32);
+              *reinterpret_cast<float4*>(&pv[g * 8 + 4]) = *reinterpret_cast<const float4*>(P.pin + o32 + 4);
+            }
+          }
+        }
         mbar_wait(tfull + a, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + a * C::ACC_STRIDE + cbase + ((uint32_t)(quad * 32) << 16);
         uint32_t v[C::EPI_COLS];
 #pragma unroll
         for (int c0 = 0; c0 < C::EPI_COLS; c0 += 16) tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(tempty + a);         // accumulator `a` is in registers: the MMA thread may reuse it
-        if (t.n < P.N && x < P.W && y < P.H) {
+        if constexpr (!SPLIT) {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty + a);         // accumulator `a` is in registers: the MMA thread may reuse it
+          if (t.n < P.N && x < P.W && y < P.H) {
 #pragma unroll
-          for (int g = 0; g < C::EPI_COLS / 8; ++g) {          // channel groups of 8
-            const int cg = cbase / 8 + g;
-            const size_t o = ((((size_t)t.n * (COUT / 8) + cg) * P.H + y) * Wp + x + 1) * 8;
-            float f[8];
+            for (int g = 0; g < C::EPI_COLS / 8; ++g) {          // channel groups of 8
+              const int cg = cbase / 8 + g;
+              const size_t o = ((((size_t)t.n * (COUT / 8) + cg) * P.H + y) * Wp + x + 1) * 8;
+              float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              f[e] = __uint_as_float(v[g * 8 + e]) + P.bias[cbase + g * 8 + e];
-              if (P.relu) f[e] = fmaxf(f[e], 0.f);
+              for (int e = 0; e < 8; ++e) {
+                f[e] = __uint_as_float(v[g * 8 + e]) + P.bias[cbase + g * 8 + e];
+                if (P.relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              if (P.mask) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(P.mask + o);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (!(__bfloat162float(mb[e]) > 0.f)) f[e] = 0.f;
+              }
+              uint4 pk;
+              __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pb[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              *reinterpret_cast<uint4*>(P.out + o) = pk;
             }
-            if (P.mask) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(P.mask + o);
-              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+          }
+        } else {
+          uint32_t vc[C::EPI_COLS];                              // correction accumulator (carries a factor 2^11)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) if (!(__bfloat162float(mb[e]) > 0.f)) f[e] = 0.f;
+          for (int c0 = 0; c0 < C::EPI_COLS; c0 += 16) tmem_ld16(taddr + C::CORR_OFF + c0, *reinterpret_cast<uint32_t(*)[16]>(&vc[c0]));
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty + a);
+          if (t.n < P.N && x < P.W && y < P.H) {
+#pragma unroll
+            for (int g = 0; g < C::EPI_COLS / 8; ++g) {
+              const int cg = cbase / 8 + g;
+              const size_t o32 = ((((size_t)t.n * (COUT / 8) + cg) * P.H + y) * Wp + x + 1) * 8;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(vc[g * 8 + e]), 1.f / 2048.f, __uint_as_float(v[g * 8 + e]));
+              if (P.pin) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += pv[g * 8 + e];
+              }
+              if (P.pout) {                                      // first K-half: hand the partial sum to the second launch
+                *reinterpret_cast<float4*>(P.pout + o32) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(P.pout + o32 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                continue;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                f[e] += P.bias[cbase + g * 8 + e];
+                if (P.relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              // piece planes of channel group cg in a tensor of COUT / 8 groups split into K-halves of out_kp groups
+              constexpr int OKP = C::OUT_KP;                       // compile-time: cg is a constant after unrolling
+              const int kh = cg / OKP, wi = cg - kh * OKP;
+              const size_t plane_hi = (size_t)t.n * (COUT / 4) + (size_t)kh * 2 * OKP + wi;
+              const size_t oh = ((plane_hi * P.H + y) * Wp + x + 1) * 8;
+              const size_t ol = oh + (size_t)OKP * P.H * Wp * 8;
+              if (P.mask16) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(P.mask16 + oh);
+                const __half* mb = reinterpret_cast<const __half*>(&mk);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (!(__half2float(mb[e]) > 0.f)) f[e] = 0.f;
+              }
+              if (P.out32) {
+                *reinterpret_cast<float4*>(P.out32 + o32) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(P.out32 + o32 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4 ph, pl;
+                __half2* hh = reinterpret_cast<__half2*>(&ph);
+                __half2* hl = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 h = cvt_sat_half2(f[2 * e], f[2 * e + 1]);             // saturating: no inf pieces
+                  const float2 hf = __half22float2(h);
+                  hh[e] = h;
+                  hl[e] = cvt_sat_half2((f[2 * e] - hf.x) * 2048.f, (f[2 * e + 1] - hf.y) * 2048.f);
+                }
+                *reinterpret_cast<uint4*>(P.out16 + oh) = ph;
+                *reinterpret_cast<uint4*>(P.out16 + ol) = pl;
+              }
             }
-            uint4 pk;
-            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pb[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-            *reinterpret_cast<uint4*>(P.out + o) = pk;
           }
         }
       }

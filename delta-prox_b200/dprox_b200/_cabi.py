@@ -86,6 +86,7 @@ SIGNATURES = {
     "dpx_ffdnet_available": (_I, []),
     "dpx_ffdnet_create": (_I, [_I, _I, C.POINTER(_VP)]),
     "dpx_ffdnet_destroy": (None, [_VP]),
+    "dpx_ffdnet_set_precision": (_I, [_VP, _I]),
     "dpx_ffdnet_set_layer": (_I, [_VP, _I, _VP, _VP, _I, _I, _VP]),
     "dpx_ffdnet_forward": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),
     "dpx_ffdnet_forward_train": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),

@@ -42,9 +42,10 @@ class NativeFFDNet:
     """FFDNet-color on tcgen05 tensor cores through the C-ABI (`dpx_ffdnet_*`, csrc/dpx_conv_tc.cuh): channel-group-major
     bf16 activations, hand-written implicit-GEMM 3x3 convolutions (CTA pairs, TMEM accumulators, TMA-staged rows reused for all
     nine taps, resident filter bank), fused bias+ReLU, fused unshuffle/sigma prologue and shuffle/crop epilogue; the data
-    gradient runs on the same kernel.  bf16 operands: ~1e-2 relative to the fp32 network."""
+    gradient runs on the same kernel.  bf16 operands: ~1e-2 relative to the fp32 network; `split=True`: fp16 operand pairs
+    (hi + 2^-11 lo'), ~1e-6 relative to the fp32 network at three times the tensor-core work."""
 
-    def __init__(self, model: "FFDNet", device):
+    def __init__(self, model: "FFDNet", device, split: bool = False):
         import ctypes as C
         from . import _cabi as cabi
         self._cabi, self.device = cabi, torch.device(device)
@@ -54,6 +55,9 @@ class NativeFFDNet:
         self.n_layers = len(convs)
         self._h = C.c_void_p()
         cabi.check(lib.dpx_ffdnet_create(len(convs), convs[1].out_channels, C.byref(self._h)), "dpx_ffdnet_create")
+        # split = fp16 hi + 2^-11 lo' operand pairs, 3 MMAs per k-step: fp32-class accuracy on the same tensor-core kernel
+        self.split = bool(split)
+        cabi.check(lib.dpx_ffdnet_set_precision(self._h, int(self.split)), "dpx_ffdnet_set_precision")
         with torch.cuda.device(self.device):
             for i, c in enumerate(convs):
                 w = c.weight.detach().to(self.device, torch.float32).contiguous()
@@ -164,13 +168,14 @@ class _NativeFFDNetFn(torch.autograd.Function):
 
 
 class FFDNetColorDenoiser(Denoiser):
-    """pnp/denoisers/wrapper.py:38-48.  `precision='fp32'` (default) keeps fp32 convolutions for 1e-5-class parity;
-    `precision='bf16'` runs the native tcgen05 network (NativeFFDNet) — the fast mode."""
+    """pnp/denoisers/wrapper.py:38-48.  `precision='fp32'` (default): the native tcgen05 network with fp16 operand pairs
+    (fp32-class accuracy, 1e-5 parity with the reference's fp32 path); `precision='bf16'`: the same kernels with bf16 operands
+    (the fast mode); `precision='torch'`: the framework's fp32 convolutions (comparison only)."""
 
     def __init__(self, model_path=None, seed=None, precision="fp32"):
         super().__init__()
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "torch"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'torch'")
         self.precision, self._native = precision, None
         self.model = FFDNet(3, 3, 96, 12)
         if model_path is not None:
@@ -198,16 +203,22 @@ class FFDNetColorDenoiser(Denoiser):
                 c.bias.copy_((torch.rand(c.bias.shape, generator=g) * 2 - 1) * bound)
         return self
 
+    def _native_net(self, device):
+        if self._native is None or self._native.device != device:
+            self._native = NativeFFDNet(self.model, device, split=self.precision == "fp32")
+        return self._native
+
     def _denoise(self, x, sigma):
-        wants_grad = torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad
-                                                   or any(p.requires_grad for p in self.model.parameters()))
-        if self.precision == "bf16" and wants_grad and not any(p.requires_grad for p in self.model.parameters()):
+        trainable = any(p.requires_grad for p in self.model.parameters())
+        wants_grad = torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad or trainable)
+        native = self.precision in ("fp32", "bf16")
+        if native and wants_grad and not trainable:
             # unrolled training with a frozen denoiser (BASELINE config 5, e2e_optics_dprox.py:34): forward and data gradient
             # both run on the native tensor-core kernels (activation recomputation when several calls are in flight)
-            if self._native is None or self._native.device != x.device:
-                self._native = NativeFFDNet(self.model, x.device)
-            return _NativeFFDNetFn.apply(x.contiguous(), sigma, self._native)
-        if self.precision == "bf16" and wants_grad:
+            return _NativeFFDNetFn.apply(x.contiguous(), sigma, self._native_net(x.device))
+        if native and not wants_grad:
+            return self._native_net(x.device)(x, sigma)
+        if self.precision == "bf16":
             # trainable denoiser weights: the weight gradient has no native kernel, so the tape runs through the framework's
             # convolutions with bf16 operands / fp32 accumulation
             if not getattr(self, "_nhwc", False):          # NHWC weights: cuDNN's tensor-core kernels for forward, dgrad and wgrad
@@ -215,11 +226,7 @@ class FFDNetColorDenoiser(Denoiser):
                 self._nhwc = True
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.model(x.contiguous(memory_format=torch.channels_last), sigma).float().contiguous()
-        if self.precision == "bf16":
-            if self._native is None or self._native.device != x.device:
-                self._native = NativeFFDNet(self.model, x.device)
-            return self._native(x, sigma)
-        # fp32 convolutions (no TF32) so that results stay within 1e-5 of the fp32 CPU reference
+        # framework fp32 convolutions (no TF32): trainable weights at fp32, or precision='torch'
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:

@@ -259,11 +259,14 @@ int dpx_cg_gate(const float* val, const float* tol, int tol_n, int strict, float
  * deep_prior -> FFDNetColorDenoiser -> FFDNet.forward (proxfn/pnp/prior.py:73-86, denoisers/wrapper.py:38-48,
  * models/network_ffdnet.py:44-68).  Hand-written sm_100a kernel (csrc/dpx_conv_tc.cuh): tcgen05.mma cta_group::2, TMEM
  * accumulators, TMA-staged activation rows reused for all nine taps, filter bank resident in shared memory.
- * bf16 operands, fp32 accumulation: the fast denoiser (~1e-2 relative to the fp32 network). */
+ * Two precisions (dpx_ffdnet_set_precision): 0 = bf16 operands, fp32 accumulation (the fast denoiser, ~1e-2 relative to the
+ * fp32 network); 1 = every operand as fp16 hi + 2^-11 lo' pieces, three MMAs per k-step into two TMEM accumulators
+ * (fp32-class: ~1e-6 relative to the fp32 network -- the mode that meets the 1e-5 parity bar of the reference's fp32 path). */
 typedef struct dpx_ffdnet dpx_ffdnet;
 int dpx_ffdnet_available(void);                       /* 1: the tensor-core path is always built */
 int dpx_ffdnet_create(int nb, int nc, dpx_ffdnet** out);          /* nb conv layers, nc = 96 channels */
 void dpx_ffdnet_destroy(dpx_ffdnet* net);
+int dpx_ffdnet_set_precision(dpx_ffdnet* net, int mode);          /* 0 = bf16 (default), 1 = fp16-pair split (fp32-class) */
 /* layer 0 = head [nc,13,3,3], 1..nb-2 = body [nc,nc,3,3], nb-1 = tail [12,nc,3,3]; w/bias: device fp32, nn.Conv2d layout */
 int dpx_ffdnet_set_layer(dpx_ffdnet* net, int layer, const float* w, const float* bias, int cout, int cin, void* stream);
 /* y = FFDNet(x, sigma); x, y device fp32 [B,3,H,W]; sigma device [B] (sigma_per_sample=1) or [1] */

@@ -406,3 +406,68 @@ def test_cg_device_side_stop_matches_host_test(dp):
         c = fn(Aop, rhs, rtol=1e-4, max_iters=60, check_every=1)        # blocking host test every step
         assert rel(a, c) < 1e-5, fn.__name__                            # (dot products use atomics: last-bit differences)
         assert rel(Aop(a), rhs) < 1e-3
+
+
+# ---- fp32-class FFDNet on the tensor cores: fp16 operand pairs (hi + 2^-11 lo'), three MMAs per k-step ------------------------
+
+def test_split_precision_conv_layers_match_fp32_conv2d(dp):
+    """every layer shape of FFDNet-color (13->96, 96->96, 96->12), forward (+bias, ReLU) and data gradient, through the SPLIT
+    tcgen05 kernel against torch's fp32 convolution in double precision: 1e-6-class, i.e. at the level of an fp32 convolution itself"""
+    import torch.nn.functional as F
+    from dprox_b200.denoisers import FFDNetColorDenoiser, NativeFFDNet
+    den = FFDNetColorDenoiser(seed=4).cuda()
+    net = NativeFFDNet(den.model, torch.device("cuda"), split=True)
+    convs = [m for m in den.model.model if isinstance(m, torch.nn.Conv2d)]
+    g = torch.Generator().manual_seed(5)
+    for layer in (0, 1, 5, len(convs) - 1):
+        c = convs[layer]
+        for shape in ((2, 40, 72), (1, 37, 300)):                       # one partial tile; ragged width over three 128-pixel tiles
+            x = torch.randn(shape[0], c.in_channels, *shape[1:], generator=g).cuda()
+            y = net.conv_layer(layer, x, direction=0, relu=True)
+            want = F.relu(F.conv2d(x.double(), c.weight.double(), c.bias.double(), padding=1))
+            assert rel(y, want) < 2e-6, (layer, shape, rel(y, want))
+            gy = torch.randn(shape[0], c.out_channels, *shape[1:], generator=g).cuda()
+            gx = net.conv_layer(layer, gy, direction=1)
+            want = F.conv_transpose2d(gy.double(), c.weight.double(), padding=1)
+            assert rel(gx, want) < 2e-6, (layer, shape, rel(gx, want))
+
+
+def test_split_precision_ffdnet_meets_the_fp32_bar(dp):
+    """default denoiser (`precision="fp32"`) = native SPLIT network: against the UNMODIFIED reference's output (golden, fp32 CPU) at
+    the 1e-5 parity bar, against the framework's fp32 convolutions on ragged shapes, and its data gradient against fp32 autograd"""
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    den = FFDNetColorDenoiser(seed=4).cuda().requires_grad_(False)
+    ref = FFDNetColorDenoiser(seed=4, precision="torch").cuda().requires_grad_(False)
+    gold = load("ffdnet_forward")
+    y = den.denoise(T(gold["x"]), T(gold["sigma"]))
+    assert den._native is not None and den._native.split
+    assert rel(y, gold["y"]) < 1e-5, rel(y, gold["y"])
+    g = torch.Generator().manual_seed(8)
+    for shape in ((2, 3, 64, 96), (1, 3, 45, 70), (1, 3, 300, 520)):
+        x = torch.rand(*shape, generator=g).cuda()
+        sig = (0.02 + 0.1 * torch.rand(shape[0], generator=g)).cuda()
+        r = rel(den.denoise(x, sig), ref.denoise(x, sig))
+        assert r < 5e-6, (shape, r)
+    # data gradient (frozen denoiser under autograd): native forward_train + backward vs fp32 autograd through the torch module
+    x = torch.rand(2, 3, 70, 90, generator=g).cuda().requires_grad_(True)
+    sig = (0.02 + 0.1 * torch.rand(2, generator=g)).cuda().requires_grad_(True)
+    w = torch.randn(2, 3, 70, 90, generator=g).cuda()
+    (den._denoise(x, sig) * w).sum().backward()
+    gx, gs = x.grad.clone(), sig.grad.clone()
+    x.grad = sig.grad = None
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        (ref.model(x, sig) * w).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    g32x, g32s = x.grad.clone(), sig.grad.clone()
+    # the input gradient of a ReLU network is discontinuous in its pre-activations: units within round-off of zero switch their
+    # whole path, so two fp32-class evaluations differ by ~sqrt(fraction of flipped units).  Arbiter: the same network in fp64.
+    import copy
+    m64 = copy.deepcopy(ref.model).double()
+    x64, s64 = x.detach().double().requires_grad_(True), sig.detach().double().requires_grad_(True)
+    (m64(x64, s64) * w.double()).sum().backward()
+    ours, torch32 = rel(gx, x64.grad), rel(g32x, x64.grad)
+    assert ours < 2 * torch32 + 1e-5, (ours, torch32)
+    assert rel(gs, s64.grad) < 2 * rel(g32s, s64.grad) + 1e-5, (rel(gs, s64.grad), rel(g32s, s64.grad))
