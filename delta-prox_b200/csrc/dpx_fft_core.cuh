@@ -262,6 +262,63 @@ struct Dft<20, INV> {  // A = 5, B = 4: m = 4 m1 + m2, q = q1 + 5 q2
   }
 };
 
+// radix 9 = 3 x 3 and 15 = 3 x 5: column lengths 1080 = 15*9*8, 720 = 10*9*8, 1440 = 15*12*8, 1200 = 15*10*8, 2160 = 15*9*16 (the
+// camera formats whose WIDTH -- 1920, 1280, 2560, 1600, 3840 -- already factors into 2, 3*4, 5*2 and 5*4)
+template <bool INV>
+DPX_HD float2 w9(int k) {
+  const float c[9] = {1.f, 0.76604444311897801f, 0.17364817766693041f, -0.49999999999999978f, -0.93969262078590832f, -0.93969262078590843f, -0.50000000000000044f, 0.17364817766692997f, 0.76604444311897779f};
+  const float s[9] = {0.f, 0.64278760968653925f, 0.98480775301220802f, 0.86602540378443871f, 0.34202014332566888f, -0.34202014332566866f, -0.86602540378443837f, -0.98480775301220813f, -0.64278760968653958f};
+  return make_float2(c[k % 9], INV ? s[k % 9] : -s[k % 9]);
+}
+template <bool INV>
+DPX_HD float2 w15(int k) {
+  const float c[15] = {1.f, 0.91354545764260087f, 0.66913060635885824f, 0.30901699437494745f, -0.10452846326765333f, -0.49999999999999978f, -0.80901699437494734f, -0.97814760073380569f, -0.97814760073380569f, -0.80901699437494756f, -0.50000000000000044f, -0.10452846326765423f, 0.30901699437494723f, 0.66913060635885846f, 0.91354545764260098f};
+  const float s[15] = {0.f, 0.40673664307580015f, 0.74314482547739413f, 0.95105651629515353f, 0.9945218953682734f, 0.86602540378443871f, 0.58778525229247325f, 0.20791169081775931f, -0.20791169081775907f, -0.58778525229247303f, -0.86602540378443837f, -0.99452189536827329f, -0.95105651629515364f, -0.74314482547739402f, -0.40673664307580015f};
+  return make_float2(c[k % 15], INV ? s[k % 15] : -s[k % 15]);
+}
+template <bool INV>
+struct Dft<9, INV> {   // A = 3, B = 3: m = 3 m1 + m2, q = q1 + 3 q2
+  static DPX_HD void run(float2 (&a)[9]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 3; ++m2) dft3<INV>(a[m2], a[3 + m2], a[6 + m2]);             // y[m2][q1] in a[3*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 3; ++q1) {
+#pragma unroll
+      for (int m2 = 1; m2 < 3; ++m2) a[3 * q1 + m2] = cmul(a[3 * q1 + m2], w9<INV>(m2 * q1));
+    }
+    float2 o[9];
+#pragma unroll
+    for (int q1 = 0; q1 < 3; ++q1) {
+      float2 y0 = a[3 * q1], y1 = a[3 * q1 + 1], y2 = a[3 * q1 + 2];
+      dft3<INV>(y0, y1, y2);
+      o[q1] = y0; o[q1 + 3] = y1; o[q1 + 6] = y2;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = o[i];
+  }
+};
+template <bool INV>
+struct Dft<15, INV> {  // A = 3, B = 5: m = 5 m1 + m2, q = q1 + 3 q2
+  static DPX_HD void run(float2 (&a)[15]) {
+#pragma unroll
+    for (int m2 = 0; m2 < 5; ++m2) dft3<INV>(a[m2], a[5 + m2], a[10 + m2]);            // y[m2][q1] in a[5*q1+m2]
+#pragma unroll
+    for (int q1 = 1; q1 < 3; ++q1) {
+#pragma unroll
+      for (int m2 = 1; m2 < 5; ++m2) a[5 * q1 + m2] = cmul(a[5 * q1 + m2], w15<INV>(m2 * q1));
+    }
+    float2 o[15];
+#pragma unroll
+    for (int q1 = 0; q1 < 3; ++q1) {
+      float2 y0 = a[5 * q1], y1 = a[5 * q1 + 1], y2 = a[5 * q1 + 2], y3 = a[5 * q1 + 3], y4 = a[5 * q1 + 4];
+      dft5<INV>(y0, y1, y2, y3, y4);
+      o[q1] = y0; o[q1 + 3] = y1; o[q1 + 6] = y2; o[q1 + 9] = y3; o[q1 + 12] = y4;
+    }
+#pragma unroll
+    for (int i = 0; i < 15; ++i) a[i] = o[i];
+  }
+};
+
 // ---- tile geometry ------------------------------------------------------------------------------------
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
@@ -276,7 +333,8 @@ struct Tile {
   // padded point index: one spare point after every 8 points and one more after every MA points.  With the
   // thread->task maps used below this makes every pass AND the digit-reversal scatter/gather of the row kernel
   // free of shared-memory bank conflicts per half-warp (COLS in {2,4}).
-  static DPX_HD int pn(int n) { return n + (n >> 3) + (n >> LOG_MA); }
+  static constexpr bool MA_POW2 = (MA & (MA - 1)) == 0;   // odd factors in the later passes (720 = 10*9*8, 1920 = 20*12*8, ...) make MA = 72, 96, ...
+  static DPX_HD int pn(int n) { return n + (n >> 3) + (MA_POW2 ? (n >> LOG_MA) : n / MA); }
   static constexpr int PADDED_N = N + N / 8 + RA;
   static constexpr int SMEM_FLOAT2 = PADDED_N * COLS;
   static DPX_HD int phys(int n, int c) { return pn(n) * COLS + c; }
@@ -308,10 +366,10 @@ template <int R, int M>
 DPX_HD void load_twiddles(const float2* __restrict__ rec, int j, float2 (&w)[R]) {
   const float4* r4 = reinterpret_cast<const float4*>(rec) + j;
 #pragma unroll
-  for (int q = 0; q < R / 2; ++q) {
+  for (int q = 0; q < (R + 1) / 2; ++q) {                 // odd radix: the last record's second factor is padding
     const float4 v = r4[q * M];
     w[2 * q] = make_float2(v.x, v.y);
-    w[2 * q + 1] = make_float2(v.z, v.w);
+    if (2 * q + 1 < R) w[2 * q + 1] = make_float2(v.z, v.w);
   }
 }
 
@@ -357,7 +415,8 @@ DPX_HD void smem_pass(float2* sm, const float2* __restrict__ rec, int tid, int n
 // twiddle-record table of a tile: [pass A: MA*RA float2][pass B: MB*RB float2]
 template <class T>
 struct TwiddleLayout {
-  static constexpr int A_OFF = 0, B_OFF = T::MA * T::RA, TOTAL = T::MA * T::RA + T::MB * T::RB;
+  static constexpr int RAE = (T::RA + 1) / 2 * 2, RBE = (T::RB + 1) / 2 * 2;      // factor pairs: odd radices are padded
+  static constexpr int A_OFF = 0, B_OFF = T::MA * RAE, TOTAL = T::MA * RAE + T::MB * RBE;
 };
 
 // Whole transforms on a tile resident in shared memory.

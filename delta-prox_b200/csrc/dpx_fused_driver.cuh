@@ -32,40 +32,45 @@ DPX_TILE_FOR(320, 10, 8, 4)        // 5 * 2^k sides: radix-10 / radix-20 first p
 DPX_TILE_FOR(640, 10, 8, 8)
 DPX_TILE_FOR(1280, 20, 8, 8)
 DPX_TILE_FOR(2560, 20, 16, 8)
+DPX_TILE_FOR(960, 12, 10, 8)       // widths and heights of the camera formats: 1920 x 1080, 1280 x 720, 2560 x 1440, 1600 x 1200,
+DPX_TILE_FOR(1600, 20, 10, 8)      // 1920 x 1200, 3840 x 2160.  Radices 10 / 12 in the second pass; 9 and 15 (odd) only in the
+DPX_TILE_FOR(1920, 20, 12, 8)      // column transform: a row transform additionally needs (W / RC) % 4 == 0 (k_rowz)
+DPX_TILE_FOR(3840, 20, 12, 16)
+DPX_TILE_FOR(720, 10, 9, 8)        // column lengths only
+DPX_TILE_FOR(1080, 15, 9, 8)
+DPX_TILE_FOR(1200, 15, 10, 8)
+DPX_TILE_FOR(1440, 15, 12, 8)
+DPX_TILE_FOR(2160, 15, 9, 16)
 #undef DPX_TILE_FOR
 
-inline bool size_supported(int n) {
-  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 192 || n == 384 ||
-         n == 768 || n == 1536 || n == 3072 || n == 320 || n == 640 || n == 1280 || n == 2560;
+// sizes usable as a row length (W) and as a column length (H) / as a column length only
+#ifdef DPX_EXP_SIZES                                   // experiment builds: only the headline size (compile time)
+#define DPX_W_SIZES(X) X(2048)
+#define DPX_H_ONLY_SIZES(X)
+#else
+#define DPX_W_SIZES(X)                                                                                                          \
+  X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(192) X(384) X(768) X(1536) X(3072) X(320) X(640) X(1280) X(2560) X(960) \
+  X(1600) X(1920) X(3840)
+#define DPX_H_ONLY_SIZES(X) X(720) X(1080) X(1200) X(1440) X(2160)
+#endif
+#define DPX_CASE_TRUE(N) case N:
+#define DPX_CASE_CALL(N) case N: f(std::integral_constant<int, N>{}); return true;
+
+inline bool size_supported(int n) {                    // as a row length (and column length)
+  switch (n) { DPX_W_SIZES(DPX_CASE_TRUE) return true; default: return false; }
+}
+inline bool size_supported_h(int n) {                  // as a column length
+  switch (n) { DPX_W_SIZES(DPX_CASE_TRUE) DPX_H_ONLY_SIZES(DPX_CASE_TRUE) return true; default: return false; }
 }
 
 // calls f(std::integral_constant<int, N>{}) for the matching supported N; returns false if unsupported
 template <class F>
 inline bool dispatch_size(int n, F&& f) {
-  switch (n) {
-#ifdef DPX_EXP_SIZES                                   // experiment builds: only the headline size (compile time)
-    case 2048: f(std::integral_constant<int, 2048>{}); return true;
-    default: return false;
-#else
-    case 64: f(std::integral_constant<int, 64>{}); return true;
-    case 128: f(std::integral_constant<int, 128>{}); return true;
-    case 256: f(std::integral_constant<int, 256>{}); return true;
-    case 512: f(std::integral_constant<int, 512>{}); return true;
-    case 1024: f(std::integral_constant<int, 1024>{}); return true;
-    case 2048: f(std::integral_constant<int, 2048>{}); return true;
-    case 4096: f(std::integral_constant<int, 4096>{}); return true;
-    case 192: f(std::integral_constant<int, 192>{}); return true;
-    case 384: f(std::integral_constant<int, 384>{}); return true;
-    case 768: f(std::integral_constant<int, 768>{}); return true;
-    case 1536: f(std::integral_constant<int, 1536>{}); return true;
-    case 3072: f(std::integral_constant<int, 3072>{}); return true;
-    case 320: f(std::integral_constant<int, 320>{}); return true;
-    case 640: f(std::integral_constant<int, 640>{}); return true;
-    case 1280: f(std::integral_constant<int, 1280>{}); return true;
-    case 2560: f(std::integral_constant<int, 2560>{}); return true;
-    default: return false;
-#endif
-  }
+  switch (n) { DPX_W_SIZES(DPX_CASE_CALL) default: return false; }
+}
+template <class F>
+inline bool dispatch_size_h(int n, F&& f) {
+  switch (n) { DPX_W_SIZES(DPX_CASE_CALL) DPX_H_ONLY_SIZES(DPX_CASE_CALL) default: return false; }
 }
 
 inline size_t s_elems(int P, int H, int W) { return (size_t)P * ((W / 2) / CG + 1) * H * CG; }     // float2 count of S
@@ -91,7 +96,7 @@ inline std::vector<float2> make_twiddle_records() {
 }
 inline std::vector<float2> twiddle_records_for(int n) {
   std::vector<float2> out;
-  dispatch_size(n, [&](auto nn) { out = make_twiddle_records<typename TileFor<decltype(nn)::value, 1>::type>(); });
+  dispatch_size_h(n, [&](auto nn) { out = make_twiddle_records<typename TileFor<decltype(nn)::value, 1>::type>(); });
   return out;
 }
 
@@ -118,7 +123,7 @@ struct Driver {
   void pack_constants(int P, int Cd, int H, int W, const float2* fb_std, float2* fbp, const float* dq_std, float* dqp,
                       int C = 0, const float* dpsi_std = nullptr, float* dpsp = nullptr) {
     const int G = (W / 2) / CG;
-    dispatch_size(H, [&](auto hn) {
+    dispatch_size_h(H, [&](auto hn) {
       using TH = typename TileFor<decltype(hn)::value, CG>::type;
       if (fb_std) be.template pack<TH, float2>(fb_std, fbp, P, H, W, G, make_float2(0.f, 0.f));
       if (dq_std) be.template pack<TH, float>(dq_std, dqp, Cd, H, W, G, 0.f);
@@ -133,7 +138,7 @@ struct Driver {
     if (n_iters <= 0) return;
     const int P = B * C, G = (W / 2) / CG;
     dispatch_size(W, [&](auto wn) {
-      dispatch_size(H, [&](auto hn) {
+      dispatch_size_h(H, [&](auto hn) {
         using TW = typename TileFor<decltype(wn)::value, ROWS / 2>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         RowParams rp;
@@ -181,7 +186,7 @@ struct Driver {
   void pack_constants_pairs(int B, int C, int H, int W, const float2* fb_std, float2* fbz, const float* dq_std, float* dqz,
                             const float* dpsi_std = nullptr, float* dpsz = nullptr) {
     dispatch_size(W, [&](auto wn) {
-      dispatch_size(H, [&](auto hn) {
+      dispatch_size_h(H, [&](auto hn) {
         using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         const PackGeom q{H, W, TH::RA, TH::RB, TH::RC, TW::RA, TW::RB, TW::RC};
@@ -198,7 +203,7 @@ struct Driver {
     if (n_iters <= 0) return;
     const int PP = (B / 2) * C, G = W / CG;
     dispatch_size(W, [&](auto wn) {
-      dispatch_size(H, [&](auto hn) {
+      dispatch_size_h(H, [&](auto hn) {
         using TW = typename TileFor<decltype(wn)::value, ROWS>::type;
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         RowParams rp;
@@ -240,7 +245,7 @@ struct Driver {
                const float2* tw_h, const float2* tw_w, const float* dpsp = nullptr) {
     const int P = B * C;
     dispatch_size(W, [&](auto wn) {
-      dispatch_size(H, [&](auto hn) {
+      dispatch_size_h(H, [&](auto hn) {
         using TH = typename TileFor<decltype(hn)::value, CG>::type;
         RowParams rp;
         rp.C = C; rp.H = H; rp.S = S; rp.psi = psi; rp.hqs = hqs; rp.it = it; rp.x = x; rp.tw = tw_w;

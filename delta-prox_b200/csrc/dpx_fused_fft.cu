@@ -378,8 +378,9 @@ class FusedEngine final : public FftEngine {
 
 int make_fused_engine(const Geom& g, FftEngine** out) {
   *out = nullptr;
-  if (!fused::size_supported(g.H) || !fused::size_supported(g.W)) {
-    set_error("fused FFT engine: shape [%d x %d] not supported (sides 2^k in 64..4096, 3*2^k in 192..3072 or 5*2^k in 320..2560)", g.H, g.W);
+  if (!fused::size_supported_h(g.H) || !fused::size_supported(g.W)) {
+    set_error("fused FFT engine: shape [%d x %d] not supported (either side 2^k in 64..4096, 3*2^k in 192..3072, 5*2^k in 320..2560, 960, 1600, "
+              "1920, 3840; height also 720, 1080, 1200, 1440, 2160)", g.H, g.W);
     return DPX_ERR_INVALID;
   }
   FusedEngine* e = new (std::nothrow) FusedEngine();

@@ -58,6 +58,7 @@ struct EmuBackend {
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int emu_fused_supported(int n) { return size_supported(n) ? 1 : 0; }
+extern "C" __attribute__((visibility("default"))) int emu_fused_supported_h(int n) { return size_supported_h(n) ? 1 : 0; }
 
 // x, v[i], u[i]: [B,C,H,W] fp32 (updated in place); fb_std: complex64 [B*C,H,W/2+1]; dq_std: [Cd,H,W/2+1], Cd = C or B*C
 // psi_*: per-term arrays; lam: [n_psi][T]; rho: [T]; offsets off[i] may be null
@@ -65,7 +66,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_run(int B, int C
                              const float* beta, float* x, float** v, float** u, const float** off, const float* fb_std,
                              const float* dq_std, int dq_batch, float wid, float eps, const float* rho, const float* lam, int T,
                              int hqs) {
-  if (!size_supported(H) || !size_supported(W)) return 1;
+  if (!size_supported_h(H) || !size_supported(W)) return 1;
   const int P = B * C, Cd = dq_batch > 1 ? P : C;
   std::vector<float2> S(s_elems(P, H, W), make_float2(0.f, 0.f));
   std::vector<float2> fbp(packed_elems(P, H, W));

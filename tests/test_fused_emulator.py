@@ -70,7 +70,9 @@ def rel(a, b):
 
 @pytest.mark.parametrize("H,W,method", [(64, 64, "admm"), (64, 128, "admm"), (128, 64, "hqs"), (256, 64, "admm"),
                                         (192, 64, "admm"), (64, 384, "hqs"),           # 3 * 2^k sides: radix-12 first pass
-                                        (320, 64, "admm"), (64, 640, "hqs")])          # 5 * 2^k sides: radix-10 first pass
+                                        (320, 64, "admm"), (64, 640, "hqs"),           # 5 * 2^k sides: radix-10 first pass
+                                        (720, 64, "admm"), (1080, 64, "hqs"),          # camera heights: 10*9*8, 15*9*8 (odd radices)
+                                        (64, 960, "admm")])                            # 12*10*8 as a row length
 def test_fused_kernels_match_oracle(emu, H, W, method):
     g = torch.Generator().manual_seed(H + W)
     B, Cc, T = 2, 1 if H > 64 else 3, 4          # the reference's OTF builder only handles C in {1, 3}
@@ -89,7 +91,9 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
 
 
 @pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm"),      # H = 1024: k_col_tma
-                                        (192, 192, "admm"), (64, 1280, "hqs")])                  # 1280: radix-20 first pass
+                                        (192, 192, "admm"), (64, 1280, "hqs"),                   # 1280: radix-20 first pass
+                                        (64, 1920, "hqs"), (2160, 64, "admm")])                  # 20*12*8 rows, 15*9*16 columns
+                                        # (1200, 1440, 1600 and 3840 points: tests/test_parity_gpu.py, against the cuFFT engine)
 def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     """One psi term: the in-place register path of k_row (template SINGLE)."""
     g = torch.Generator().manual_seed(H * 3 + W)

@@ -24,6 +24,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--vars", default="-")
     ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--height", type=int, default=0, help="non-square problems: rows (default --size)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--backend", type=int, default=2, help="2 = fused engine, 1 = cuFFT engine")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--reps", type=int, default=6)
@@ -34,6 +37,7 @@ def main():
 
     dev = torch.device("cuda", 0)
     S = args.size
+    Hh, Ww = args.height or S, args.width or S
     psf = psf_gaussian(15, 5.0)
 
     def setenv(spec):
@@ -49,8 +53,8 @@ def main():
         x = dp.Variable()
         y = dp.Placeholder()
         op = dp.conv(x, psf)
-        solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method=args.method, device=dev, fft_backend=2)
-        img, noise = make_measurements(B, 3, S, S, seed=99, device=dev)
+        solver = dp.compile(dp.sum_squares(dp.conv(x, psf) - y) + dp.nonneg(x), method=args.method, device=dev, fft_backend=args.backend)
+        img, noise = make_measurements(B, 3, Hh, Ww, seed=99, device=dev)
         b = op.to(dev).forward(img) + noise
         y.value = b
         return solver, b
@@ -87,7 +91,7 @@ def main():
             times.sort()
             out["us_per_iteration_best"] = times[0]
             out["us_per_iteration_median"] = times[len(times) // 2]
-            nbytes = (16.0 if args.method == "hqs" else 24.0) * args.batch * 3 * S * S
+            nbytes = (16.0 if args.method == "hqs" else 24.0) * args.batch * 3 * Hh * Ww
             out["frac_median"] = nbytes / (out["us_per_iteration_median"] * 1e-6) / 1e9 / 6534.1
             del solver, b, state
             torch.cuda.empty_cache()
