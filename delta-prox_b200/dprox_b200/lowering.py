@@ -465,6 +465,14 @@ class GenericEngine(_EngineBase):
         self.cfg = linear_solve_config
         self.plan = None
         self.ktb = None
+        self._step, self._cg_rho, self._cg_cache = 0, None, {}
+        self._has_blackbox = False
+        for t in spec.psi + spec.quad:
+            stack = [t.fn.linop] if t.fn.linop is not None else []
+            while stack:
+                n = stack.pop()
+                self._has_blackbox = self._has_blackbox or type(n).__name__ == "BlackBox"
+                stack += list(n.input_nodes)
         if spec.xupdate in ("freq", "spatial", "scalar"):
             B, Cc, H, W = self.shape4
             d = cabi.ProblemDesc()
@@ -545,6 +553,19 @@ class GenericEngine(_EngineBase):
             return ops.xsolve(self.plan, t.contiguous(), rt, rs, self.ktb)
         # CG on the normal equations (solve_cg, sum_square.py:158-197)
         rhs = self.ktb if t is None else (ops.lincomb(t, rho) if self.ktb is None else ops.lincomb(self.ktb, None, t, rho))
+        # The CG step is captured as a CUDA graph on the first solve and replayed afterwards (linalg._capture): everything the
+        # normal operator reads must therefore live in storage that persists between solves -- rho is copied into a buffer the
+        # engine owns.  A BlackBox receives the iteration index as a Python argument (linop/blackbox.py:38-41), which a graph
+        # would freeze: trees with BlackBox nodes get one graph per iteration index.
+        cache = None if torch.is_grad_enabled() else self._cg_cache      # replay only outside autograd (backward re-runs KtK later)
+        if cache is not None:
+            if self._cg_rho is None or self._cg_rho.shape != rho.shape:
+                self._cg_rho = rho.clone()
+                cache.clear()
+            else:
+                self._cg_rho.copy_(rho)
+            rho = self._cg_rho
+        step_key = self._step if self._has_blackbox else None
 
         def KtK(x):
             out = None
@@ -559,7 +580,7 @@ class GenericEngine(_EngineBase):
                 out = ops.lincomb(acc, rho) if out is None else ops.lincomb(out, None, acc, rho)
             return out
 
-        return linear_solve(KtK, rhs, self.cfg)
+        return linear_solve(KtK, rhs, self.cfg, cache=cache, cache_key=step_key)
 
     # state + one iteration ----------------------------------------------------------------------------
     def initialize(self, x0):
@@ -582,6 +603,7 @@ class GenericEngine(_EngineBase):
         spec, m = self.spec, self.spec.method
         for t in spec.psi + spec.quad:
             _set_step(t.fn, it)
+        self._step = it
         if m in ("admm", "ladmm"):
             x, v, u = state
             if m == "admm":

@@ -471,3 +471,30 @@ def test_split_precision_ffdnet_meets_the_fp32_bar(dp):
     ours, torch32 = rel(gx, x64.grad), rel(g32x, x64.grad)
     assert ours < 2 * torch32 + 1e-5, (ours, torch32)
     assert rel(gs, s64.grad) < 2 * rel(g32s, s64.grad) + 1e-5, (rel(gs, s64.grad), rel(g32s, s64.grad))
+
+
+# ---- CG inner solve as a replayed CUDA graph (launch-bound at the reference's problem sizes) ---------------------------------
+
+@pytest.mark.parametrize("solver", ["cg", "pcg"])
+def test_cg_graph_replay_matches_eager_steps(dp, solver, monkeypatch):
+    """The generic engine captures one CG step on the first solve and replays it afterwards (linalg._capture).  Same iterates
+    as the eagerly stepped loop: reference golden on the first solve() (capture) and on the second (pure replay), with a
+    per-iteration rho schedule (rho lives in a buffer the graph reads) and an early-converging tolerance (device-side gate)."""
+    g = load("admm_cg_mosaic_conv" if solver == "cg" else "admm_pcg_mosaic_conv")
+    x = dp.Variable()
+    b = T(g["b"])
+    cfg = dp.LinearSolveConfig(rtol=1e-6, max_iters=int(g["cg_iters"]), solver_type=solver)
+    s = dp.compile(dp.sum_squares(dp.mosaic(dp.conv(x, g["psf"])) - b) + dp.nonneg(x), method="admm", device="cuda", linear_solve_config=cfg)
+    for _ in range(2):
+        st = s.solve(x0=b, rhos=float(g["rho"]), lams=0.02, max_iter=int(g["T"]), return_full_states=True)
+        check_state(st, g, tol_x=2e-5, tol_aux=1e-4)
+    # schedules that change per iteration, loose tolerance (the gate freezes the iterate early): replay == eager
+    rhos = torch.tensor([0.4, 0.9, 1.7, 0.6])
+    cfg2 = dp.LinearSolveConfig(rtol=1e-3, max_iters=40, solver_type=solver)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DPX_CG_GRAPH", mode)
+        s2 = dp.compile(dp.sum_squares(dp.mosaic(dp.conv(x, g["psf"])) - b) + dp.nonneg(x), method="admm", device="cuda", linear_solve_config=cfg2)
+        s2.solve(x0=b, rhos=rhos, lams=0.02, max_iter=4)
+        outs[mode] = s2.solve(x0=b, rhos=rhos.flip(0), lams=0.02, max_iter=4)       # second call: replay, different rho per step
+    assert rel(outs["1"], outs["0"]) < 2e-5, rel(outs["1"], outs["0"])
