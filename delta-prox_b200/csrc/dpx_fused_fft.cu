@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "dpx_fft.cuh"
-#include "dpx_fused_driver.cuh"
+#include "dpx_fused_launch.cuh"
 
 namespace dpx {
 
@@ -26,42 +26,29 @@ struct CudaBackend {
   cudaStream_t s;
   int rc = DPX_OK;
 
-  template <class K>
-  void prep(K kernel, size_t smem) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess && rc == DPX_OK) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); rc = DPX_ERR_CUDA; }
-    }
-  }
-  void after() {
+  void done(cudaError_t e) {
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess && rc == DPX_OK) { set_error("fused kernel launch failed: %s", cudaGetErrorString(e)); rc = DPX_ERR_CUDA; }
   }
+  void after() { done(cudaGetLastError()); }
   template <class TW, int MODE, bool SINGLE>
   void row(dim3 grid, size_t smem, const RowParams& p) {
     if (rc) return;
-    prep(k_row<TW, MODE, SINGLE>, smem);
-    k_row<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
-    after();
+    done(launch::row<TW, MODE, SINGLE>(grid, smem, p, s));
   }
   int n_persist = 0;                                  // CTAs of the persistent row kernel (2 per SM); 0 disables it
   int persistent_ctas() const { return n_persist; }
   template <class TW>
   void row_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
-    prep(k_row_mid_persist<TW>, smem);
-    k_row_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
-    after();
+    done(launch::row_persist<TW>(grid, smem, p, n_tiles, s));
   }
   int n_sm = 0;                                       // SMs for the persistent TMA column kernel; 0 disables it
   int sm_count() const { return n_sm; }
   template <class TH>
   void col_tma(dim3 grid, size_t smem, const ColParams& p, int n_tiles, int nb) {
     if (rc) return;
-    prep(k_col_tma<TH>, smem);
-    k_col_tma<TH><<<grid, ColTmaCfg<TH>::NT, smem, s>>>(p, n_tiles, nb);
-    after();
+    done(launch::col_tma<TH>(grid, smem, p, n_tiles, nb, s));
   }
   static constexpr int kRowCtrs = 4096;                 // dynamic-tile counters: one per persistent row launch of a call (zeroed per call)
   int* row_ctr = nullptr;
@@ -72,26 +59,20 @@ struct CudaBackend {
     if (rc) return;
     ColParams q = p;
     q.trace = trace_col;
-    prep(k_col<TH>, smem);
-    k_col<TH><<<grid, kThreads, smem, s>>>(q);
-    after();
+    done(launch::col<TH>(grid, smem, q, s));
   }
   template <class TW, int MODE, bool SINGLE>
   void rowz(dim3 grid, size_t smem, const RowParams& p) {
     if (rc) return;
-    prep(k_rowz<TW, MODE, SINGLE>, smem);
-    k_rowz<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
-    after();
+    done(launch::rowz<TW, MODE, SINGLE>(grid, smem, p, s));
   }
   template <class TW>
   void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
-    prep(k_rowz_mid_persist<TW>, smem);
     RowParams q = p;
     q.trace = trace_row;
     if (row_ctr && row_dyn) { q.ctr = row_ctr + (row_ctr_next++ % kRowCtrs); }
-    k_rowz_mid_persist<TW><<<grid, kThreads, smem, s>>>(q, n_tiles);
-    after();
+    done(launch::rowz_persist<TW>(grid, smem, q, n_tiles, s));
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, const PackGeom& q) {
     if (rc) return;
@@ -108,9 +89,7 @@ struct CudaBackend {
   template <class TH, typename V>
   void pack(const V* src, V* dst, int planes, int H, int W, int G, V zero) {
     if (rc) return;
-    const size_t total = (size_t)planes * (G + 1) * H * CG;
-    k_pack<TH, V><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, planes, H, W, G, zero);
-    after();
+    done(launch::pack<TH, V>(src, dst, planes, H, W, G, zero, s));
   }
 };
 

@@ -1227,7 +1227,7 @@ DPX_HD int freq_of_pos_rt(int p, int N, int RA, int RB) {   // fft::Tile::freq_o
   const int MA = N / RA, MB = MA / RB;
   return p / MA + RA * ((p % MA) / MB) + RA * RB * (p % MB);
 }
-__global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, PackGeom q) {
+static __global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, PackGeom q) {
   const int H = q.H, W = q.W, RC = q.hRC;
   const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
   const size_t total = (size_t)pairs * G * H * CG;
@@ -1255,7 +1255,7 @@ __global__ void k_packz_fb(const float2* __restrict__ src, float2* __restrict__ 
   }
   dst[i] = make_float2(fa.x - fb.y, fa.y + fb.x);
 }
-__global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, PackGeom q) {
+static __global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, PackGeom q) {
   const int H = q.H, W = q.W, RC = q.hRC;
   const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
   const size_t total = (size_t)C * G * H * CG;

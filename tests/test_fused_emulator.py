@@ -71,7 +71,7 @@ def rel(a, b):
 @pytest.mark.parametrize("H,W,method", [(64, 64, "admm"), (64, 128, "admm"), (128, 64, "hqs"), (256, 64, "admm"),
                                         (192, 64, "admm"), (64, 384, "hqs"),           # 3 * 2^k sides: radix-12 first pass
                                         (320, 64, "admm"), (64, 640, "hqs"),           # 5 * 2^k sides: radix-10 first pass
-                                        (720, 64, "admm"), (1080, 64, "hqs"),          # camera heights: 10*9*8, 15*9*8 (odd radices)
+                                        (1080, 64, "hqs"),                             # camera height 15*9*8: radix-15 and radix-9 passes
                                         (64, 960, "admm")])                            # 12*10*8 as a row length
 def test_fused_kernels_match_oracle(emu, H, W, method):
     g = torch.Generator().manual_seed(H + W)
@@ -92,8 +92,8 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
 
 @pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm"),      # H = 1024: k_col_tma
                                         (192, 192, "admm"), (64, 1280, "hqs"),                   # 1280: radix-20 first pass
-                                        (64, 1920, "hqs"), (2160, 64, "admm")])                  # 20*12*8 rows, 15*9*16 columns
-                                        # (1200, 1440, 1600 and 3840 points: tests/test_parity_gpu.py, against the cuFFT engine)
+                                        (64, 1920, "hqs")])                                      # 20*12*8 as a row length
+                                        # (720, 1200, 1440, 1600, 2160, 3840 points: tests/test_parity_gpu.py, against the cuFFT engine)
 def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     """One psi term: the in-place register path of k_row (template SINGLE)."""
     g = torch.Generator().manual_seed(H * 3 + W)
