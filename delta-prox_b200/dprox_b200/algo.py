@@ -272,7 +272,12 @@ class Algorithm(nn.Module):
         return self.engine(x0, diff).initialize(x0)
 
     def iters(self, state, rhos, lams, max_iter, pbar=False, callback=None, stop: Optional[ResidualStop] = None, _diff=None):
-        """Algorithm.iters (base.py:128-156)."""
+        """Algorithm.iters (base.py:128-156).
+
+        State ownership differs from the reference on the native engine: x, v, u are updated IN PLACE (the reference returns
+        fresh tensors every iteration, admm.py:49-59), and x / v are only materialised by the last iteration of a native call.
+        The `state` a `callback` receives therefore aliases buffers that the next iteration overwrites -- clone what must
+        outlive the call."""
         diff = self._wants_grad(state, rhos, lams) if _diff is None else _diff
         eng = self.engine(state[0], diff)
         if _isscalar(lams) or not isinstance(lams, dict):
