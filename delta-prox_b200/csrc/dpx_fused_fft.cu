@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "dpx_fft.cuh"
+#include <cuda.h>
+
 #include "dpx_fused_launch.cuh"
 
 namespace dpx {
@@ -54,12 +56,15 @@ struct CudaBackend {
   int* row_ctr = nullptr;
   int row_ctr_next = 0, row_dyn = 1;
   unsigned long long *trace_col = nullptr, *trace_row = nullptr;
+  const void* row_smap = nullptr;                     // tensor map of S for the persistent pair kernel's staging (DPX_ROW_TMA=0: LDGSTS)
+  int col_bulk = 0;                                   // column tile staged by TMA bulk copies (DPX_COL_BULK=0: LDGSTS)
   template <class TH>
   void col(dim3 grid, size_t smem, const ColParams& p) {
     if (rc) return;
     ColParams q = p;
     q.trace = trace_col;
-    done(launch::col<TH>(grid, smem, q, s));
+    q.bulk = col_bulk;
+    done(launch::col<TH>(grid, smem + (col_bulk ? 16 : 0), q, s));
   }
   template <class TW, int MODE, bool SINGLE>
   void rowz(dim3 grid, size_t smem, const RowParams& p) {
@@ -71,6 +76,7 @@ struct CudaBackend {
     if (rc) return;
     RowParams q = p;
     q.trace = trace_row;
+    q.smap = row_smap;
     if (row_ctr && row_dyn) { q.ctr = row_ctr + (row_ctr_next++ % kRowCtrs); }
     done(launch::rowz_persist<TW>(grid, smem, q, n_tiles, s));
   }
@@ -116,6 +122,10 @@ class FusedEngine final : public FftEngine {
       const char* pe = getenv("DPX_PAIRS");                   // 0 disables the plane-pair engine (for A/B runs)
       pairs_enabled_ = !(pe && pe[0] == '0');
       DPX_CUDA(cudaMalloc(&row_ctr_, sizeof(int) * CudaBackend::kRowCtrs));
+      const char* be_ = getenv("DPX_COL_BULK");
+      col_bulk_ = (be_ && be_[0] == '0') ? 0 : 1;             // 0 = LDGSTS staging of the column tile (A/B runs)
+      const char* te2 = getenv("DPX_ROW_TMA");
+      row_tma_ = (te2 && te2[0] == '0') ? 0 : 1;             // 0 = LDGSTS staging of the spectrum rows (A/B runs)
       const char* de = getenv("DPX_ROW_DYN");                 // 0 = static round-robin tiles in the persistent pair kernel
       row_dyn_ = !(de && de[0] == '0');
       trace_path_ = getenv("DPX_TRACE");
@@ -146,7 +156,7 @@ class FusedEngine final : public FftEngine {
     dump_trace();
     if (inner_) inner_->destroy();
     cudaFree(S_); cudaFree(fbp_); cudaFree(dqp_); cudaFree(dpsp_); cudaFree(S1_); cudaFree(fbp1_); cudaFree(dqp1_);
-    cudaFree(tw_h_); cudaFree(tw_w_); cudaFree(row_ctr_);
+    cudaFree(tw_h_); cudaFree(tw_w_); cudaFree(row_ctr_); cudaFree(smap_dev_);
     if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_join_); }
     delete this;
   }
@@ -267,12 +277,17 @@ class FusedEngine final : public FftEngine {
     be.n_persist = persist_ctas_;
     be.n_sm = col_tma_sms_;
     be.trace_col = trace_col_; be.trace_row = trace_row_;
-    be.row_ctr = row_ctr_; be.row_dyn = row_dyn_ && n_iters <= CudaBackend::kRowCtrs;   // one zeroed counter per launch
+    be.col_bulk = col_bulk_; be.row_ctr = row_ctr_;
+    be.row_smap = nullptr; be.row_dyn = row_dyn_ && n_iters <= CudaBackend::kRowCtrs;   // one zeroed counter per launch
     if (row_ctr_ && be.row_dyn) DPX_CUDA(cudaMemsetAsync(row_ctr_, 0, sizeof(int) * std::min(n_iters, (int)CudaBackend::kRowCtrs), s));
     Mode mode = PLANES;
     int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
     Driver<CudaBackend> drv(be);
+    if (row_tma_ && mode != PLANES) {
+      if (ensure_smap(mode == PAIRS ? (g.B / 2) * g.C : (g.P - g.P % 2) / 2, s) == DPX_OK) be.row_smap = smap_dev_;
+      else row_tma_ = 0;                                  // driver without cuTensorMapEncodeTiled: LDGSTS staging
+    }
     if (mode == PAIRS)
       drv.iterate_pairs(g.B, g.C, g.H, g.W, S_, psi, hqs ? 1 : 0, x, fbp_, dqp_, wid, eps, rho, it0, n_iters, tw_h_, tw_w_);
     else if (mode == PLANES)
@@ -320,6 +335,34 @@ class FusedEngine final : public FftEngine {
   }
 
  private:
+  // tensor map of the pair spectrum S[pp][g][h][c] as {H*CG*2 floats (one column group), G, pairs}; box {ZR*CG*2 floats = 64 B, min(G,256), 1}
+  int ensure_smap(int pairs, cudaStream_t s) {
+    if (smap_dev_ && smap_pairs_ == pairs) return DPX_OK;
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return DPX_ERR_CUDA;
+    }
+    const int G = g_.W / fused::CG;
+    const cuuint64_t dims[3] = {(cuuint64_t)g_.H * fused::CG * 2, (cuuint64_t)G, (cuuint64_t)pairs};
+    const cuuint64_t strides[2] = {(cuuint64_t)g_.H * fused::CG * 8, (cuuint64_t)G * g_.H * fused::CG * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)(fused::ZR * fused::CG * 2), (cuuint32_t)fused::rowz_tma_box(G), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    alignas(64) CUtensorMap m;
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(fp)(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, S_, dims, strides, box, estr,
+                                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(S) failed with CUresult %d", (int)r); return DPX_ERR_CUDA; }
+    if (!smap_dev_) DPX_CUDA(cudaMalloc(&smap_dev_, 128));
+    DPX_CUDA(cudaMemcpyAsync(smap_dev_, &m, sizeof(m), cudaMemcpyHostToDevice, s));
+    DPX_CUDA(cudaStreamSynchronize(s));               // `m` is a stack object (cold path: once per plan)
+    smap_pairs_ = pairs;
+    return DPX_OK;
+  }
   static int upload_twiddles(int n, float2** out) {
     const std::vector<float2> t = twiddle_records_for(n);
     DPX_CUDA(cudaMalloc(out, t.size() * sizeof(float2)));
@@ -335,7 +378,9 @@ class FusedEngine final : public FftEngine {
   int persist_ctas_ = 0;
   int col_tma_sms_ = 0;
   int* row_ctr_ = nullptr;
-  int row_dyn_ = 1;
+  int row_dyn_ = 1, col_bulk_ = 0, row_tma_ = 0;
+  void* smap_dev_ = nullptr;
+  int smap_pairs_ = 0;
   static constexpr size_t kTraceRecs = 16384;          // >= CTAs of k_col / tiles of the row kernel at the traced batch
   const char* trace_path_ = nullptr;
   unsigned long long *trace_col_ = nullptr, *trace_row_ = nullptr;

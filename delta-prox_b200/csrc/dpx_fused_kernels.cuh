@@ -24,7 +24,7 @@
 #include "dpx_types.cuh"
 
 #ifndef DPX_EMU
-#define DPX_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type* name = reinterpret_cast<type*>(name##_raw)
+#define DPX_DYN_SMEM(type, name) extern __shared__ __align__(128) unsigned char name##_raw[]; type* name = reinterpret_cast<type*>(name##_raw)
 #endif
 
 namespace dpx {
@@ -46,6 +46,7 @@ struct RowParams {
   int it;                        // schedule column for lam
   float* x;                      // ROW_LAST: receives x
   const float2* tw;              // twiddle records of the W-tile (fft::TwiddleLayout)
+  const void* smap = nullptr;    // persistent pair kernel: tensor map of S {H*8 floats, G, pairs} in global memory, or nullptr = LDGSTS staging
   int* ctr = nullptr;            // persistent pair kernel: dynamic tile counter of this launch (zeroed), or nullptr = static round robin
   unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
 };
@@ -64,6 +65,7 @@ struct ColParams {
   RhoRef rho;
   const float2* tw;              // twiddle records of the H-tile
   unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
+  int bulk = 0;                  // staged tile through TMA bulk copies (needs 16 bytes of shared memory behind the tile)
 };
 
 DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
@@ -134,6 +136,7 @@ DPX_HD void bulk_wait_read_all() {}
 DPX_HD void bulk_wait_all() {}
 DPX_HD void fence_async_smem() {}
 DPX_HD void bulk_prefetch_l2(const void*, unsigned) {}
+DPX_HD void tma_load_3d(void*, const void*, mbar_t*, int, int, int) {}
 #else
 // one instruction pulls a whole run into L2 (TMA engine); unlike prefetch.global.L2 it is not dropped under load
 DPX_HD void bulk_prefetch_l2(const void* p, unsigned bytes) {
@@ -169,6 +172,13 @@ DPX_HD void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memo
 DPX_HD void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DPX_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DPX_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// tiled TMA load of one box of a 3-D tensor map that lives in global memory (UTMALDG); completion on `b`
+DPX_HD void tma_load_3d(void* dst, const void* map, mbar_t* b, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(b)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 #endif
 
 template <class TW>
@@ -618,7 +628,17 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
   float2* tile = P.S + ((size_t)p * NG + g) * H * CG;
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
-  if (STAGE) {
+  mbar_t* stage_bar = reinterpret_cast<mbar_t*>(sm + TH::SMEM_FLOAT2);    // (P.bulk) one transaction barrier behind the tile
+  if (STAGE && P.bulk) {
+    // TMA bulk copies: 8 rows x CG columns = 256 contiguous bytes in global memory AND at the padded position (one spare point
+    // follows every 8 points), so the tile arrives through the async proxy -- no LSU wavefronts, no per-thread address stream
+    if (tid == 0) { mbar_init(stage_bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) mbar_expect_tx(stage_bar, H * CG * sizeof(float2));
+    __syncthreads();
+    for (int i = tid; i < H / 8; i += kThreads)
+      bulk_load(sm + TH::pn(8 * i) * CG, tile + (size_t)i * 8 * CG, 8 * CG * sizeof(float2), stage_bar);
+  } else if (STAGE) {
     // 16-byte pieces = columns (0,1) / (2,3) of one row, contiguous both in global memory and at the padded position
     for (int i = tid; i < H * CG / 2; i += kThreads) {
       const int n = i >> 1, c2 = (i & 1) * 2;
@@ -633,7 +653,11 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
 
   // ---- pass A of the forward FFT: in place on the staged tile, or fed straight from global memory ---------------------
   if (STAGE) {
-    cp_async_wait_all();
+    if (P.bulk) {
+      if (DPX_MBAR_ALL_WAIT || tid == 0) mbar_wait(stage_bar, 0);       // one poller; the barrier below publishes the tile
+    } else {
+      cp_async_wait_all();
+    }
     __syncthreads();
     if (tid == 0) trace_stamp(P.trace, rec, 2);
     fft::smem_pass<TH, RA, H, false, true>(sm, twA, tid, kThreads);
@@ -1021,7 +1045,8 @@ struct RowZPersistSmem {
   static constexpr int G = TW::N / CG;
   static constexpr int STS_F2 = G * ZR * CG;                     // staged spectrum rows: [g][r][c]
   static constexpr int RSU = TW::N + 16;                         // staged dual-row stride (floats): rows land in disjoint banks
-  static constexpr size_t BYTES = (TW::SMEM_FLOAT2 + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t) + 16;   // + next-tile slot
+  static constexpr int STS_OFF = (TW::SMEM_FLOAT2 + 15) / 16 * 16;   // float2 offset of the stage: 128-byte aligned (TMA tensor loads land there)
+  static constexpr size_t BYTES = (STS_OFF + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t) + 16;   // + next-tile slot
   // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
   static constexpr int CTAS_PER_SM = (TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2;
 };
@@ -1050,6 +1075,19 @@ DPX_HD void rowz_stage_S(const RowParams& P, const RowZTile& t, float2* stS, int
     cp_async16(reinterpret_cast<char*>(stS + g * (ZR * CG)) + ch * 16, base + (size_t)g * P.H * CG * sizeof(float2) + ch * 16);
   }
 }
+// the same rows through the TMA engine: one tensor-map box {2 rows x CG columns = 64 B, up to 256 column groups} per instruction,
+// landing in the [g][r][c] order of the stage; no LSU wavefronts and no per-thread address stream (one elected thread)
+constexpr int rowz_tma_box(int G) {                 // column groups per TMA box: the largest divisor of G that a box dimension can hold
+  int b = G < 256 ? G : 256;
+  while (G % b) --b;
+  return b;
+}
+template <class TW>
+DPX_HD void rowz_stage_S_tma(const RowParams& P, const RowZTile& t, float2* stS, mbar_t* bar) {
+  constexpr int G = TW::N / CG, BOX = rowz_tma_box(G);
+  mbar_expect_tx(bar, G * ZR * CG * sizeof(float2));
+  for (int g0 = 0; g0 < G; g0 += BOX) tma_load_3d(stS + g0 * (ZR * CG), P.smap, bar, t.h0 * CG * 2, g0, t.pp);
+}
 template <class TW>
 DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar_t* bar, int tid) {
   constexpr int W = TW::N, RSU = RowZPersistSmem<TW>::RSU;
@@ -1068,7 +1106,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   constexpr unsigned U_BYTES = 2 * ZR * W * sizeof(float);
   static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass fall into the same column of different groups");
   DPX_DYN_SMEM(float2, sm);
-  float2* stS = sm + TW::SMEM_FLOAT2;
+  float2* stS = sm + RowZPersistSmem<TW>::STS_OFF;
   float* stU = reinterpret_cast<float*>(stS + RowZPersistSmem<TW>::STS_F2);
   mbar_t* bars = reinterpret_cast<mbar_t*>(stU + 2 * ZR * RSU);    // [1]: dual stage
   const int tid = threadIdx.x;
@@ -1089,7 +1127,8 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   if (tile < n_tiles) {
     if (tid == 0 && !hqs) mbar_expect_tx(bars + 1, U_BYTES);
     __syncthreads();
-    rowz_stage_S<TW>(P, cur, stS, tid);
+    if (P.smap) { if (tid == 0) rowz_stage_S_tma<TW>(P, cur, stS, bars + 0); }
+    else rowz_stage_S<TW>(P, cur, stS, tid);
     if (!hqs) rowz_stage_u<TW>(P, cur, stU, bars + 1, tid);
   }
   cp_async_commit();
@@ -1111,7 +1150,10 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
         *s_next = tile + (int)gridDim.x;
     }
     cp_async_wait_all();
-    if (DPX_MBAR_ALL_WAIT || tid == 0) { if (!hqs) mbar_wait(bars + 1, phase); }   // one poller; the barrier below publishes it
+    if (DPX_MBAR_ALL_WAIT || tid == 0) {                                           // one poller; the barrier below publishes it
+      if (P.smap) mbar_wait(bars + 0, phase);
+      if (!hqs) mbar_wait(bars + 1, phase);
+    }
     __syncthreads();                                   // staged inputs are visible; the tile buffer is free
     next = *s_next;
     const RowZTile nxt = rowz_tile(P, next < n_tiles ? next : tile, tpp, n_tiles);
@@ -1133,7 +1175,10 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     }
     __syncthreads();                                   // stS consumed
     if (tid == 0) trace_stamp(P.trace, tile, 3);
-    if (next < n_tiles) rowz_stage_S<TW>(P, nxt, stS, tid);
+    if (next < n_tiles) {
+      if (P.smap) { if (tid == 0) rowz_stage_S_tma<TW>(P, nxt, stS, bars + 0); }
+      else rowz_stage_S<TW>(P, nxt, stS, tid);
+    }
     cp_async_commit();
     fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
     __syncthreads();
