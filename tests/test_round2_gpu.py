@@ -498,3 +498,21 @@ def test_cg_graph_replay_matches_eager_steps(dp, solver, monkeypatch):
         s2.solve(x0=b, rhos=rhos, lams=0.02, max_iter=4)
         outs[mode] = s2.solve(x0=b, rhos=rhos.flip(0), lams=0.02, max_iter=4)       # second call: replay, different rho per step
     assert rel(outs["1"], outs["0"]) < 2e-5, rel(outs["1"], outs["0"])
+
+
+def test_cfg4_size_hqs_vs_oracle(dp):
+    """BASELINE config 4 per GPU at its stated size: HQS deconv + nonneg on [2,3,1024,1024] (plane-pair engine, TMA-staged rows,
+    radix-16*8*8 tiles), 24 iterations, against the oracle; x and v."""
+    g = torch.Generator().manual_seed(41)
+    B, T_ = 2, 24
+    img = torch.rand(B, 3, 1024, 1024, generator=g) - 0.2
+    psf = orc.point_spread_function(15, 5)
+    b = orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, 3, 1024, 1024, generator=g)
+    data, o1 = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=b), orc.Term("nonneg")
+    want = orc.Solver([data, o1], "hqs").solve(b.clone(), rhos=1.0, lams=0.02, max_iter=T_, return_full_states=True)
+    x = dp.Variable()
+    bd = b.cuda()
+    s = dp.compile(dp.sum_squares(dp.conv(x, psf) - bd) + dp.nonneg(x), method="hqs", device="cuda")
+    st = s.solve(x0=bd, rhos=1.0, lams=0.02, max_iter=T_, return_full_states=True)
+    assert rel(st[0], want[0]) < TOL_X, rel(st[0], want[0])
+    assert rel(st[1][0], want[1][0]) < TOL_AUX

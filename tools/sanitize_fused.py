@@ -13,7 +13,9 @@ import torch  # noqa: E402
 import dprox_b200 as dp  # noqa: E402
 
 psf = np.ones((5, 5, 1), "float32") / 25.0
-for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64, "hqs")):
+# round 2: (2, 2048, 64) takes the TMA-staged column tile (bulk copies + transaction barrier), every pair case the tensor-map
+# staging of the spectrum rows and the dynamic tile counter; (2, 1080, 64): radix-15 / radix-9 column passes
+for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64, "hqs"), (2, 2048, 64, "admm"), (2, 1080, 64, "admm")):
     g = torch.Generator(device="cuda").manual_seed(B + H)
     b = torch.rand(B, 3, H, W, device="cuda", generator=g) - 0.3
     x = dp.Variable()
@@ -21,3 +23,13 @@ for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64
     out = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=4)
     torch.cuda.synchronize()
     print(B, H, W, method, float(out.abs().mean()))
+
+# fp32-class FFDNet: fp16-pair split convolution (tcgen05, two TMEM accumulators), forward + data gradient at a ragged size
+from dprox_b200.denoisers import FFDNetColorDenoiser  # noqa: E402
+
+den = FFDNetColorDenoiser(seed=4).cuda().requires_grad_(False)
+xx = torch.rand(1, 3, 37, 70, device="cuda").requires_grad_(True)
+y = den._denoise(xx, torch.tensor([0.05], device="cuda"))
+y.sum().backward()
+torch.cuda.synchronize()
+print("ffdnet split", float(y.abs().mean()), float(xx.grad.abs().mean()))
