@@ -228,13 +228,13 @@ struct Driver {
           cp.rho.it = it0 + k;
           launch_col<TH>(cp, B / 2, G, C);
           rp.it = it0 + k;
-          if (k + 1 < n_iters) {
-            if (psi.n == 1 && be.persistent_ctas() > 0) {
-              using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
-              be.template rowz_persist<TW2>(dim3(be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM), RowZPersistSmem<TW2>::BYTES, rp,
-                                            (H / ZR) * PP);
-            } else row(std::integral_constant<int, ROW_MID>{});
+          if (psi.n == 1 && be.persistent_ctas() > 0) {
+            using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
+            const dim3 pg(be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM);
+            if (k + 1 < n_iters) be.template rowz_persist<TW2, false>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);
+            else be.template rowz_persist<TW2, true>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);   // last: x, v, u out
           }
+          else if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
           else row(std::integral_constant<int, ROW_LAST>{});
         }
       });

@@ -71,19 +71,21 @@ struct CudaBackend {
     if (rc) return;
     done(launch::rowz<TW, MODE, SINGLE>(grid, smem, p, s));
   }
-  template <class TW>
+  template <class TW, bool LAST = false>
   void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
     RowParams q = p;
     q.trace = trace_row;
     q.smap = row_smap;
     if (row_ctr && row_dyn) { q.ctr = row_ctr + (row_ctr_next++ % kRowCtrs); }
-    done(launch::rowz_persist<TW>(grid, smem, q, n_tiles, s));
+    done(launch::rowz_persist<TW, LAST>(grid, smem, q, n_tiles, s));
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, const PackGeom& q) {
     if (rc) return;
-    const size_t total = (size_t)pairs * q.H * q.W;
-    k_packz_fb<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, pairs, C, q);
+    const size_t smem = (size_t)8 * (q.W / 2 + 1) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_packz_fb_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    k_packz_fb_rows<<<dim3(q.hRC / 2, q.H / q.hRC, pairs), 256, smem, s>>>(src, dst, pairs, C, q);
     after();
   }
   void packz_dq(const float* src, float* dst, int C, const PackGeom& q) {

@@ -444,17 +444,19 @@ DPX_HD void row_stage_u(const RowParams& P, int tile, float* stU, int tid) {
 }
 
 // prox + dual + next-rhs for the 2*RA elements a thread holds, bare `_prox` body of kind KIND (see `simple` below)
-template <int KIND, int RA, int MA>
+template <int KIND, int RA, int MA, bool LAST = false>
 DPX_HD void mid_simple(float2 (&a)[RA], const float* ua_s, const float* ub_s, float* __restrict__ up, size_t ea, size_t eb,
-                       int hqs, float lam_eff, float lo, float hi) {
+                       int hqs, float lam_eff, float lo, float hi, float* __restrict__ xp = nullptr, float* __restrict__ vp = nullptr) {
 #pragma unroll
   for (int m = 0; m < RA; ++m) {
     float wa = a[m].x, wb = a[m].y;
+    if (LAST) { xp[ea + m * MA] = wa; xp[eb + m * MA] = wb; }          // last iteration: x leaves the kernel
     if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
     const float va = prox_body(KIND, wa, lam_eff, lo, hi), vb = prox_body(KIND, wb, lam_eff, lo, hi);
     const float ua = wa - va, ub = wb - vb;
     if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
-    a[m] = make_float2(hqs ? va : va - ua, hqs ? vb : vb - ub);
+    if (LAST) { vp[ea + m * MA] = va; vp[eb + m * MA] = vb; }
+    else a[m] = make_float2(hqs ? va : va - ua, hqs ? vb : vb - ub);
   }
 }
 
@@ -1097,7 +1099,9 @@ DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar
   }
 }
 
-template <class TW>
+// LAST: the final iteration of a call -- x and v are written out next to u and there is no forward transform (the same staged,
+// persistent pipeline instead of the non-persistent k_rowz<ROW_LAST>: 350 -> ~200 us per two problems at 2048^2)
+template <class TW, bool LAST = false>
 __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_rowz_mid_persist(RowParams P, int n_tiles) {
   static_assert(TW::COLS == ZR, "tile holds one complex sequence per image row");
   constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
@@ -1209,28 +1213,34 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
         const float* ub_s = stU + (ZR + c) * RSU + j;
         if (simple) {
           switch (ps.kind) {
-            case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
-            case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
-            case DPX_PROX_L2SQ: mid_simple<DPX_PROX_L2SQ, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
-            default: mid_simple<DPX_PROX_BOX, RA, MA>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi); break;
+            case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
+            case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
+            case DPX_PROX_L2SQ: mid_simple<DPX_PROX_L2SQ, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
+            default: mid_simple<DPX_PROX_BOX, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
           }
         } else {
+          float* __restrict__ xp = P.x;
+          float* __restrict__ vp = tm.v;
 #pragma unroll
           for (int m = 0; m < RA; ++m) {
+            if (LAST) { xp[ea + m * MA] = a[m].x; xp[eb + m * MA] = a[m].y; }
             const float offa = op ? op[ea + m * MA] : 0.f, offb = op ? op[eb + m * MA] : 0.f;
             float wa = scale * a[m].x - offa, wb = scale * a[m].y - offb;
             if (!hqs) { wa += ua_s[m * MA]; wb += ub_s[m * MA]; }
             const float va = prox_wrapped(ps, wa, lam, offa), vb = prox_wrapped(ps, wb, lam, offb);
             const float ua = wa - va, ub = wb - vb;
             if (!hqs) { up[ea + m * MA] = ua; up[eb + m * MA] = ub; }
-            a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
+            if (LAST) { vp[ea + m * MA] = va; vp[eb + m * MA] = vb; }
+            else a[m] = make_float2(scale * (hqs ? va : va - ua), scale * (hqs ? vb : vb - ub));
           }
         }
-        fft::Dft<RA, false>::run(a);
+        if (!LAST) {
+          fft::Dft<RA, false>::run(a);
 #pragma unroll
-        for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);   // twiddles stay in registers (2 CTAs/SM leave 128 each)
+          for (int q = 1; q < RA; ++q) a[q] = fft::cmul(a[q], w[q]);   // twiddles stay in registers (2 CTAs/SM leave 128 each)
 #pragma unroll
-        for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
+          for (int m = 0; m < RA; ++m) sm[p0 + TW::template delta<MA>(m) * NSEQ] = a[m];
+        }
       }
     }
     __syncthreads();                                   // stU consumed, tile holds pass-A output
@@ -1238,6 +1248,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, nxt, stU, bars + 1, tid);
 
     // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
+    if (!LAST) {
     fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
     __syncthreads();
     if (tid == 0) trace_stamp(P.trace, tile, 6);
@@ -1252,6 +1263,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       float2* dst = P.S + (((size_t)pp * G + gq) * H + h0 + r) * CG + cc;
 #pragma unroll
       for (int m = 0; m < RC; ++m) dst[(size_t)m * (W / RC / CG) * H * CG] = a[m];
+    }
     }
     cur = nxt;
     if (tid == 0) trace_stamp(P.trace, tile, 7);
@@ -1300,6 +1312,44 @@ static __global__ void k_packz_fb(const float2* __restrict__ src, float2* __rest
   }
   dst[i] = make_float2(fa.x - fb.y, fa.y + fb.x);
 }
+// Same packing, organised around the SOURCE rows: a CTA stages the 8 rows one (pair, block, m-pair) needs -- rows h(m), h(m+1) and
+// their mirrors H - h of both planes -- with fully coalesced loads and writes, per column group, the 64-byte run
+// (c = 0..3) x (m % 2) of the record layout.  k_packz_fb reads one scattered 8-byte element per thread (every load its own
+// 32-byte sector, 256 rows apart): 318 us per two problems at 2048^2, 10 % of an end-to-end step; this form is bandwidth-bound.
+// grid (RC / 2, H / RC, pairs), dynamic shared memory 8 * (W / 2 + 1) * 8 bytes.
+#ifndef DPX_EMU
+static __global__ void k_packz_fb_rows(const float2* __restrict__ src, float2* __restrict__ dst, int pairs, int C, PackGeom q) {
+  extern __shared__ __align__(16) unsigned char rows_raw[];
+  float2* rows = reinterpret_cast<float2*>(rows_raw);              // [plane][mirror][m % 2][Wc]
+  const int H = q.H, W = q.W, RC = q.hRC;
+  const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
+  const int mg = blockIdx.x, blk = blockIdx.y, pp = blockIdx.z;
+  const int bq = pp / C, pA = 2 * bq * C + (pp - bq * C), pB = pA + C;
+  for (int r = 0; r < 8; ++r) {
+    const int pl = r >> 2, mir = (r >> 1) & 1, m2 = r & 1;
+    const int h = freq_of_pos_rt(blk * RC + mg * 2 + m2, H, q.hRA, q.hRB);
+    const float2* s = src + ((size_t)(pl ? pB : pA) * H + (mir ? (H - h) % H : h)) * Wc;
+    for (int k = threadIdx.x; k < Wc; k += blockDim.x) rows[r * Wc + k] = s[k];
+  }
+  __syncthreads();
+  const int WR = W / q.wRC;
+  for (int idx = threadIdx.x; idx < G * 8; idx += blockDim.x) {
+    const int g = idx >> 3, c = (idx >> 1) & 3, m2 = idx & 1;
+    const int sc = g * CG + c;
+    const int k = freq_of_pos_rt((sc % WR) * q.wRC + sc / WR, W, q.wRA, q.wRB);
+    float2 fa, fb;
+    if (k < Wc) {
+      fa = rows[(0 + m2) * Wc + k];
+      fb = rows[(4 + m2) * Wc + k];
+    } else {
+      fa = rows[(2 + m2) * Wc + (W - k)]; fa.y = -fa.y;
+      fb = rows[(6 + m2) * Wc + (W - k)]; fb.y = -fb.y;
+    }
+    const size_t i = ((((size_t)pp * G + g) * (RC / 2) + mg) * NT + blk * CG + c) * 2 + m2;
+    dst[i] = make_float2(fa.x - fb.y, fa.y + fb.x);
+  }
+}
+#endif
 static __global__ void k_packz_dq(const float* __restrict__ src, float* __restrict__ dst, int C, PackGeom q) {
   const int H = q.H, W = q.W, RC = q.hRC;
   const int NT = CG * (H / RC), G = W / CG, Wc = W / 2 + 1;
