@@ -44,8 +44,7 @@ constexpr int TILE_PX = 128;             // output pixels per CTA and tile row (
 constexpr int HALO_PX = TILE_PX + 2;     // staged pixels per row
 constexpr int ROW_BLOCK = 16;            // output rows per work unit
 constexpr int NSLOT = 5;                 // activation row slots in the ring (3 live + 2 in flight)
-constexpr int N_EPI_WARPS = 8;
-constexpr int NTHREADS = 64 + 32 * N_EPI_WARPS;
+constexpr int N_EPI_WARPS = 8;            // bf16 kernel; the SPLIT kernel of a 96-channel layer runs 12 (Cfg::NTHREADS)
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
 
 template <int CGIN, int COUT, bool SPLIT = false>
@@ -65,8 +64,12 @@ struct Cfg {
   static constexpr int OUT_KP = COUT >= 96 ? 6 : COUT / 8;              // SPLIT: groups per piece and K-half of the OUTPUT tensor (a
                                                                         // 96-channel tensor is consumed in two K-halves of 6 groups)
   static_assert(!SPLIT || CGIN % 4 == 0, "SPLIT: hi and lo' pieces of an even number of channel groups");
-  static constexpr int EPI_COLS = COUT / 2 >= 16 ? COUT / 2 : COUT;     // channels per epilogue warp (two warps per lane quadrant)
-  static constexpr int EPI_SPLIT = COUT / EPI_COLS;                     // 2, or 1 when the layer is too narrow to split
+  // epilogue warps per TMEM lane quadrant: 2 (1 when the layer is too narrow to split); the SPLIT epilogue of a 96-channel layer
+  // (two accumulators, the partial sum of the other K-half, the re-split) was the bottleneck of its launch with 2 -> 3 x 32 channels
+  static constexpr int EPI_SPLIT = (COUT == 96) ? 3 : (COUT / 2 >= 16 ? 2 : 1);
+  static constexpr int EPI_COLS = COUT / EPI_SPLIT;                     // channels per epilogue warp
+  static constexpr int NTHREADS = 64 + 32 * 4 * (EPI_SPLIT > 2 ? EPI_SPLIT : 2);
+  static_assert(EPI_COLS % 16 == 0, "tcgen05.ld x16");
   static constexpr size_t SMEM = 1024 + (W_BYTES + 127) / 128 * 128 + (size_t)NSLOT * SLOT_BYTES + 256;
   static_assert(CGIN % 2 == 0 && COUT % 16 == 0 && COUT <= 128, "shape");
   static_assert(W_TAP_BYTES % 16 == 0, "alignment");
@@ -203,7 +206,7 @@ __device__ __forceinline__ Unit unit_of(const Params& P, int u, int rank) {
 }
 
 template <int CGIN, int COUT, bool SPLIT = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg<CGIN, COUT, SPLIT>::NTHREADS), 1)
     k_conv3x3_tc(const __grid_constant__ CUtensorMap in_map, Params P) {
   using C = Cfg<CGIN, COUT, SPLIT>;
   extern __shared__ uint8_t smem_raw[];

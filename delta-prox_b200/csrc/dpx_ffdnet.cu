@@ -443,7 +443,7 @@ int launch_conv(const __nv_bfloat16* in, const __nv_bfloat16* wpack, const float
   DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int units = (P.n_tiles + 1) / 2;
   const int clusters = units < sms / 2 ? units : sms / 2;
-  convtc::k_conv3x3_tc<CGIN, COUT><<<2 * clusters, convtc::NTHREADS, C::SMEM, s>>>(map, P);
+  convtc::k_conv3x3_tc<CGIN, COUT><<<2 * clusters, C::NTHREADS, C::SMEM, s>>>(map, P);
   DPX_LAUNCH_CHECK();
   return DPX_OK;
 }
@@ -480,7 +480,7 @@ int launch_conv_split(const __half* in, int in_cgt, int khalf, const __half* wpa
   DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int units = (P.n_tiles + 1) / 2;
   const int clusters = units < sms / 2 ? units : sms / 2;
-  convtc::k_conv3x3_tc<CGIN, COUT, true><<<2 * clusters, convtc::NTHREADS, C::SMEM, s>>>(map, P);
+  convtc::k_conv3x3_tc<CGIN, COUT, true><<<2 * clusters, C::NTHREADS, C::SMEM, s>>>(map, P);
   DPX_LAUNCH_CHECK();
   return DPX_OK;
 }
