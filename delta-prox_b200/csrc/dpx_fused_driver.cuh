@@ -223,7 +223,11 @@ struct Driver {
           else if (psi.n == 1) be.template rowz<TW, MODE, true>(rgrid, rsm, rp);
           else be.template rowz<TW, MODE, false>(rgrid, rsm, rp);
         };
-        row(std::integral_constant<int, ROW_FIRST>{});
+        if (psi.n == 1 && be.persistent_ctas() > 0) {
+          using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
+          be.template rowz_persist<TW2, PM_FIRST>(dim3(be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM), RowZPersistSmem<TW2>::BYTES, rp,
+                                                  (H / ZR) * PP);
+        } else row(std::integral_constant<int, ROW_FIRST>{});
         for (int k = 0; k < n_iters; ++k) {
           cp.rho.it = it0 + k;
           launch_col<TH>(cp, B / 2, G, C);
@@ -231,8 +235,8 @@ struct Driver {
           if (psi.n == 1 && be.persistent_ctas() > 0) {
             using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
             const dim3 pg(be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM);
-            if (k + 1 < n_iters) be.template rowz_persist<TW2, false>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);
-            else be.template rowz_persist<TW2, true>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);   // last: x, v, u out
+            if (k + 1 < n_iters) be.template rowz_persist<TW2, PM_MID>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);
+            else be.template rowz_persist<TW2, PM_LAST>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * PP);   // last: x, v, u out
           }
           else if (k + 1 < n_iters) row(std::integral_constant<int, ROW_MID>{});
           else row(std::integral_constant<int, ROW_LAST>{});
@@ -262,9 +266,14 @@ struct Driver {
           cp.groups = G; cp.bmul = 2; cp.eps_im = eps; cp.dq_batch = 1; cp.rho.stride = 0;
           const dim3 rgrid(H / ROWS, P / 2);
           const size_t rsm = TW::SMEM_FLOAT2 * sizeof(float2);
-          be.template rowz<TW, ROW_FIRST, false>(rgrid, rsm, rp);
+          using TW2 = typename TileFor<decltype(wn)::value, ZR>::type;
+          const bool persist = be.persistent_ctas() > 0;
+          const dim3 pg(persist ? be.persistent_ctas() / 2 * RowZPersistSmem<TW2>::CTAS_PER_SM : 1);
+          if (persist && psi.n == 1) be.template rowz_persist<TW2, PM_FIRST>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * (P / 2));
+          else be.template rowz<TW, ROW_FIRST, false>(rgrid, rsm, rp);
           launch_col<TH>(cp, B / 2, G, C);
-          be.template rowz<TW, ROW_XONLY, false>(rgrid, rsm, rp);
+          if (persist) be.template rowz_persist<TW2, PM_XONLY>(pg, RowZPersistSmem<TW2>::BYTES, rp, (H / ZR) * (P / 2));
+          else be.template rowz<TW, ROW_XONLY, false>(rgrid, rsm, rp);
         } else {
           using TW = typename TileFor<decltype(wn)::value, ROWS / 2>::type;
           const int G = (W / 2) / CG;

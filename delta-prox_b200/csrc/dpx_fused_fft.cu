@@ -71,14 +71,14 @@ struct CudaBackend {
     if (rc) return;
     done(launch::rowz<TW, MODE, SINGLE>(grid, smem, p, s));
   }
-  template <class TW, bool LAST = false>
+  template <class TW, int PM = PM_MID>
   void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
     RowParams q = p;
     q.trace = trace_row;
     q.smap = row_smap;
     if (row_ctr && row_dyn) { q.ctr = row_ctr + (row_ctr_next++ % kRowCtrs); }
-    done(launch::rowz_persist<TW, LAST>(grid, smem, q, n_tiles, s));
+    done(launch::rowz_persist<TW, PM>(grid, smem, q, n_tiles, s));
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, const PackGeom& q) {
     if (rc) return;
@@ -280,8 +280,8 @@ class FusedEngine final : public FftEngine {
     be.n_sm = col_tma_sms_;
     be.trace_col = trace_col_; be.trace_row = trace_row_;
     be.col_bulk = col_bulk_; be.row_ctr = row_ctr_;
-    be.row_smap = nullptr; be.row_dyn = row_dyn_ && n_iters <= CudaBackend::kRowCtrs;   // one zeroed counter per launch
-    if (row_ctr_ && be.row_dyn) DPX_CUDA(cudaMemsetAsync(row_ctr_, 0, sizeof(int) * std::min(n_iters, (int)CudaBackend::kRowCtrs), s));
+    be.row_smap = nullptr; be.row_dyn = row_dyn_ && n_iters + 1 <= CudaBackend::kRowCtrs;   // one zeroed counter per persistent launch:
+    if (row_ctr_ && be.row_dyn) DPX_CUDA(cudaMemsetAsync(row_ctr_, 0, sizeof(int) * (n_iters + 1), s));   // first pass + n_iters iterations
     Mode mode = PLANES;
     int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
@@ -317,9 +317,16 @@ class FusedEngine final : public FftEngine {
                     int rho_stride, int it, cudaStream_t s) override {
     CudaBackend be{s};
     be.n_sm = col_tma_sms_;
+    be.n_persist = persist_ctas_;
+    be.col_bulk = col_bulk_; be.row_ctr = row_ctr_; be.row_dyn = row_dyn_; be.trace_col = trace_col_; be.trace_row = trace_row_;
+    if (row_ctr_ && be.row_dyn) DPX_CUDA(cudaMemsetAsync(row_ctr_, 0, sizeof(int) * 4, s));   // two persistent row launches per x-update
     Mode mode = PLANES;
     int rc = prepare(psi, rho_stride, s, be, &mode);
     if (rc) return rc;
+    if (row_tma_ && mode != PLANES) {
+      if (ensure_smap(mode == PAIRS ? (g.B / 2) * g.C : (g.P - g.P % 2) / 2, s) == DPX_OK) be.row_smap = smap_dev_;
+      else row_tma_ = 0;
+    }
     Driver<CudaBackend> drv(be);
     const float* dps = dpsi_std_ ? dpsp_ : nullptr;
     if (mode != FLAT) {

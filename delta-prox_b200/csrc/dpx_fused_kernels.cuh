@@ -1091,18 +1091,26 @@ DPX_HD void rowz_stage_S_tma(const RowParams& P, const RowZTile& t, float2* stS,
   for (int g0 = 0; g0 < G; g0 += BOX) tma_load_3d(stS + g0 * (ZR * CG), P.smap, bar, t.h0 * CG * 2, g0, t.pp);
 }
 template <class TW>
-DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar_t* bar, int tid) {
+DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar_t* bar, int tid, const float* base = nullptr) {
   constexpr int W = TW::N, RSU = RowZPersistSmem<TW>::RSU;
+  if (!base) base = P.psi.t[0].u;
   if (tid < 2 * ZR) {
     const int pl = tid / ZR, r = tid % ZR;                         // row = plane * ZR + r
-    bulk_load(stU + tid * RSU, P.psi.t[0].u + ((size_t)(pl ? t.pB : t.pA) * P.H + t.h0 + r) * W, W * sizeof(float), bar);
+    bulk_load(stU + tid * RSU, base + ((size_t)(pl ? t.pB : t.pA) * P.H + t.h0 + r) * W, W * sizeof(float), bar);
   }
 }
 
 // LAST: the final iteration of a call -- x and v are written out next to u and there is no forward transform (the same staged,
 // persistent pipeline instead of the non-persistent k_rowz<ROW_LAST>: 350 -> ~200 us per two problems at 2048^2)
-template <class TW, bool LAST = false>
+// PM (persist mode): PM_MID; PM_LAST; PM_XONLY = inverse transform -> x only (staged x-update: an external prox or a stencil
+// prox follows); PM_FIRST = forward transform of scale * (v - u) of the single psi term (the rows of v arrive through the dual
+// stage; the dual itself, read once per solve, straight from global memory).  The last two replace the non-persistent, unstaged
+// k_rowz<ROW_XONLY / ROW_FIRST> on the staged x-update path (TV objectives, deep priors) and at the start of every solve.
+enum PersistMode { PM_MID = 0, PM_LAST = 1, PM_XONLY = 2, PM_FIRST = 3 };
+template <class TW, int PM = PM_MID>
 __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_rowz_mid_persist(RowParams P, int n_tiles) {
+  constexpr bool LAST = PM == PM_LAST || PM == PM_XONLY;       // no forward transform, x leaves the kernel
+  constexpr bool XONLY = PM == PM_XONLY, FIRST = PM == PM_FIRST;
   static_assert(TW::COLS == ZR, "tile holds one complex sequence per image row");
   constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
   constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
@@ -1119,6 +1127,8 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
   const PsiTerm& tm = P.psi.t[0];
   const int hqs = P.hqs;
+  const bool ust = FIRST || (!XONLY && !hqs);       // rows staged next to the spectrum: the dual (v for PM_FIRST)
+  const bool sst = !FIRST;                          // spectrum rows staged (PM_FIRST has no inverse transform)
 
   if (tid == 0) {
     mbar_init(bars + 0, 1);
@@ -1129,11 +1139,13 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
   int tile = blockIdx.x;
   RowZTile cur = rowz_tile(P, tile < n_tiles ? tile : 0, tpp, n_tiles);
   if (tile < n_tiles) {
-    if (tid == 0 && !hqs) mbar_expect_tx(bars + 1, U_BYTES);
+    if (tid == 0 && ust) mbar_expect_tx(bars + 1, U_BYTES);
     __syncthreads();
-    if (P.smap) { if (tid == 0) rowz_stage_S_tma<TW>(P, cur, stS, bars + 0); }
-    else rowz_stage_S<TW>(P, cur, stS, tid);
-    if (!hqs) rowz_stage_u<TW>(P, cur, stU, bars + 1, tid);
+    if (sst) {
+      if (P.smap) { if (tid == 0) rowz_stage_S_tma<TW>(P, cur, stS, bars + 0); }
+      else rowz_stage_S<TW>(P, cur, stS, tid);
+    }
+    if (ust) rowz_stage_u<TW>(P, cur, stU, bars + 1, tid, FIRST ? tm.v : tm.u);
   }
   cp_async_commit();
 
@@ -1155,16 +1167,17 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     }
     cp_async_wait_all();
     if (DPX_MBAR_ALL_WAIT || tid == 0) {                                           // one poller; the barrier below publishes it
-      if (P.smap) mbar_wait(bars + 0, phase);
-      if (!hqs) mbar_wait(bars + 1, phase);
+      if (P.smap && sst) mbar_wait(bars + 0, phase);
+      if (ust) mbar_wait(bars + 1, phase);
     }
     __syncthreads();                                   // staged inputs are visible; the tile buffer is free
     next = *s_next;
     const RowZTile nxt = rowz_tile(P, next < n_tiles ? next : tile, tpp, n_tiles);
     if (tid == 0) trace_stamp(P.trace, tile, 2);
-    if (tid == 0 && next < n_tiles && !hqs) mbar_expect_tx(bars + 1, U_BYTES);   // copies are issued behind later barriers
+    if (tid == 0 && next < n_tiles && ust) mbar_expect_tx(bars + 1, U_BYTES);   // copies are issued behind later barriers
 
     // ---- 1. inverse pass C out of the staged spectrum rows (column storage order: see k_rowz) ----------------------------
+    if (!FIRST) {
     for (int t = tid; t < NT1; t += kThreads) {
       const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
       const int blk = gq * CG + cc;
@@ -1186,12 +1199,13 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     cp_async_commit();
     fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
     __syncthreads();
+    }
     if (tid == 0) trace_stamp(P.trace, tile, 4);
 
     // ---- 2. last inverse pass -> (x_A, x_B);  prox / dual / next rhs in registers (dual rows from the stage);  first forward pass
     {
       const float scale = tm.scale;
-      const float lam = tm.lam[(size_t)b * tm.lam_stride + P.it];
+      const float lam = (XONLY || FIRST) ? 0.f : tm.lam[(size_t)b * tm.lam_stride + P.it];
       const ProxSpec ps{tm.prox, tm.alpha, tm.beta, tm.inv_beta, tm.lo, tm.hi};
       float* __restrict__ up = tm.u;
       const float* __restrict__ op = tm.off;
@@ -1202,16 +1216,30 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
         const int c = t % NSEQ, j = t / NSEQ;
         const int p0 = TW::phys(j, c);
         float2 a[RA], w[RA];
-#pragma unroll
-        for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NSEQ];
         fft::load_twiddles<RA, MA>(twA, j, w);
+        if (!FIRST) {
 #pragma unroll
-        for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
-        fft::Dft<RA, true>::run(a);
+          for (int m = 0; m < RA; ++m) a[m] = sm[p0 + TW::template delta<MA>(m) * NSEQ];
+#pragma unroll
+          for (int q = 1; q < RA; ++q) a[q] = fft::cmulc(a[q], w[q]);
+          fft::Dft<RA, true>::run(a);
+        }
         const size_t ea = ((size_t)pA * H + h0 + c) * W + j, eb = ((size_t)pB * H + h0 + c) * W + j;
         const float* ua_s = stU + c * RSU + j;
         const float* ub_s = stU + (ZR + c) * RSU + j;
-        if (simple) {
+        if (XONLY) {
+          float* __restrict__ xp = P.x;
+#pragma unroll
+          for (int m = 0; m < RA; ++m) { xp[ea + m * MA] = a[m].x; xp[eb + m * MA] = a[m].y; }
+        } else if (FIRST) {
+          // right-hand side of the first x-update from the stored state: scale * (v - u) (ADMM) / scale * v (HQS); v is staged
+#pragma unroll
+          for (int m = 0; m < RA; ++m) {
+            float da = ua_s[m * MA], db = ub_s[m * MA];
+            if (!hqs) { da -= up[ea + m * MA]; db -= up[eb + m * MA]; }
+            a[m] = make_float2(scale * da, scale * db);
+          }
+        } else if (simple) {
           switch (ps.kind) {
             case DPX_PROX_NONNEG: mid_simple<DPX_PROX_NONNEG, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
             case DPX_PROX_L1: mid_simple<DPX_PROX_L1, RA, MA, LAST>(a, ua_s, ub_s, up, ea, eb, hqs, lam_eff, ps.lo, ps.hi, P.x, tm.v); break;
@@ -1245,7 +1273,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
     }
     __syncthreads();                                   // stU consumed, tile holds pass-A output
     if (tid == 0) trace_stamp(P.trace, tile, 5);
-    if (next < n_tiles && !hqs) rowz_stage_u<TW>(P, nxt, stU, bars + 1, tid);
+    if (next < n_tiles && ust) rowz_stage_u<TW>(P, nxt, stU, bars + 1, tid, FIRST ? tm.v : tm.u);
 
     // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
     if (!LAST) {

@@ -14,7 +14,7 @@ namespace launch {
 template <class TW, int MODE, bool SINGLE> cudaError_t row(dim3 grid, size_t smem, const RowParams& p, cudaStream_t s);
 template <class TW> cudaError_t row_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s);
 template <class TW, int MODE, bool SINGLE> cudaError_t rowz(dim3 grid, size_t smem, const RowParams& p, cudaStream_t s);
-template <class TW, bool LAST> cudaError_t rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s);
+template <class TW, int PM> cudaError_t rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s);
 template <class TH> cudaError_t col(dim3 grid, size_t smem, const ColParams& p, cudaStream_t s);
 template <class TH> cudaError_t col_tma(dim3 grid, size_t smem, const ColParams& p, int n_tiles, int nb, cudaStream_t s);
 template <class TH, typename V> cudaError_t pack(const V* src, V* dst, int planes, int H, int W, int G, V zero, cudaStream_t s);

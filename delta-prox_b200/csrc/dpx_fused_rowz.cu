@@ -12,11 +12,11 @@ cudaError_t rowz(dim3 grid, size_t smem, const RowParams& p, cudaStream_t s) {
   k_rowz<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
-template <class TW, bool LAST>
+template <class TW, int PM>
 cudaError_t rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s) {
-  cudaError_t e = prep(k_rowz_mid_persist<TW, LAST>, smem);
+  cudaError_t e = prep(k_rowz_mid_persist<TW, PM>, smem);
   if (e != cudaSuccess) return e;
-  k_rowz_mid_persist<TW, LAST><<<grid, kThreads, smem, s>>>(p, n_tiles);
+  k_rowz_mid_persist<TW, PM><<<grid, kThreads, smem, s>>>(p, n_tiles);
   return cudaGetLastError();
 }
 
@@ -28,8 +28,10 @@ cudaError_t rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles
   template cudaError_t rowz<typename TileFor<N, ROWS>::type, ROW_LAST, true>(dim3, size_t, const RowParams&, cudaStream_t);   \
   template cudaError_t rowz<typename TileFor<N, ROWS>::type, ROW_LAST, false>(dim3, size_t, const RowParams&, cudaStream_t);  \
   template cudaError_t rowz<typename TileFor<N, ROWS>::type, ROW_XONLY, false>(dim3, size_t, const RowParams&, cudaStream_t); \
-  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, false>(dim3, size_t, const RowParams&, int, cudaStream_t); \
-  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, true>(dim3, size_t, const RowParams&, int, cudaStream_t);
+  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, PM_MID>(dim3, size_t, const RowParams&, int, cudaStream_t);   \
+  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, PM_LAST>(dim3, size_t, const RowParams&, int, cudaStream_t);  \
+  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, PM_XONLY>(dim3, size_t, const RowParams&, int, cudaStream_t); \
+  template cudaError_t rowz_persist<typename TileFor<N, ZR>::type, PM_FIRST>(dim3, size_t, const RowParams&, int, cudaStream_t);
 DPX_W_SIZES(DPX_INST_ROW)
 
 }  // namespace launch

@@ -37,9 +37,9 @@ struct EmuBackend {
   void rowz(dim3 grid, size_t smem, RowParams p) {
     emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz<TW, MODE, SINGLE>(p); });
   }
-  template <class TW, bool LAST>
+  template <class TW, int PM>
   void rowz_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
-    emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz_mid_persist<TW, LAST>(p, n_tiles); });
+    emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz_mid_persist<TW, PM>(p, n_tiles); });
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, PackGeom q) {
     const size_t total = (size_t)pairs * q.H * q.W;
