@@ -14,6 +14,7 @@
 
 #include "dpx_common.cuh"
 #include "dpx_conv_tc.cuh"
+#include "dpx_conv_wgrad.cuh"
 
 using namespace dpx;
 
@@ -485,6 +486,62 @@ int launch_conv_split(const __half* in, int in_cgt, int khalf, const __half* wpa
   return DPX_OK;
 }
 
+// ---- weight gradient (dpx_conv_wgrad.cuh) -------------------------------------------------------------------------------------
+// dW accumulator [9][128][N] fp32 -> nn.Conv2d layout gw[co][ci][ky][kx] (+= when accumulate)
+__global__ void k_wgrad_unpack(const float* __restrict__ dw, float* __restrict__ gw, int cout, int cin, int N, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * 9) return;
+  const int tap = i % 9, ci = (i / 9) % cin, co = i / (9 * cin);
+  const float v = dw[((size_t)tap * 128 + co) * N + ci];
+  gw[i] = accumulate ? gw[i] + v : v;
+}
+// bias gradient: db[co] = sum over pixels of gy (channel-group-major bf16 input), one block per (image, group, row)
+__global__ void k_bias_grad(const __nv_bfloat16* __restrict__ gy, float* __restrict__ db, int CG, int H, int W, int cout) {
+  const int row = blockIdx.x;                                   // (n * CG + cg) * H + y
+  const int cg = (row / H) % CG;
+  const __nv_bfloat16* src = gy + (size_t)row * (W + 2) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(x + 1) * 8);
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(b[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float s = warp_sum(acc[e]);
+    if ((threadIdx.x & 31) == 0 && cg * 8 + e < cout) atomicAdd(db + cg * 8 + e, s);
+  }
+}
+
+template <int CGG, int CGA>
+int launch_wgrad(const __nv_bfloat16* gy, const __nv_bfloat16* a, float* dw, int cout, int N, int H, int W, cudaStream_t s) {
+  using C = convtc::WgCfg<CGG, CGA>;
+  DPX_REQUIRE(W % convtc::TILE_PX == 0, "native weight gradient needs a row length that is a multiple of 128 (got %d)", W);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPX_CUDA(cudaFuncSetAttribute(convtc::k_conv3x3_wgrad<CGG, CGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap gmap, amap;
+  int rc = make_row_map(&gmap, gy, N, CGG, H, W);
+  if (!rc) rc = make_row_map(&amap, a, N, CGA, H, W);
+  if (rc) return rc;
+  convtc::WgParams P;
+  P.dw = dw; P.cout = cout; P.N = N; P.H = H; P.W = W;
+  P.x_tiles = W / convtc::TILE_PX;
+  P.row_blocks = (H + convtc::ROW_BLOCK - 1) / convtc::ROW_BLOCK;
+  P.n_tiles = N * P.x_tiles * P.row_blocks;
+  int dev = 0, sms = 0;
+  DPX_CUDA(cudaGetDevice(&dev));
+  DPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ctas = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;   // x 2 tap halves = one CTA per SM
+  DPX_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * 128 * C::N, s));
+  convtc::k_conv3x3_wgrad<CGG, CGA><<<dim3(ctas, 2), convtc::WG_THREADS, C::SMEM, s>>>(gmap, amap, P);
+  DPX_LAUNCH_CHECK();
+  return DPX_OK;
+}
+
 }  // namespace
 
 struct dpx_ffdnet {
@@ -863,6 +920,46 @@ int dpx_ffdnet_conv_layer(dpx_ffdnet* n, int layer, int direction, int relu, con
   }
   cudaStreamSynchronize(s);
   cudaFree(a); cudaFree(o);
+  return rc;
+}
+
+
+// Weight (and bias) gradient of one layer on fp32 NCHW tensors (per-layer parity tests): x [B,cin,H,W] = the layer's input,
+// gy [B,cout,H,W] = the gradient w.r.t. its (pre-activation) output; gw [cout,cin,3,3], gb [cout] (may be NULL).  bf16 operands.
+int dpx_ffdnet_wgrad_layer(dpx_ffdnet* n, int layer, const float* x, const float* gy, float* gw, float* gb, int B, int H, int W,
+                           void* stream) {
+  DPX_REQUIRE(n && x && gy && gw, "null argument");
+  DPX_REQUIRE(layer >= 0 && layer < n->nb, "layer %d out of range", layer);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool head = layer == 0, tail = layer == n->nb - 1;
+  const int cin = head ? 13 : 96, cout = tail ? 12 : 96, cin_pad = head ? 16 : 96, cout_pad = tail ? 16 : 96;
+  const size_t pix = (size_t)B * H * W;
+  __nv_bfloat16 *a = nullptr, *g = nullptr;
+  float* dw = nullptr;
+  DPX_CUDA(cudaMalloc(&a, sizeof(__nv_bfloat16) * padded_elems(B, cin_pad, H, W)));
+  DPX_CUDA(cudaMalloc(&g, sizeof(__nv_bfloat16) * padded_elems(B, cout_pad, H, W)));
+  DPX_CUDA(cudaMalloc(&dw, sizeof(float) * 9 * 128 * 96));
+  DPX_CUDA(cudaMemsetAsync(a, 0, sizeof(__nv_bfloat16) * padded_elems(B, cin_pad, H, W), s));
+  DPX_CUDA(cudaMemsetAsync(g, 0, sizeof(__nv_bfloat16) * padded_elems(B, cout_pad, H, W), s));
+  k_nchw_to_c8<<<(unsigned)((pix * cin_pad + 255) / 256), 256, 0, s>>>(x, a, B, cin, cin_pad / 8, H, W);
+  DPX_LAUNCH_CHECK();
+  k_nchw_to_c8<<<(unsigned)((pix * cout_pad + 255) / 256), 256, 0, s>>>(gy, g, B, cout, cout_pad / 8, H, W);
+  DPX_LAUNCH_CHECK();
+  int rc;
+  if (head) rc = launch_wgrad<12, 2>(g, a, dw, cout, B, H, W, s);
+  else if (tail) rc = launch_wgrad<2, 12>(g, a, dw, cout, B, H, W, s);
+  else rc = launch_wgrad<12, 12>(g, a, dw, cout, B, H, W, s);
+  if (!rc) {
+    k_wgrad_unpack<<<(cout * cin * 9 + 255) / 256, 256, 0, s>>>(dw, gw, cout, cin, cin_pad, 0);
+    ++g_launches;
+    if (gb) {
+      DPX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * cout, s));
+      k_bias_grad<<<B * (cout_pad / 8) * H, 128, 0, s>>>(g, gb, cout_pad / 8, H, W, cout);
+      ++g_launches;
+    }
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(a); cudaFree(g); cudaFree(dw);
   return rc;
 }
 

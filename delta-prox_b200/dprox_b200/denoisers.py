@@ -129,6 +129,20 @@ class NativeFFDNet:
                                                         cabi.stream_ptr(x.device)), "dpx_ffdnet_conv_layer")
         return y
 
+    def wgrad_layer(self, layer: int, x: torch.Tensor, gy: torch.Tensor):
+        """(dL/dW, dL/db) of one convolution given its input `x` and the gradient `gy` w.r.t. its pre-activation output, on the
+        tensor-core weight-gradient kernel (csrc/dpx_conv_wgrad.cuh; bf16 operands; needs a width that is a multiple of 128)"""
+        cabi = self._cabi
+        x, gy = cabi.require_cuda_f32(x, "x"), cabi.require_cuda_f32(gy, "gy")
+        B, cin, H, W = x.shape
+        cout = gy.shape[1]
+        gw = torch.empty(cout, cin, 3, 3, device=x.device, dtype=torch.float32)
+        gb = torch.empty(cout, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            cabi.check(cabi.lib().dpx_ffdnet_wgrad_layer(self._h, int(layer), cabi.ptr(x), cabi.ptr(gy), cabi.ptr(gw), cabi.ptr(gb), B, H, W,
+                                                         cabi.stream_ptr(x.device)), "dpx_ffdnet_wgrad_layer")
+        return gw, gb
+
     def __deepcopy__(self, memo):
         raise TypeError("NativeFFDNet owns device filter banks; copy the owning denoiser instead (it rebuilds them lazily)")
 

@@ -285,6 +285,12 @@ int dpx_ffdnet_backward(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_
  * 1 = data gradient.  x [B,cin,H,W] -> y [B,cout,H,W], (cin, cout) = the layer's channel counts in that direction. */
 int dpx_ffdnet_conv_layer(dpx_ffdnet* net, int layer, int direction, int relu, const float* x, float* y, int B, int H, int W,
                           void* stream);
+/* Weight and bias gradient of one layer on fp32 NCHW tensors (torch: conv2d's grad_weight / grad_bias; network_ffdnet.py:27-68
+ * under training): x [B,cin,H,W] = the layer's input, gy [B,cout,H,W] = gradient w.r.t. its pre-activation output;
+ * gw [cout,cin,3,3], gb [cout] (may be NULL).  tcgen05 kernel with MN-major operands (csrc/dpx_conv_wgrad.cuh), bf16 operands,
+ * fp32 accumulation in TMEM over all pixels.  Needs W % 128 == 0. */
+int dpx_ffdnet_wgrad_layer(dpx_ffdnet* net, int layer, const float* x, const float* gy, float* gw, float* gb, int B, int H, int W,
+                           void* stream);
 
 /* ---- CS-MRI closed-form data term on complex iterates (proxfn/fast/csmri.py:14-25; the ext_sum_squares hook,
  * proxfn/sum_square.py:44-48).  v, y, out: complex64 [B,C,H,W] (interleaved re,im); mask: fp32 0/1 [mask_batch,C,H,W],

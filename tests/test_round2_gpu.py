@@ -516,3 +516,24 @@ def test_cfg4_size_hqs_vs_oracle(dp):
     st = s.solve(x0=bd, rhos=1.0, lams=0.02, max_iter=T_, return_full_states=True)
     assert rel(st[0], want[0]) < TOL_X, rel(st[0], want[0])
     assert rel(st[1][0], want[1][0]) < TOL_AUX
+
+
+def test_tcgen05_weight_gradient_matches_conv2d_grad(dp):
+    """weight / bias gradient of every FFDNet layer shape (13->96, 96->96, 96->12) on the MN-major tcgen05 kernel against torch's
+    conv2d weight gradient evaluated in fp64 on the same bf16-rounded operands (what is left is fp32 accumulation order)"""
+    import torch.nn.functional as F
+    from dprox_b200.denoisers import FFDNetColorDenoiser, NativeFFDNet
+    den = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
+    net = NativeFFDNet(den.model, torch.device("cuda"))
+    convs = [m for m in den.model.model if isinstance(m, torch.nn.Conv2d)]
+    g = torch.Generator().manual_seed(11)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    for layer in (0, 3, len(convs) - 1):
+        c = convs[layer]
+        for shape in ((2, 40, 128), (1, 21, 256)):                      # 3 / 2 row blocks (one ragged), one / two 128-pixel tiles
+            x = torch.randn(shape[0], c.in_channels, *shape[1:], generator=g).cuda()
+            gy = torch.randn(shape[0], c.out_channels, *shape[1:], generator=g).cuda()
+            gw, gb = net.wgrad_layer(layer, x, gy)
+            want = torch.nn.grad.conv2d_weight(bf(x), c.weight.shape, bf(gy), padding=1)
+            assert rel(gw, want) < 2e-5, (layer, shape, rel(gw, want))
+            assert rel(gb, bf(gy).sum((0, 2, 3))) < 2e-5, (layer, shape)
