@@ -551,6 +551,7 @@ struct dpx_ffdnet {
   __half* acts[MAXL] = {nullptr};           // SPLIT activations (piece tensors)
   __half *ios = nullptr, *gas = nullptr, *gbs = nullptr;
   float *part32 = nullptr, *out32 = nullptr;
+  float* dw = nullptr;                      // weight-gradient accumulator [9][128][96] fp32
   size_t acts_cap = 0;
   int n_acts = 0;
   int sbuf_B = 0, sbuf_h2 = 0, sbuf_w2 = 0;
@@ -758,7 +759,7 @@ void dpx_ffdnet_destroy(dpx_ffdnet* n) {
   for (int i = 0; i < MAXL; ++i) { cudaFree(n->w[i]); cudaFree(n->wd[i]); cudaFree(n->act[i]); }
   cudaFree(n->io16); cudaFree(n->out16); cudaFree(n->ga); cudaFree(n->gb);
   for (int i = 0; i < MAXL; ++i) { cudaFree(n->ws[i]); cudaFree(n->wds[i]); cudaFree(n->acts[i]); }
-  cudaFree(n->ios); cudaFree(n->gas); cudaFree(n->gbs); cudaFree(n->part32); cudaFree(n->out32);
+  cudaFree(n->ios); cudaFree(n->gas); cudaFree(n->gbs); cudaFree(n->part32); cudaFree(n->out32); cudaFree(n->dw);
   delete n;
 }
 
@@ -817,6 +818,57 @@ int dpx_ffdnet_forward_train(dpx_ffdnet* n, const float* x, const float* sigma, 
   return run_forward(n, x, sigma, sigma_per_sample, y, B, H, W, true, (cudaStream_t)stream);
 }
 
+// shared by dpx_ffdnet_backward (gw = gb = NULL) and dpx_ffdnet_backward_params
+static int backward_bf16(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, float* const* gw,
+                         float* const* gb, int B, int H, int W, cudaStream_t s) {
+  const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+  const size_t pix = (size_t)B * h2 * w2;
+  if (!n->ga) {
+    DPX_CUDA(cudaMalloc(&n->ga, sizeof(__nv_bfloat16) * n->act_cap));
+    DPX_CUDA(cudaMalloc(&n->gb, sizeof(__nv_bfloat16) * n->act_cap));
+    DPX_CUDA(cudaMemsetAsync(n->ga, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
+    DPX_CUDA(cudaMemsetAsync(n->gb, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
+  }
+  if (gw && !n->dw) DPX_CUDA(cudaMalloc(&n->dw, sizeof(float) * 9 * 128 * 96));
+  // weight / bias gradient of layer l from its input activation and the gradient w.r.t. its pre-activation output
+  auto params_of = [&](int l, const __nv_bfloat16* gy, const __nv_bfloat16* a) -> int {
+    if (!gw) return DPX_OK;
+    const bool head = l == 0, tail = l == n->nb - 1;
+    const int cin = head ? 13 : 96, cout = tail ? 12 : 96, cin_pad = head ? 16 : 96, cout_pad = tail ? 16 : 96;
+    int rc = head ? launch_wgrad<12, 2>(gy, a, n->dw, cout, B, h2, w2, s)
+                  : (tail ? launch_wgrad<2, 12>(gy, a, n->dw, cout, B, h2, w2, s) : launch_wgrad<12, 12>(gy, a, n->dw, cout, B, h2, w2, s));
+    if (rc) return rc;
+    k_wgrad_unpack<<<(cout * cin * 9 + 255) / 256, 256, 0, s>>>(n->dw, gw[l], cout, cin, cin_pad, 0);
+    DPX_LAUNCH_CHECK();
+    if (gb && gb[l]) {
+      DPX_CUDA(cudaMemsetAsync(gb[l], 0, sizeof(float) * cout, s));
+      k_bias_grad<<<B * (cout_pad / 8) * h2, 128, 0, s>>>(gy, gb[l], cout_pad / 8, h2, w2, cout);
+      DPX_LAUNCH_CHECK();
+    }
+    return DPX_OK;
+  };
+  // g wrt the tail's output (16 channels, 12 real)
+  k_shuffle_out_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(g_y, n->out16, B, H, W, h2, w2);
+  DPX_LAUNCH_CHECK();
+  int rc = params_of(n->nb - 1, n->out16, n->act[n->nb - 2]);
+  // tail: g wrt its input a_{nb-2}, masked by the ReLU of the layer that produced it -> g wrt that layer's pre-activation
+  __nv_bfloat16 *cur = n->ga, *nxt = n->gb;
+  if (!rc) rc = launch_conv<2, 96>(n->out16, n->wd[n->nb - 1], nullptr, cur, n->act[n->nb - 2], 0, B, h2, w2, s);
+  for (int l = n->nb - 2; l >= 1 && !rc; --l) {
+    rc = params_of(l, cur, n->act[l - 1]);
+    if (!rc) rc = launch_conv<12, 96>(cur, n->wd[l], nullptr, nxt, n->act[l - 1], 0, B, h2, w2, s);
+    __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+  }
+  if (!rc) rc = params_of(0, cur, n->io16);                     // the head's input is the saved 16-channel tensor ...
+  if (!rc) rc = launch_conv<12, 16>(cur, n->wd[0], nullptr, n->io16, nullptr, 0, B, h2, w2, s);     // ... overwritten here: g wrt it
+  if (rc) return rc;
+  if (g_sigma) DPX_CUDA(cudaMemsetAsync(g_sigma, 0, sizeof(float) * (sigma_per_sample ? B : 1), s));
+  k_unshuffle_in_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(n->io16, g_x, g_sigma, sigma_per_sample, B, H, W, h2, w2);
+  DPX_LAUNCH_CHECK();
+  n->saved = false;                                             // io16 was reused: the saved input is gone
+  return DPX_OK;
+}
+
 int dpx_ffdnet_backward(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, int B, int H, int W,
                         void* stream) {
   DPX_REQUIRE(n && g_y && g_x, "null argument");
@@ -825,30 +877,20 @@ int dpx_ffdnet_backward(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_si
               "dpx_ffdnet_backward needs the activations of a matching dpx_ffdnet_forward_train call");
   cudaStream_t s = (cudaStream_t)stream;
   if (n->precision) return run_backward_split(n, g_y, g_x, g_sigma, sigma_per_sample, B, H, W, s);
-  const size_t pix = (size_t)B * h2 * w2;
-  if (!n->ga) {
-    DPX_CUDA(cudaMalloc(&n->ga, sizeof(__nv_bfloat16) * n->act_cap));
-    DPX_CUDA(cudaMalloc(&n->gb, sizeof(__nv_bfloat16) * n->act_cap));
-    DPX_CUDA(cudaMemsetAsync(n->ga, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
-    DPX_CUDA(cudaMemsetAsync(n->gb, 0, sizeof(__nv_bfloat16) * n->act_cap, s));
-  }
-  // g wrt the tail's output (16 channels, 12 real)
-  k_shuffle_out_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(g_y, n->out16, B, H, W, h2, w2);
-  DPX_LAUNCH_CHECK();
-  // tail: g wrt its input a_{nb-2}, masked by the ReLU of the layer that produced it -> g wrt that layer's pre-activation
-  __nv_bfloat16 *cur = n->ga, *nxt = n->gb;
-  int rc = launch_conv<2, 96>(n->out16, n->wd[n->nb - 1], nullptr, cur, n->act[n->nb - 2], 0, B, h2, w2, s);
-  for (int l = n->nb - 2; l >= 1 && !rc; --l) {
-    rc = launch_conv<12, 96>(cur, n->wd[l], nullptr, nxt, n->act[l - 1], 0, B, h2, w2, s);
-    __nv_bfloat16* t = cur; cur = nxt; nxt = t;
-  }
-  if (!rc) rc = launch_conv<12, 16>(cur, n->wd[0], nullptr, n->io16, nullptr, 0, B, h2, w2, s);     // g wrt the 16-channel input
-  if (rc) return rc;
-  if (g_sigma) DPX_CUDA(cudaMemsetAsync(g_sigma, 0, sizeof(float) * (sigma_per_sample ? B : 1), s));
-  k_unshuffle_in_bwd<<<(unsigned)((pix + 255) / 256), 256, 0, s>>>(n->io16, g_x, g_sigma, sigma_per_sample, B, H, W, h2, w2);
-  DPX_LAUNCH_CHECK();
-  n->saved = false;                                             // io16 was reused: the saved input is gone
-  return DPX_OK;
+  return backward_bf16(n, g_y, g_x, g_sigma, sigma_per_sample, nullptr, nullptr, B, H, W, s);
+}
+
+// Same, and the gradients w.r.t. every layer's weights and biases (training the denoiser): gw[l] device fp32 [cout,cin,3,3],
+// gb[l] device fp32 [cout] (gb or its entries may be NULL).  bf16 precision only; needs ceil(W / 2) % 128 == 0.
+int dpx_ffdnet_backward_params(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, float* const* gw,
+                               float* const* gb, int B, int H, int W, void* stream) {
+  DPX_REQUIRE(n && g_y && g_x && gw, "null argument");
+  DPX_REQUIRE(n->precision == 0, "the weight gradient runs in the bf16 mode only");
+  const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+  DPX_REQUIRE(w2 % convtc::TILE_PX == 0, "native weight gradient needs ceil(W / 2) %% 128 == 0 (got %d)", w2);
+  DPX_REQUIRE(n->saved && n->saved_B == B && n->saved_h2 == h2 && n->saved_w2 == w2,
+              "dpx_ffdnet_backward_params needs the activations of a matching dpx_ffdnet_forward_train call");
+  return backward_bf16(n, g_y, g_x, g_sigma, sigma_per_sample, gw, gb, B, H, W, (cudaStream_t)stream);
 }
 
 // one convolution layer on fp32 NCHW tensors (debug / per-layer parity tests): direction 0 = forward (bias, optional ReLU),

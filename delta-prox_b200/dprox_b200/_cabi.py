@@ -91,6 +91,7 @@ SIGNATURES = {
     "dpx_ffdnet_forward": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),
     "dpx_ffdnet_forward_train": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _VP]),
     "dpx_ffdnet_backward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dpx_ffdnet_backward_params": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "dpx_ffdnet_conv_layer": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "dpx_ffdnet_wgrad_layer": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "dpx_csmri_prox": (_I, [_VP, _VP, _VP, _I, _VP, _I, _F, _VP, _I, _I, _I, _I, _VP]),

@@ -112,6 +112,36 @@ class NativeFFDNet:
         self._mark(ev, "bwd", B * H * W)
         return g_x, g_s
 
+    def load_weights(self, convs):
+        """(re)pack the filter banks from the modules' current weights (after an optimizer step)"""
+        cabi, lib = self._cabi, self._cabi.lib()
+        with torch.cuda.device(self.device):
+            for i, c in enumerate(convs):
+                w = c.weight.detach().to(self.device, torch.float32).contiguous()
+                b = c.bias.detach().to(self.device, torch.float32).contiguous()
+                cabi.check(lib.dpx_ffdnet_set_layer(self._h, i, cabi.ptr(w), cabi.ptr(b), w.shape[0], w.shape[1],
+                                                    cabi.stream_ptr(self.device)), "dpx_ffdnet_set_layer")
+
+    def backward_params(self, g_y: torch.Tensor, n_sigma: int, shapes):
+        """(dL/dx, dL/dsigma, [dL/dW_l], [dL/db_l]) of the last `train=True` call: data gradient and weight gradient both on the
+        tensor-core kernels (dpx_ffdnet_backward_params)."""
+        import ctypes as C
+        cabi = self._cabi
+        g_y = cabi.require_cuda_f32(g_y, "g_y")
+        B, _, H, W = g_y.shape
+        g_x = torch.empty_like(g_y)
+        g_s = torch.empty(n_sigma, device=g_y.device, dtype=torch.float32)
+        gws = [torch.empty(sw, device=g_y.device, dtype=torch.float32) for sw, _ in shapes]
+        gbs = [torch.empty(sb, device=g_y.device, dtype=torch.float32) for _, sb in shapes]
+        pw = (C.c_void_p * len(gws))(*[t.data_ptr() for t in gws])
+        pb = (C.c_void_p * len(gbs))(*[t.data_ptr() for t in gbs])
+        ev = self._mark()
+        with torch.cuda.device(g_y.device):
+            cabi.check(cabi.lib().dpx_ffdnet_backward_params(self._h, cabi.ptr(g_y), cabi.ptr(g_x), cabi.ptr(g_s), int(n_sigma > 1), pw, pb,
+                                                             B, H, W, cabi.stream_ptr(g_y.device)), "dpx_ffdnet_backward_params")
+        self._mark(ev, "bwd", B * H * W)
+        return g_x, g_s, gws, gbs
+
     def conv_layer(self, layer: int, x: torch.Tensor, direction: int = 0, relu: bool = False) -> torch.Tensor:
         """one convolution of the network on fp32 NCHW tensors (per-layer parity tests)"""
         cabi = self._cabi
@@ -181,6 +211,36 @@ class _NativeFFDNetFn(torch.autograd.Function):
         return g_x, g_s.reshape(ctx.sigma_shape), None
 
 
+class _NativeFFDNetTrainFn(torch.autograd.Function):
+    """y = FFDNet(x, sigma; weights) with TRAINABLE weights: forward, data gradient and weight gradient on the tensor-core kernels.
+    `params` = (w_0, b_0, w_1, b_1, ...) of the convolutions, passed so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, x, sigma, net, convs, *params):
+        ctx.net, ctx.convs, ctx.sigma_shape = net, convs, sigma.shape
+        ctx.n_sigma = int(sigma.numel())
+        ctx.shapes = [(tuple(c.weight.shape), tuple(c.bias.shape)) for c in convs]
+        net.load_weights(convs)                                    # the banks follow the optimizer
+        _NativeFFDNetFn._calls += 1
+        ctx.graph_id = net._graph_id = _NativeFFDNetFn._calls
+        ctx.save_for_backward(x.detach(), sigma.detach())
+        return net(x.detach(), sigma.detach(), train=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        if ctx.graph_id != net._graph_id:                          # another forward ran in between: recompute this call's
+            x, sigma = ctx.saved_tensors
+            net(x, sigma, train=True)
+            net._graph_id = ctx.graph_id
+        g_x, g_s, gws, gbs = net.backward_params(g.contiguous(), ctx.n_sigma, ctx.shapes)
+        net._graph_id = -1
+        grads = []
+        for gw_, gb_ in zip(gws, gbs):
+            grads += [gw_, gb_]
+        return (g_x, g_s.reshape(ctx.sigma_shape), None, None, *grads)
+
+
 class FFDNetColorDenoiser(Denoiser):
     """pnp/denoisers/wrapper.py:38-48.  `precision='fp32'` (default): the native tcgen05 network with fp16 operand pairs
     (fp32-class accuracy, 1e-5 parity with the reference's fp32 path); `precision='bf16'`: the same kernels with bf16 operands
@@ -232,9 +292,17 @@ class FFDNetColorDenoiser(Denoiser):
             return _NativeFFDNetFn.apply(x.contiguous(), sigma, self._native_net(x.device))
         if native and not wants_grad:
             return self._native_net(x.device)(x, sigma)
+        if self.precision == "bf16" and ((x.shape[-1] + 1) // 2) % 128 == 0:
+            # trainable denoiser weights: forward, data gradient AND weight gradient on the native kernels (the weight-gradient
+            # kernel needs quarter-resolution rows that are a multiple of 128 pixels; other widths take the branch below)
+            convs = [m for m in self.model.model if isinstance(m, nn.Conv2d)]
+            params = []
+            for c in convs:
+                params += [c.weight, c.bias]
+            return _NativeFFDNetTrainFn.apply(x.contiguous(), sigma, self._native_net(x.device), convs, *params)
         if self.precision == "bf16":
-            # trainable denoiser weights: the weight gradient has no native kernel, so the tape runs through the framework's
-            # convolutions with bf16 operands / fp32 accumulation
+            # trainable denoiser weights at a width the native weight-gradient kernel does not take: the tape runs through the
+            # framework's convolutions with bf16 operands / fp32 accumulation
             if not getattr(self, "_nhwc", False):          # NHWC weights: cuDNN's tensor-core kernels for forward, dgrad and wgrad
                 self.model.to(memory_format=torch.channels_last)
                 self._nhwc = True

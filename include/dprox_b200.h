@@ -281,6 +281,11 @@ int dpx_ffdnet_forward_train(dpx_ffdnet* net, const float* x, const float* sigma
  * same tensor-core kernel, with the ReLU mask of the saved activation applied in its epilogue.  Consumes the saved state. */
 int dpx_ffdnet_backward(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, int B, int H,
                         int W, void* stream);
+/* dpx_ffdnet_backward plus the gradients w.r.t. every layer's parameters (training the denoiser's weights without leaving
+ * native code): gw[l] device fp32 [cout,cin,3,3] (nn.Conv2d layout), gb[l] device fp32 [cout]; gb or entries of it may be NULL.
+ * Weight gradient on the MN-major tcgen05 kernel (csrc/dpx_conv_wgrad.cuh).  bf16 precision; needs ceil(W / 2) % 128 == 0. */
+int dpx_ffdnet_backward_params(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample,
+                               float* const* gw, float* const* gb, int B, int H, int W, void* stream);
 /* One convolution layer on fp32 NCHW tensors (per-layer parity tests): direction 0 = forward (+bias, optional ReLU),
  * 1 = data gradient.  x [B,cin,H,W] -> y [B,cout,H,W], (cin, cout) = the layer's channel counts in that direction. */
 int dpx_ffdnet_conv_layer(dpx_ffdnet* net, int layer, int direction, int relu, const float* x, float* y, int B, int H, int W,

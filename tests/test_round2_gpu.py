@@ -537,3 +537,47 @@ def test_tcgen05_weight_gradient_matches_conv2d_grad(dp):
             want = torch.nn.grad.conv2d_weight(bf(x), c.weight.shape, bf(gy), padding=1)
             assert rel(gw, want) < 2e-5, (layer, shape, rel(gw, want))
             assert rel(gb, bf(gy).sum((0, 2, 3))) < 2e-5, (layer, shape)
+
+
+def test_native_ffdnet_training_gradients(dp):
+    """trainable FFDNet weights in the bf16 mode: forward, data gradient and weight / bias gradients all on the tensor-core kernels
+    (`_NativeFFDNetTrainFn`).  A bf16 ReLU network's gradients are noisy by nature, so -- like the data-gradient test -- the native
+    gradients are held to the distance torch's own bf16 autocast backward has from the fp32 gradients."""
+    from dprox_b200.denoisers import FFDNetColorDenoiser
+    den = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
+    ref = FFDNetColorDenoiser(seed=4, precision="torch").cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(2, 3, 64, 256, device="cuda", generator=g)                   # quarter-resolution rows of 128 pixels
+    sig = 0.02 + 0.1 * torch.rand(2, device="cuda", generator=g)
+    w = torch.rand(2, 3, 64, 256, device="cuda", generator=g)
+
+    def grads(model_den, autocast=False):
+        for p_ in model_den.model.parameters():
+            p_.grad = None
+        xa = x.clone().requires_grad_(True)
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = model_den.model(xa, sig)
+            loss = (y.float() * w).sum()
+        else:
+            loss = (model_den._denoise(xa, sig) * w).sum()
+        loss.backward()
+        return [p_.grad.detach().clone() for p_ in model_den.model.parameters()], xa.grad.detach().clone(), float(loss)
+
+    ours_p, ours_x, ours_l = grads(den)
+    assert den._native is not None                                              # the native training path ran
+    ref_p, ref_x, ref_l = grads(ref)
+    t16_p, t16_x, _ = grads(ref, autocast=True)
+    assert abs(ours_l - ref_l) < 1e-2 * abs(ref_l)
+    assert rel(ours_x, ref_x) < 1.15 * rel(t16_x, ref_x) + 1e-2
+    for i, (a, b, c) in enumerate(zip(ours_p, ref_p, t16_p)):
+        assert a.shape == b.shape
+        assert rel(a, b) < 1.25 * rel(c, b) + 2e-2, (i, rel(a, b), rel(c, b))
+    # one optimizer step moves the native network too (the filter banks are re-packed from the updated weights)
+    y0 = den.denoise(x, sig).clone()
+    with torch.no_grad():
+        for p_ in den.model.parameters():
+            p_.add_(0.05 * torch.sign(p_))
+    xa = x.clone().requires_grad_(True)
+    y1 = den._denoise(xa, sig)
+    assert rel(y1, y0) > 1e-3
