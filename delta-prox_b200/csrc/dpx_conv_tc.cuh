@@ -3,7 +3,7 @@
 //
 // Formulation.  Implicit GEMM  D[pixel, cout] = sum_{tap, cin} A_tap[pixel, cin] * W_tap[cout, cin]  with
 //   * activations in HBM as channel-group-major bf16 with one explicit zero column on either side of every row,
-//       X[n][cg][h][W + 2][8]   (cg = channel / 8: 16 bytes per pixel and group; image pixel x lives at index x + 1),
+//       X[n][cg][h][row_pitch(W)][8]   (cg = channel / 8: 16 bytes per pixel and group; image pixel x lives at index x + 1),
 //   * one MMA = 2 x 128 pixels of one image row each, issued for a CTA PAIR (tcgen05 cta_group::2, M = 256, N = cout): each
 //     CTA owns 128 pixels (its TMEM lanes) and HALF of the filter bank (N/2 output channels), so the whole 3x3xCinxCout
 //     filter (162 KB for 96 -> 96) stays RESIDENT in shared memory for the lifetime of the kernel,
@@ -41,6 +41,10 @@ namespace dpx {
 namespace convtc {
 
 constexpr int TILE_PX = 128;             // output pixels per CTA and tile row (= UMMA M per CTA)
+// pixels per padded row of an activation tensor: one zero column on either side, and the row is extended with zeros to a whole
+// number of 128-pixel tiles so that a staged 130-pixel run never reaches into the next row (the weight-gradient kernel SUMS over
+// every staged pixel; the forward kernel merely discarded what it computed from the overhang)
+__host__ __device__ constexpr int row_pitch(int W) { return (W + TILE_PX - 1) / TILE_PX * TILE_PX + 2; }
 constexpr int HALO_PX = TILE_PX + 2;     // staged pixels per row
 constexpr int ROW_BLOCK = 16;            // output rows per work unit
 constexpr int NSLOT = 5;                 // activation row slots in the ring (3 live + 2 in flight)
@@ -340,7 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg<CGIN, COUT, SPL
     const int part = (warp - 2) >> 2;                          // which half of the output channels
     const int m = quad * 32 + lane;                            // pixel of the tile
     const int cbase = part * C::EPI_COLS;
-    const int Wp = P.W + 2;
+    const int Wp = row_pitch(P.W);
     uint32_t acc_it = 0;
     for (int u = cluster_id; u < n_units; u += n_clusters) {
       const Unit t = unit_of(P, u, rank);

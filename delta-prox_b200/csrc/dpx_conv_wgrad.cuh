@@ -4,7 +4,7 @@
 //
 // Formulation.  A GEMM whose REDUCTION dimension is the pixel: per 128-pixel piece of an image row and per tap
 //     D_tap[co, ci] += GY[pixel, co]^T  A_tap[pixel, ci]          (M = 128 >= C_out, N = C_in, K = 128 pixels = 8 MMAs of K = 16).
-// Both operands are the channel-group-major activation tensors the forward kernel reads and writes, [N][C/8][h][W + 2][8] bf16:
+// Both operands are the channel-group-major activation tensors the forward kernel reads and writes, [N][C/8][h][row_pitch(W)][8] bf16:
 // for one pixel the 8 channels of a group are 16 contiguous bytes and consecutive pixels follow at 16 bytes -- exactly the
 // canonical MN-MAJOR shared-memory operand of tcgen05.mma without swizzle (an 8 pixel x 8 channel core matrix = 128 contiguous
 // bytes; next 8 pixels +128 B = the descriptor's leading-dimension byte offset; next channel group + one staged row of a group =
@@ -17,9 +17,8 @@
 //     garbage and ignored (each row of D depends on its own row of GY^T only); the gy ring is followed by the a ring, so the
 //     over-read stays inside initialised shared memory.
 //   * at the end each CTA adds its tiles to dW (fp32, global atomics: 148 x 2 CTAs x 9 x 96 x 96 values).
-// Requirement: the padded row must contain every staged 130-pixel run, i.e. W % 128 == 0 (a run that spills into the next row
-// would feed foreign pixels into the sum; the forward kernel may ignore that because it discards those outputs).  Other widths
-// use the framework's weight gradient (dprox_b200/denoisers.py).
+// Every staged pixel enters the sum, so a run must never reach into the next row: the padded rows are extended with zeros to a
+// whole number of 128-pixel tiles (row_pitch), and pixels beyond the image width are never written by any producer.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2..5 = final read-out.
 #pragma once
 #include "dpx_conv_tc.cuh"

@@ -44,7 +44,7 @@ EncodeTiledFn encode_tiled() {
 int make_row_map(CUtensorMap* map, const void* ptr, int N, int CG, int H, int W, int box_planes = 0) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DPX_ERR_CUDA; }
-  const cuuint64_t Wp = (cuuint64_t)W + 2;
+  const cuuint64_t Wp = (cuuint64_t)convtc::row_pitch(W);
   const cuuint64_t dims[5] = {(cuuint64_t)convtc::HALO_PX, 2, Wp, (cuuint64_t)H, (cuuint64_t)N * CG};
   const cuuint64_t strides[4] = {(cuuint64_t)convtc::HALO_PX * 8, 16, Wp * 16, (cuuint64_t)H * Wp * 16};
   const cuuint32_t box[5] = {(cuuint32_t)convtc::HALO_PX, 2, 1, 1, (cuuint32_t)(box_planes ? box_planes : CG)};
@@ -58,7 +58,7 @@ int make_row_map(CUtensorMap* map, const void* ptr, int N, int CG, int H, int W,
 
 // elements of a padded activation buffer: rows of W + 2 pixels, plus slack for the last tile's overhang (a 130-pixel run that
 // starts inside the last row may end up to 129 pixels past it)
-inline size_t padded_elems(int N, int C, int H, int W) { return ((size_t)N * (C / 8) * H * (W + 2) + 256) * 8; }
+inline size_t padded_elems(int N, int C, int H, int W) { return ((size_t)N * (C / 8) * H * convtc::row_pitch(W) + 256) * 8; }
 
 // nn.Conv2d weight [Cout,Cin,3,3] fp32 -> the shared-memory image of the kernel: [half][tap][cg][n][8] bf16, zero padded.
 // transpose = 1 builds the data-gradient filter  Wd[ci][co][ky][kx] = W[co][ci][2-ky][2-kx]  (roles of cin / cout swapped).
@@ -101,8 +101,8 @@ __global__ void k_unshuffle_in(const float* __restrict__ x, const float* __restr
       }
   v[12] = __float2bfloat16(sigma[sigma_per_sample ? b : 0]);
   v[13] = v[14] = v[15] = __float2bfloat16(0.f);
-  const size_t plane = (size_t)h2 * (w2 + 2);
-  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
   *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(v)[0];
   *reinterpret_cast<uint4*>(out + o + plane * 8) = reinterpret_cast<const uint4*>(v)[1];
 }
@@ -113,8 +113,8 @@ __global__ void k_shuffle_out(const __nv_bfloat16* __restrict__ in, float* __res
   const size_t total = (size_t)B * h2 * w2;
   if (i >= total) return;
   const int w = (int)(i % w2), h = (int)((i / w2) % h2), b = (int)(i / ((size_t)w2 * h2));
-  const size_t plane = (size_t)h2 * (w2 + 2);
-  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
   __align__(16) __nv_bfloat16 v[16];
   reinterpret_cast<uint4*>(v)[0] = *reinterpret_cast<const uint4*>(in + o);
   reinterpret_cast<uint4*>(v)[1] = *reinterpret_cast<const uint4*>(in + o + plane * 8);
@@ -146,8 +146,8 @@ __global__ void k_shuffle_out_bwd(const float* __restrict__ gy, __nv_bfloat16* _
         v[c * 4 + dy * 2 + dx] = __float2bfloat16((yy < H && xx < W) ? gy[(((size_t)b * 3 + c) * H + yy) * W + xx] : 0.f);
       }
   v[12] = v[13] = v[14] = v[15] = __float2bfloat16(0.f);
-  const size_t plane = (size_t)h2 * (w2 + 2);
-  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
   *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(v)[0];
   *reinterpret_cast<uint4*>(out + o + plane * 8) = reinterpret_cast<const uint4*>(v)[1];
 }
@@ -163,8 +163,8 @@ __global__ void k_unshuffle_in_bwd(const __nv_bfloat16* __restrict__ g16, float*
   if (i < total) {
     const int w = (int)(i % w2), h = (int)((i / w2) % h2);
     b = (int)(i / ((size_t)w2 * h2));
-    const size_t plane = (size_t)h2 * (w2 + 2);
-    const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+    const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+    const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
     __align__(16) __nv_bfloat16 v[16];
     reinterpret_cast<uint4*>(v)[0] = *reinterpret_cast<const uint4*>(g16 + o);
     reinterpret_cast<uint4*>(v)[1] = *reinterpret_cast<const uint4*>(g16 + o + plane * 8);
@@ -258,7 +258,7 @@ __global__ void k_unshuffle_in_split(const float* __restrict__ x, const float* _
       }
   split_half(sigma[sigma_per_sample ? b : 0], vh[12], vl[12]);
   vh[13] = vh[14] = vh[15] = vl[13] = vl[14] = vl[15] = __float2half_rn(0.f);
-  const size_t plane = (size_t)h2 * (w2 + 2) * 8, px = ((size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2) * 8, px = ((size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     *reinterpret_cast<uint4*>(out + piece_plane(b, g, 0, 2, 2) * plane + px) = reinterpret_cast<const uint4*>(vh)[g];
@@ -272,8 +272,8 @@ __global__ void k_shuffle_out32(const float* __restrict__ in, float* __restrict_
   const size_t total = (size_t)B * h2 * w2;
   if (i >= total) return;
   const int w = (int)(i % w2), h = (int)((i / w2) % h2), b = (int)(i / ((size_t)w2 * h2));
-  const size_t plane = (size_t)h2 * (w2 + 2);
-  const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+  const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
   float v[16];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -308,7 +308,7 @@ __global__ void k_shuffle_out_bwd_split(const float* __restrict__ gy, __half* __
         split_half((yy < H && xx < W) ? gy[(((size_t)b * 3 + c) * H + yy) * W + xx] : 0.f, vh[c * 4 + dy * 2 + dx], vl[c * 4 + dy * 2 + dx]);
       }
   vh[12] = vh[13] = vh[14] = vh[15] = vl[12] = vl[13] = vl[14] = vl[15] = __float2half_rn(0.f);
-  const size_t plane = (size_t)h2 * (w2 + 2) * 8, px = ((size_t)h * (w2 + 2) + w + 1) * 8;
+  const size_t plane = (size_t)h2 * convtc::row_pitch(w2) * 8, px = ((size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     *reinterpret_cast<uint4*>(out + piece_plane(b, g, 0, 2, 2) * plane + px) = reinterpret_cast<const uint4*>(vh)[g];
@@ -326,8 +326,8 @@ __global__ void k_unshuffle_in_bwd32(const float* __restrict__ g32, float* __res
   if (i < total) {
     const int w = (int)(i % w2), h = (int)((i / w2) % h2);
     b = (int)(i / ((size_t)w2 * h2));
-    const size_t plane = (size_t)h2 * (w2 + 2);
-    const size_t o = ((size_t)b * 2 * plane + (size_t)h * (w2 + 2) + w + 1) * 8;
+    const size_t plane = (size_t)h2 * convtc::row_pitch(w2);
+    const size_t o = ((size_t)b * 2 * plane + (size_t)h * convtc::row_pitch(w2) + w + 1) * 8;
     float v[16];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -377,7 +377,7 @@ __global__ void k_nchw_to_split(const float* __restrict__ x, __half* __restrict_
   const int c = cg * 8 + c8;
   __half hi, lo;
   split_half(c < Cc ? x[(((size_t)b * Cc + c) * H + h) * W + w] : 0.f, hi, lo);
-  const size_t plane = (size_t)H * (W + 2) * 8, px = ((size_t)h * (W + 2) + w + 1) * 8 + c8;
+  const size_t plane = (size_t)H * convtc::row_pitch(W) * 8, px = ((size_t)h * convtc::row_pitch(W) + w + 1) * 8 + c8;
   out[piece_plane(b, cg, 0, CG, kp) * plane + px] = hi;
   out[piece_plane(b, cg, 1, CG, kp) * plane + px] = lo;
 }
@@ -390,7 +390,7 @@ __global__ void k_c8f32_to_nchw(const float* __restrict__ in, float* __restrict_
   const int h = (int)(r % H); r /= H;
   const int c = (int)(r % Cc);
   const int b = (int)(r / Cc);
-  y[i] = in[((((size_t)b * CG + c / 8) * H + h) * (W + 2) + w + 1) * 8 + c % 8];
+  y[i] = in[((((size_t)b * CG + c / 8) * H + h) * convtc::row_pitch(W) + w + 1) * 8 + c % 8];
 }
 
 // fp32 NCHW <-> channel-group-major bf16 (per-layer debug entry)
@@ -405,7 +405,7 @@ __global__ void k_nchw_to_c8(const float* __restrict__ x, __nv_bfloat16* __restr
   const int cg = (int)(r % CG);
   const int b = (int)(r / CG);
   const int c = cg * 8 + c8;
-  out[((((size_t)b * CG + cg) * H + h) * (W + 2) + w + 1) * 8 + c8] = __float2bfloat16(c < Cc ? x[(((size_t)b * Cc + c) * H + h) * W + w] : 0.f);
+  out[((((size_t)b * CG + cg) * H + h) * convtc::row_pitch(W) + w + 1) * 8 + c8] = __float2bfloat16(c < Cc ? x[(((size_t)b * Cc + c) * H + h) * W + w] : 0.f);
 }
 __global__ void k_c8_to_nchw(const __nv_bfloat16* __restrict__ in, float* __restrict__ y, int B, int Cc, int CG, int H, int W) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,7 +416,7 @@ __global__ void k_c8_to_nchw(const __nv_bfloat16* __restrict__ in, float* __rest
   const int h = (int)(r % H); r /= H;
   const int c = (int)(r % Cc);
   const int b = (int)(r / Cc);
-  y[i] = __bfloat162float(in[((((size_t)b * CG + c / 8) * H + h) * (W + 2) + w + 1) * 8 + c % 8]);
+  y[i] = __bfloat162float(in[((((size_t)b * CG + c / 8) * H + h) * convtc::row_pitch(W) + w + 1) * 8 + c % 8]);
 }
 
 template <int CGIN, int COUT>
@@ -499,7 +499,7 @@ __global__ void k_wgrad_unpack(const float* __restrict__ dw, float* __restrict__
 __global__ void k_bias_grad(const __nv_bfloat16* __restrict__ gy, float* __restrict__ db, int CG, int H, int W, int cout) {
   const int row = blockIdx.x;                                   // (n * CG + cg) * H + y
   const int cg = (row / H) % CG;
-  const __nv_bfloat16* src = gy + (size_t)row * (W + 2) * 8;
+  const __nv_bfloat16* src = gy + (size_t)row * convtc::row_pitch(W) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
     const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(x + 1) * 8);
@@ -517,7 +517,6 @@ __global__ void k_bias_grad(const __nv_bfloat16* __restrict__ gy, float* __restr
 template <int CGG, int CGA>
 int launch_wgrad(const __nv_bfloat16* gy, const __nv_bfloat16* a, float* dw, int cout, int N, int H, int W, cudaStream_t s) {
   using C = convtc::WgCfg<CGG, CGA>;
-  DPX_REQUIRE(W % convtc::TILE_PX == 0, "native weight gradient needs a row length that is a multiple of 128 (got %d)", W);
   static bool attr_set = false;
   if (!attr_set) {
     DPX_CUDA(cudaFuncSetAttribute(convtc::k_conv3x3_wgrad<CGG, CGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -529,7 +528,7 @@ int launch_wgrad(const __nv_bfloat16* gy, const __nv_bfloat16* a, float* dw, int
   if (rc) return rc;
   convtc::WgParams P;
   P.dw = dw; P.cout = cout; P.N = N; P.H = H; P.W = W;
-  P.x_tiles = W / convtc::TILE_PX;
+  P.x_tiles = (W + convtc::TILE_PX - 1) / convtc::TILE_PX;
   P.row_blocks = (H + convtc::ROW_BLOCK - 1) / convtc::ROW_BLOCK;
   P.n_tiles = N * P.x_tiles * P.row_blocks;
   int dev = 0, sms = 0;
@@ -881,13 +880,12 @@ int dpx_ffdnet_backward(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_si
 }
 
 // Same, and the gradients w.r.t. every layer's weights and biases (training the denoiser): gw[l] device fp32 [cout,cin,3,3],
-// gb[l] device fp32 [cout] (gb or its entries may be NULL).  bf16 precision only; needs ceil(W / 2) % 128 == 0.
+// gb[l] device fp32 [cout] (gb or its entries may be NULL).  bf16 precision only.
 int dpx_ffdnet_backward_params(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample, float* const* gw,
                                float* const* gb, int B, int H, int W, void* stream) {
   DPX_REQUIRE(n && g_y && g_x && gw, "null argument");
   DPX_REQUIRE(n->precision == 0, "the weight gradient runs in the bf16 mode only");
   const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
-  DPX_REQUIRE(w2 % convtc::TILE_PX == 0, "native weight gradient needs ceil(W / 2) %% 128 == 0 (got %d)", w2);
   DPX_REQUIRE(n->saved && n->saved_B == B && n->saved_h2 == h2 && n->saved_w2 == w2,
               "dpx_ffdnet_backward_params needs the activations of a matching dpx_ffdnet_forward_train call");
   return backward_bf16(n, g_y, g_x, g_sigma, sigma_per_sample, gw, gb, B, H, W, (cudaStream_t)stream);

@@ -161,7 +161,7 @@ class NativeFFDNet:
 
     def wgrad_layer(self, layer: int, x: torch.Tensor, gy: torch.Tensor):
         """(dL/dW, dL/db) of one convolution given its input `x` and the gradient `gy` w.r.t. its pre-activation output, on the
-        tensor-core weight-gradient kernel (csrc/dpx_conv_wgrad.cuh; bf16 operands; needs a width that is a multiple of 128)"""
+        tensor-core weight-gradient kernel (csrc/dpx_conv_wgrad.cuh; bf16 operands)"""
         cabi = self._cabi
         x, gy = cabi.require_cuda_f32(x, "x"), cabi.require_cuda_f32(gy, "gy")
         B, cin, H, W = x.shape
@@ -292,22 +292,13 @@ class FFDNetColorDenoiser(Denoiser):
             return _NativeFFDNetFn.apply(x.contiguous(), sigma, self._native_net(x.device))
         if native and not wants_grad:
             return self._native_net(x.device)(x, sigma)
-        if self.precision == "bf16" and ((x.shape[-1] + 1) // 2) % 128 == 0:
-            # trainable denoiser weights: forward, data gradient AND weight gradient on the native kernels (the weight-gradient
-            # kernel needs quarter-resolution rows that are a multiple of 128 pixels; other widths take the branch below)
+        if self.precision == "bf16":
+            # trainable denoiser weights: forward, data gradient AND weight gradient on the native tensor-core kernels
             convs = [m for m in self.model.model if isinstance(m, nn.Conv2d)]
             params = []
             for c in convs:
                 params += [c.weight, c.bias]
             return _NativeFFDNetTrainFn.apply(x.contiguous(), sigma, self._native_net(x.device), convs, *params)
-        if self.precision == "bf16":
-            # trainable denoiser weights at a width the native weight-gradient kernel does not take: the tape runs through the
-            # framework's convolutions with bf16 operands / fp32 accumulation
-            if not getattr(self, "_nhwc", False):          # NHWC weights: cuDNN's tensor-core kernels for forward, dgrad and wgrad
-                self.model.to(memory_format=torch.channels_last)
-                self._nhwc = True
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                return self.model(x.contiguous(memory_format=torch.channels_last), sigma).float().contiguous()
         # framework fp32 convolutions (no TF32): trainable weights at fp32, or precision='torch'
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False

@@ -283,7 +283,7 @@ int dpx_ffdnet_backward(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_
                         int W, void* stream);
 /* dpx_ffdnet_backward plus the gradients w.r.t. every layer's parameters (training the denoiser's weights without leaving
  * native code): gw[l] device fp32 [cout,cin,3,3] (nn.Conv2d layout), gb[l] device fp32 [cout]; gb or entries of it may be NULL.
- * Weight gradient on the MN-major tcgen05 kernel (csrc/dpx_conv_wgrad.cuh).  bf16 precision; needs ceil(W / 2) % 128 == 0. */
+ * Weight gradient on the MN-major tcgen05 kernel (csrc/dpx_conv_wgrad.cuh).  bf16 precision. */
 int dpx_ffdnet_backward_params(dpx_ffdnet* net, const float* g_y, float* g_x, float* g_sigma, int sigma_per_sample,
                                float* const* gw, float* const* gb, int B, int H, int W, void* stream);
 /* One convolution layer on fp32 NCHW tensors (per-layer parity tests): direction 0 = forward (+bias, optional ReLU),
@@ -293,7 +293,7 @@ int dpx_ffdnet_conv_layer(dpx_ffdnet* net, int layer, int direction, int relu, c
 /* Weight and bias gradient of one layer on fp32 NCHW tensors (torch: conv2d's grad_weight / grad_bias; network_ffdnet.py:27-68
  * under training): x [B,cin,H,W] = the layer's input, gy [B,cout,H,W] = gradient w.r.t. its pre-activation output;
  * gw [cout,cin,3,3], gb [cout] (may be NULL).  tcgen05 kernel with MN-major operands (csrc/dpx_conv_wgrad.cuh), bf16 operands,
- * fp32 accumulation in TMEM over all pixels.  Needs W % 128 == 0. */
+ * fp32 accumulation in TMEM over all pixels. */
 int dpx_ffdnet_wgrad_layer(dpx_ffdnet* net, int layer, const float* x, const float* gy, float* gw, float* gb, int B, int H, int W,
                            void* stream);
 

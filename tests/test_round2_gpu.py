@@ -530,7 +530,7 @@ def test_tcgen05_weight_gradient_matches_conv2d_grad(dp):
     bf = lambda t: t.to(torch.bfloat16).double()
     for layer in (0, 3, len(convs) - 1):
         c = convs[layer]
-        for shape in ((2, 40, 128), (1, 21, 256)):                      # 3 / 2 row blocks (one ragged), one / two 128-pixel tiles
+        for shape in ((2, 40, 128), (1, 21, 256), (1, 37, 300), (2, 18, 70)):   # ragged row blocks; widths that end inside a 128-pixel tile
             x = torch.randn(shape[0], c.in_channels, *shape[1:], generator=g).cuda()
             gy = torch.randn(shape[0], c.out_channels, *shape[1:], generator=g).cuda()
             gw, gb = net.wgrad_layer(layer, x, gy)
@@ -547,9 +547,9 @@ def test_native_ffdnet_training_gradients(dp):
     den = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
     ref = FFDNetColorDenoiser(seed=4, precision="torch").cuda()
     g = torch.Generator(device="cuda").manual_seed(5)
-    x = torch.rand(2, 3, 64, 256, device="cuda", generator=g)                   # quarter-resolution rows of 128 pixels
+    x = torch.rand(2, 3, 64, 180, device="cuda", generator=g)                   # quarter-resolution rows of 90 pixels: a partial tile
     sig = 0.02 + 0.1 * torch.rand(2, device="cuda", generator=g)
-    w = torch.rand(2, 3, 64, 256, device="cuda", generator=g)
+    w = torch.rand(2, 3, 64, 180, device="cuda", generator=g)
 
     def grads(model_den, autocast=False):
         for p_ in model_den.model.parameters():
