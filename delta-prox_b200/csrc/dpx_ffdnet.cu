@@ -495,22 +495,35 @@ __global__ void k_wgrad_unpack(const float* __restrict__ dw, float* __restrict__
   const float v = dw[((size_t)tap * 128 + co) * N + ci];
   gw[i] = accumulate ? gw[i] + v : v;
 }
-// bias gradient: db[co] = sum over pixels of gy (channel-group-major bf16 input), one block per (image, group, row)
-__global__ void k_bias_grad(const __nv_bfloat16* __restrict__ gy, float* __restrict__ db, int CG, int H, int W, int cout) {
-  const int row = blockIdx.x;                                   // (n * CG + cg) * H + y
-  const int cg = (row / H) % CG;
-  const __nv_bfloat16* src = gy + (size_t)row * convtc::row_pitch(W) * 8;
+// bias gradient: db[co] = sum over pixels of gy (channel-group-major bf16 input).  grid (CG, slices): a block walks the rows of one
+// channel group with a stride, keeps 8 partial sums per thread and ends with ONE atomic per channel (a block per row with a warp-level
+// atomic each was 740 us per layer -- 0.8 M atomics on 96 addresses -- against 420 us for the weight gradient itself)
+__global__ void k_bias_grad(const __nv_bfloat16* __restrict__ gy, float* __restrict__ db, int NB, int CG, int H, int W, int cout) {
+  __shared__ float red[8][8];
+  const int cg = blockIdx.x;
+  const int pitch = convtc::row_pitch(W);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(x + 1) * 8);
-    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v);
+  for (int r = blockIdx.y; r < NB * H; r += gridDim.y) {
+    const int n = r / H, y = r - n * H;
+    const __nv_bfloat16* src = gy + (((size_t)n * CG + cg) * H + y) * pitch * 8;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(x + 1) * 8);
+      const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(b[e]);
+      for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(b[e]);
+    }
   }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float s = warp_sum(acc[e]);
-    if ((threadIdx.x & 31) == 0 && cg * 8 + e < cout) atomicAdd(db + cg * 8 + e, s);
+    if (lane == 0) red[warp][e] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    if (cg * 8 + threadIdx.x < cout) atomicAdd(db + cg * 8 + threadIdx.x, s);
   }
 }
 
@@ -841,7 +854,7 @@ static int backward_bf16(dpx_ffdnet* n, const float* g_y, float* g_x, float* g_s
     DPX_LAUNCH_CHECK();
     if (gb && gb[l]) {
       DPX_CUDA(cudaMemsetAsync(gb[l], 0, sizeof(float) * cout, s));
-      k_bias_grad<<<B * (cout_pad / 8) * h2, 128, 0, s>>>(gy, gb[l], cout_pad / 8, h2, w2, cout);
+      k_bias_grad<<<dim3(cout_pad / 8, 48), 256, 0, s>>>(gy, gb[l], B, cout_pad / 8, h2, w2, cout);
       DPX_LAUNCH_CHECK();
     }
     return DPX_OK;
@@ -994,7 +1007,7 @@ int dpx_ffdnet_wgrad_layer(dpx_ffdnet* n, int layer, const float* x, const float
     ++g_launches;
     if (gb) {
       DPX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * cout, s));
-      k_bias_grad<<<B * (cout_pad / 8) * H, 128, 0, s>>>(g, gb, cout_pad / 8, H, W, cout);
+      k_bias_grad<<<dim3(cout_pad / 8, 48), 256, 0, s>>>(g, gb, B, cout_pad / 8, H, W, cout);
       ++g_launches;
     }
   }
