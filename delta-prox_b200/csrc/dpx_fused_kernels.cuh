@@ -613,8 +613,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
 // flight at once without holding registers or L1 lines -- and pass A runs in place (measured +2.8 % on the headline workload
 // against register-fed 2 x 16 loads per thread, +6.5 % at 4096 points; -1.4 ... -4 % for tiles of 1024 points and fewer, whose
 // CTAs are short enough for their co-resident siblings to cover the load; profiles/README.md round 2) -- hence by tile size.
+// Residency: tiles up to 1280 points leave room for FOUR co-resident CTAs (32 warps per SM) if the kernel stays within 64 registers,
+// which it does without spilling: +2-4 % at 512 ... 1024 points (0.602 -> 0.615 at 1024^2); longer tiles keep three.
 template <class TH, bool STAGE = (TH::N >= 2048)>
-__global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 3 <= 225 * 1024) ? 3 : 1) k_col(ColParams P) {
+__global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 4 <= 200 * 1024) ? 4 : ((TH::SMEM_FLOAT2 * sizeof(float2) * 3 <= 225 * 1024) ? 3 : 1)) k_col(ColParams P) {
   static_assert(TH::COLS == CG, "column tile holds CG columns");
   constexpr int H = TH::N, RA = TH::RA, RC = TH::RC, MA = TH::MA;
   DPX_DYN_SMEM(float2, sm);
