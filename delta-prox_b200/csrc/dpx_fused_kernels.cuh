@@ -1052,7 +1052,8 @@ struct RowZPersistSmem {
   static constexpr int STS_OFF = (TW::SMEM_FLOAT2 + 15) / 16 * 16;   // float2 offset of the stage: 128-byte aligned (TMA tensor loads land there)
   static constexpr size_t BYTES = (STS_OFF + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t) + 16;   // + next-tile slot
   // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
-  static constexpr int CTAS_PER_SM = (TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2;
+  // ... and a fourth up to 768 points (64 registers; 0.577 -> 0.613 at 768^2; at 1024 points the 64-register version spills and loses)
+  static constexpr int CTAS_PER_SM = (TW::N <= 768 && BYTES * 4 <= 225 * 1024) ? 4 : ((TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2);
 };
 
 struct RowZTile { int pp, h0, pA, pB; };
