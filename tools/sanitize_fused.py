@@ -33,3 +33,21 @@ y = den._denoise(xx, torch.tensor([0.05], device="cuda"))
 y.sum().backward()
 torch.cuda.synchronize()
 print("ffdnet split", float(y.abs().mean()), float(xx.grad.abs().mean()))
+
+# bf16 training path: forward_train, data gradient, MN-major tcgen05 weight gradient (ragged width: partial 128-pixel tile)
+dent = FFDNetColorDenoiser(seed=4, precision="bf16").cuda()
+xt = torch.rand(1, 3, 40, 150, device="cuda").requires_grad_(True)
+yt = dent._denoise(xt, torch.tensor([0.05], device="cuda"))
+yt.sum().backward()
+torch.cuda.synchronize()
+print("ffdnet train", float(yt.abs().mean()), float(sum(p.grad.abs().sum() for p in dent.model.parameters())))
+
+# staged x-update path (external prox between the stages): persistent PM_FIRST / PM_XONLY row kernels
+xv = dp.Variable()
+bb = torch.rand(2, 3, 64, 128, device="cuda")
+prior = dp.deep_prior(xv, denoiser=FFDNetColorDenoiser(seed=4, precision="bf16").cuda().requires_grad_(False))
+sv = dp.compile(dp.sum_squares(dp.conv(xv, psf) - bb) + prior, method="admm", device="cuda")
+with torch.no_grad():
+    ov = sv.solve(x0=bb, rhos=1.0, lams=0.05, max_iter=2)
+torch.cuda.synchronize()
+print("pnp staged", float(ov.abs().mean()))
