@@ -456,6 +456,8 @@ def main():
     ap.add_argument("--stop-leg", type=int, default=1, help="0: skip the residual-stop leg (the path's only collective, untimed extra)")
     ap.add_argument("--denoiser", default="fp32", choices=["fp32", "bf16"],
                     help="cfg2: FFDNet precision on the tensor cores: fp32 = fp16 operand pairs (1e-5 parity bar), bf16 = fast mode")
+    ap.add_argument("--train-denoiser", action="store_true",
+                    help="cfg5: the FFDNet weights are trained too (native weight-gradient kernel) instead of frozen")
     ap.add_argument("--workload", default="headline", choices=["headline", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json configs: headline = configs[1]-shape batch (default); cfg1 = single 256x256 ADMM x 50; cfg2 = PnP "
                          "deconv with the deep denoiser; cfg3 = CS-MRI + TV with PCG; cfg4 = HQS 8 x 1024^2 per GPU; cfg5 = unrolled training step")

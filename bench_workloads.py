@@ -388,14 +388,15 @@ def run_cfg5(args):
     doe = build_doe_model(DOEModelConfig(patch_size=psf_n, wave_resolution=(2 * psf_n, 2 * psf_n))).to(dev)
     r0, s0 = dp.log_descent(49, 7.65, T, sigma=7.65 / 255)
     rhos, sigmas = torch.nn.Parameter(r0.to(dev)), torch.nn.Parameter(s0.to(dev))
-    params = [doe.height_map.height_map_sqrt, rhos, sigmas]
-    opt = torch.optim.Adam(params, lr=1e-4)
-    den = FFDNetColorDenoiser(seed=4, precision="bf16").to(dev).requires_grad_(False)
+    train_den = bool(getattr(args, "train_denoiser", False))
+    den = FFDNetColorDenoiser(seed=4, precision="bf16").to(dev).requires_grad_(train_den)
+    params = [doe.height_map.height_map_sqrt, rhos, sigmas] + (list(den.model.parameters()) if train_den else [])
+    opt = torch.optim.Adam(params, lr=1e-4 if not train_den else 1e-6)
     den._native = NativeFFDNet(den.model, dev)
     timer = _TimedDenoiser(den._native).install()
     x, y, PSF = dp.Variable(), dp.Placeholder(), dp.Placeholder()
     data_term = dp.sum_squares(dp.conv_doe(x, PSF, circular=True), y)
-    reg_term = dp.deep_prior(x, denoiser=den, sqrt=True)
+    reg_term = dp.deep_prior(x, denoiser=den, sqrt=True, trainable=train_den)
     solver = dp.specialize(dp.compile(data_term + reg_term, method="admm", device=dev), method="unroll", max_iter=T)
     gt_host = torch.rand(Bn, 3, H, H).pin_memory()
     gt_dev = gt_host.to(dev)
@@ -456,7 +457,8 @@ def run_cfg5(args):
         if not args.skip_cpu:
             cpu = _cfg5_cpu(H, psf_n, T, os.cpu_count() or 1)
         nbytes = sum(p.numel() for p in params) * 4
-        wl = {"workload": f"cfg5: unrolled {T}-iteration ADMM (conv_doe + deep_prior(ffdnet_color, sqrt), bf16 tcgen05 denoiser, frozen) train step "
+        dmode = "TRAINED: data + weight + bias gradients on the native kernels" if train_den else "frozen"
+        wl = {"workload": f"cfg5: unrolled {T}-iteration ADMM (conv_doe + deep_prior(ffdnet_color, sqrt), bf16 tcgen05 denoiser, {dmode}) train step "
                           f"with DOE optics model, backward and Adam, {Bn} x [3,{H},{H}] per GPU, psf {psf_n}", "batch_per_gpu": Bn,
               "iters_per_step": T, "l2_policy": "denoiser activations (11 x 28 MB saved per call) and the 2244^2 Fresnel fields exceed L2",
               "parallelism": f"dp{D.world}: NCCL all-reduce of {nbytes / 1e6:.1f} MB of gradients per step ({ar_ms:.3f} ms on the launching stream)",
