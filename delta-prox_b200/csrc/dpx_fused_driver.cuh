@@ -48,8 +48,8 @@ DPX_TILE_FOR(2160, 15, 9, 16)
 #define DPX_W_SIZES(X) X(2048)
 #define DPX_H_ONLY_SIZES(X)
 #elif defined(DPX_EMU)                                 // CPU emulator build (tests/emu): the sizes its tests run, one per radix family
-#define DPX_W_SIZES(X) X(64) X(128) X(256) X(1024) X(192) X(384) X(320) X(640) X(1280) X(960) X(1920)
-#define DPX_H_ONLY_SIZES(X) X(1080)
+#define DPX_W_SIZES(X) X(64) X(128) X(256) X(1024) X(192) X(384) X(320) X(640) X(1280) X(960) X(1920) X(2560)
+#define DPX_H_ONLY_SIZES(X) X(1080) X(4096)            // 2560-point rows / 4096-point columns: the 512-thread, one-CTA-per-SM tiles
 #else
 #define DPX_W_SIZES(X)                                                                                                          \
   X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(192) X(384) X(768) X(1536) X(3072) X(320) X(640) X(1280) X(2560) X(960) \

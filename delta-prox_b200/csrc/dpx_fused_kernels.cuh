@@ -33,6 +33,9 @@ namespace fused {
 constexpr int CG = 4;            // spectrum columns per column tile
 constexpr int ROWS = 4;          // image rows per row tile (2 pairs)
 constexpr int kThreads = 256;
+// column tiles so long that only ONE fits an SM (3840 and 4096 points: 139 / 148 KB) run 512 threads per CTA: 16 warps per SM
+// instead of 8 (tiles up to 3072 points are co-resident two to four at a time with 256 threads each)
+template <class TH> struct ColThreads { static constexpr int value = (TH::SMEM_FLOAT2 * 8 * 2 > 225 * 1024) ? 512 : kThreads; };
 constexpr int kPrefetchAhead = 148 * 3;   // ~ number of k_col CTAs resident on the chip
 constexpr int kPrefetchAhead4 = 148 * 4;  // ~ number of k_row CTAs resident on the chip
 
@@ -616,9 +619,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
 // Residency: tiles up to 1280 points leave room for FOUR co-resident CTAs (32 warps per SM) if the kernel stays within 64 registers,
 // which it does without spilling: +2-4 % at 512 ... 1024 points (0.602 -> 0.615 at 1024^2); longer tiles keep three.
 template <class TH, bool STAGE = (TH::N >= 2048)>
-__global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 4 <= 200 * 1024) ? 4 : ((TH::SMEM_FLOAT2 * sizeof(float2) * 3 <= 225 * 1024) ? 3 : 1)) k_col(ColParams P) {
+__global__ void __launch_bounds__(ColThreads<TH>::value, (TH::SMEM_FLOAT2 * sizeof(float2) * 4 <= 200 * 1024) ? 4 : ((TH::SMEM_FLOAT2 * sizeof(float2) * 3 <= 225 * 1024) ? 3 : 1)) k_col(ColParams P) {
   static_assert(TH::COLS == CG, "column tile holds CG columns");
-  constexpr int H = TH::N, RA = TH::RA, RC = TH::RC, MA = TH::MA;
+  constexpr int H = TH::N, RA = TH::RA, RC = TH::RC, MA = TH::MA, NTH = ColThreads<TH>::value;
   DPX_DYN_SMEM(float2, sm);
   const int tid = threadIdx.x;
   // grid = (B, G+1, C): the problems of the batch are adjacent in launch order, so the sum|OTF|^2 records of
@@ -640,11 +643,11 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
     __syncthreads();
     if (tid == 0) mbar_expect_tx(stage_bar, H * CG * sizeof(float2));
     __syncthreads();
-    for (int i = tid; i < H / 8; i += kThreads)
+    for (int i = tid; i < H / 8; i += NTH)
       bulk_load(sm + TH::pn(8 * i) * CG, tile + (size_t)i * 8 * CG, 8 * CG * sizeof(float2), stage_bar);
   } else if (STAGE) {
     // 16-byte pieces = columns (0,1) / (2,3) of one row, contiguous both in global memory and at the padded position
-    for (int i = tid; i < H * CG / 2; i += kThreads) {
+    for (int i = tid; i < H * CG / 2; i += NTH) {
       const int n = i >> 1, c2 = (i & 1) * 2;
       cp_async16(sm + TH::phys(n, c2), tile + (size_t)n * CG + c2);
     }
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
   }
   {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
     const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * NG + g) * H * CG);
-    for (int o = tid * 128; o < H * CG * 8; o += kThreads * 128) prefetch_l2(nf + o);
+    for (int o = tid * 128; o < H * CG * 8; o += NTH * 128) prefetch_l2(nf + o);
   }
 
   // ---- pass A of the forward FFT: in place on the staged tile, or fed straight from global memory ---------------------
@@ -664,9 +667,9 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
     }
     __syncthreads();
     if (tid == 0) trace_stamp(P.trace, rec, 2);
-    fft::smem_pass<TH, RA, H, false, true>(sm, twA, tid, kThreads);
+    fft::smem_pass<TH, RA, H, false, true>(sm, twA, tid, NTH);
   } else {
-    for (int t = tid; t < CG * MA; t += kThreads) {
+    for (int t = tid; t < CG * MA; t += NTH) {
       const int c = t % CG, j = t / CG;
       const int p0 = TH::phys(j, c);
       float2 a[RA], w[RA];
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
   }
   __syncthreads();
   if (tid == 0) trace_stamp(P.trace, rec, 3);
-  fft::smem_pass<TH, TH::RB, TH::MA, false, true>(sm, twB, tid, kThreads);
+  fft::smem_pass<TH, TH::RB, TH::MA, false, true>(sm, twB, tid, NTH);
   __syncthreads();
   if (tid == 0) trace_stamp(P.trace, rec, 4);
 
@@ -690,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
   const float rho = P.rho.p[(size_t)b * P.rho.stride + P.rho.it];
   const int pd = P.dq_batch > 1 ? p : p % P.C;
   const float den0 = rho * P.wid + P.eps;
-  for (int t = tid; t < CG * (H / RC); t += kThreads) {
+  for (int t = tid; t < CG * (H / RC); t += NTH) {
     const int c = t % CG, blk = t / CG;
     const int p0 = TH::phys(blk * RC, c);
     // constants of this block first (their DRAM/L2 latency overlaps the forward butterfly below): record [m/2][task]
@@ -735,12 +738,12 @@ __global__ void __launch_bounds__(kThreads, (TH::SMEM_FLOAT2 * sizeof(float2) * 
   }
   __syncthreads();
   if (tid == 0) trace_stamp(P.trace, rec, 5);
-  fft::smem_pass<TH, TH::RB, TH::MA, true, true>(sm, twB, tid, kThreads);
+  fft::smem_pass<TH, TH::RB, TH::MA, true, true>(sm, twB, tid, NTH);
   __syncthreads();
   if (tid == 0) trace_stamp(P.trace, rec, 6);
 
   // ---- inverse pass A, written straight to global memory ------------------------------------------------------------------
-  for (int t = tid; t < CG * MA; t += kThreads) {
+  for (int t = tid; t < CG * MA; t += NTH) {
     const int c = t % CG, j = t / CG;
     const int p0 = TH::phys(j, c);
     float2 a[RA], w[RA];
@@ -1053,7 +1056,11 @@ struct RowZPersistSmem {
   static constexpr size_t BYTES = (STS_OFF + STS_F2) * sizeof(float2) + 2 * ZR * RSU * sizeof(float) + 2 * sizeof(mbar_t) + 16;   // + next-tile slot
   // rows up to 1024 points leave room for a third co-resident CTA (24 instead of 16 warps per SM) at 85 registers per thread
   // ... and a fourth up to 768 points (64 registers; 0.577 -> 0.613 at 768^2; at 1024 points the 64-register version spills and loses)
-  static constexpr int CTAS_PER_SM = (TW::N <= 768 && BYTES * 4 <= 225 * 1024) ? 4 : ((TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2);
+  // rows from 3072 points (tile + stages > 113 KB) fit ONE CTA per SM: it runs 512 threads, so the SM keeps the 16 warps that two
+  // co-resident 256-thread CTAs give the 2048-point rows (8 warps per SM measured 0.47 of the roofline at 4096^2, 0.40 at 3840 x 2160)
+  static constexpr bool SOLO = BYTES * 2 > 225 * 1024;
+  static constexpr int THREADS = SOLO ? 512 : kThreads;
+  static constexpr int CTAS_PER_SM = SOLO ? 1 : ((TW::N <= 768 && BYTES * 4 <= 225 * 1024) ? 4 : ((TW::N <= 1024 && BYTES * 3 <= 225 * 1024) ? 3 : 2));
 };
 
 struct RowZTile { int pp, h0, pA, pB; };
@@ -1075,7 +1082,7 @@ DPX_HD void rowz_stage_S(const RowParams& P, const RowZTile& t, float2* stS, int
   // LDGSTS), so the spectrum rows are staged with 16-byte cp.async; the 8 KB dual rows below go through the TMA engine
   constexpr int G = TW::N / CG, SEG16 = ZR * CG * 8 / 16;
   const char* base = reinterpret_cast<const char*>(P.S + ((size_t)t.pp * G * P.H + t.h0) * CG);
-  for (int i = tid; i < G * SEG16; i += kThreads) {
+  for (int i = tid; i < G * SEG16; i += RowZPersistSmem<TW>::THREADS) {
     const int g = i / SEG16, ch = i % SEG16;
     cp_async16(reinterpret_cast<char*>(stS + g * (ZR * CG)) + ch * 16, base + (size_t)g * P.H * CG * sizeof(float2) + ch * 16);
   }
@@ -1111,13 +1118,13 @@ DPX_HD void rowz_stage_u(const RowParams& P, const RowZTile& t, float* stU, mbar
 // k_rowz<ROW_XONLY / ROW_FIRST> on the staged x-update path (TV objectives, deep priors) and at the start of every solve.
 enum PersistMode { PM_MID = 0, PM_LAST = 1, PM_XONLY = 2, PM_FIRST = 3 };
 template <class TW, int PM = PM_MID>
-__global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_rowz_mid_persist(RowParams P, int n_tiles) {
+__global__ void __launch_bounds__(RowZPersistSmem<TW>::THREADS, RowZPersistSmem<TW>::CTAS_PER_SM) k_rowz_mid_persist(RowParams P, int n_tiles) {
   constexpr bool LAST = PM == PM_LAST || PM == PM_XONLY;       // no forward transform, x leaves the kernel
   constexpr bool XONLY = PM == PM_XONLY, FIRST = PM == PM_FIRST;
   static_assert(TW::COLS == ZR, "tile holds one complex sequence per image row");
   constexpr int W = TW::N, NSEQ = ZR, G = W / CG;
   constexpr int RA = TW::RA, RB = TW::RB, RC = TW::RC, MA = TW::MA, RSU = RowZPersistSmem<TW>::RSU;
-  constexpr int NT1 = NSEQ * (W / RC);
+  constexpr int NT1 = NSEQ * (W / RC), NTH = RowZPersistSmem<TW>::THREADS;
   constexpr unsigned U_BYTES = 2 * ZR * W * sizeof(float);
   static_assert((W / RC) % CG == 0, "butterfly inputs of the global-facing pass fall into the same column of different groups");
   DPX_DYN_SMEM(float2, sm);
@@ -1181,7 +1188,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
 
     // ---- 1. inverse pass C out of the staged spectrum rows (column storage order: see k_rowz) ----------------------------
     if (!FIRST) {
-    for (int t = tid; t < NT1; t += kThreads) {
+    for (int t = tid; t < NT1; t += NTH) {
       const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
       const int blk = gq * CG + cc;
       const float2* src = stS + gq * (ZR * CG) + r * CG + cc;
@@ -1200,7 +1207,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       else rowz_stage_S<TW>(P, nxt, stS, tid);
     }
     cp_async_commit();
-    fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, kThreads);
+    fft::smem_pass<TW, RB, MA, true, true>(sm, twB, tid, NTH);
     __syncthreads();
     }
     if (tid == 0) trace_stamp(P.trace, tile, 4);
@@ -1215,7 +1222,7 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
       const bool simple = scale == 1.f && tm.beta == 1.f && op == nullptr &&
                           (ps.kind == DPX_PROX_NONNEG || ps.kind == DPX_PROX_L1 || ps.kind == DPX_PROX_L2SQ || ps.kind == DPX_PROX_BOX);
       const float lam_eff = lam * tm.alpha;
-      for (int t = tid; t < NSEQ * MA; t += kThreads) {
+      for (int t = tid; t < NSEQ * MA; t += NTH) {
         const int c = t % NSEQ, j = t / NSEQ;
         const int p0 = TW::phys(j, c);
         float2 a[RA], w[RA];
@@ -1280,10 +1287,10 @@ __global__ void __launch_bounds__(kThreads, RowZPersistSmem<TW>::CTAS_PER_SM) k_
 
     // ---- 3. forward pass B in shared memory, forward pass C stored straight to global memory ---------------------------
     if (!LAST) {
-    fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, kThreads);
+    fft::smem_pass<TW, RB, MA, false, true>(sm, twB, tid, NTH);
     __syncthreads();
     if (tid == 0) trace_stamp(P.trace, tile, 6);
-    for (int t = tid; t < NT1; t += kThreads) {
+    for (int t = tid; t < NT1; t += NTH) {
       const int cc = t % CG, r = (t / CG) % NSEQ, gq = t / (CG * NSEQ);
       const int blk = gq * CG + cc;
       const int p0 = TW::phys(blk * RC, r);

@@ -31,7 +31,7 @@ struct EmuBackend {
   }
   template <class TH>
   void col(dim3 grid, size_t smem, ColParams p) {
-    emu::launch(grid, dim3(kThreads), smem, [=]() { k_col<TH>(p); });
+    emu::launch(grid, dim3(ColThreads<TH>::value), smem, [=]() { k_col<TH>(p); });
   }
   template <class TW, int MODE, bool SINGLE>
   void rowz(dim3 grid, size_t smem, RowParams p) {
@@ -39,7 +39,7 @@ struct EmuBackend {
   }
   template <class TW, int PM>
   void rowz_persist(dim3 grid, size_t smem, RowParams p, int n_tiles) {
-    emu::launch(grid, dim3(kThreads), smem, [=]() { k_rowz_mid_persist<TW, PM>(p, n_tiles); });
+    emu::launch(grid, dim3(RowZPersistSmem<TW>::THREADS), smem, [=]() { k_rowz_mid_persist<TW, PM>(p, n_tiles); });
   }
   void packz_fb(const float2* src, float2* dst, int pairs, int C, PackGeom q) {
     const size_t total = (size_t)pairs * q.H * q.W;

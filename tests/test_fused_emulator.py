@@ -150,6 +150,27 @@ def test_tma_column_kernel_with_plane_pairs(emu, monkeypatch):
 
 @pytest.mark.parametrize("B", [1, 2])
 def test_staged_xupdate_matches_first_iteration(emu, B, monkeypatch):
+    _staged_xupdate_first_iteration(emu, B, monkeypatch)
+
+
+@pytest.mark.parametrize("H,W", [(64, 2560), (4096, 64)])
+def test_solo_tiles_run_512_threads(emu, H, W):
+    """Tiles of which only one fits an SM run 512 threads per CTA (RowZPersistSmem::SOLO rows from 2560 points in the persistent pair
+    kernel, ColThreads for 3840- / 4096-point columns): same arithmetic, task loops strided by the larger block."""
+    g = torch.Generator().manual_seed(H + 7 * W)
+    B, Cc, T = 2, 1, 3
+    img = torch.rand(B, Cc, H, W, generator=g) - 0.3
+    psf = orc.point_spread_function(5, 1.5)
+    b = (orc.Conv(psf, orc.Identity()).fwd(img) + 0.01 * torch.randn(B, Cc, H, W, generator=g)).numpy()
+    f = orc.Term("nonneg")
+    data = orc.Term("sum_squares", orc.Conv(psf, orc.Identity()), c=torch.from_numpy(b))
+    want = orc.Solver([data, f], "admm").solve(torch.from_numpy(b), rhos=1.0, lams=0.02, max_iter=T, return_full_states=True)
+    x, v, u = run_emu(emu, b, psf, [0], [1.0], [1.0], 1.0, [0.02], T, False)
+    assert run_emu.last_engine == "pairs"
+    assert rel(x, want[0].numpy()) < 5e-6 and rel(v[0], want[1][0].numpy()) < 5e-5 and rel(u[0], want[2][0].numpy()) < 5e-5
+
+
+def _staged_xupdate_first_iteration(emu, B, monkeypatch):
     """dpx_stage_xupdate's fused form (ROW_FIRST -> k_col -> ROW_XONLY, used when an external prox sits between the stages)
     gives bit-for-bit the x of a one-iteration fused run, on both engines, and leaves v / u untouched."""
     g = torch.Generator().manual_seed(29)

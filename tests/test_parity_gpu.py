@@ -587,10 +587,12 @@ def test_fused_single_term_paths(dp, method, H, W, Cc):
     assert seen == list(range(T_)) and rel(out, want[0]) < TOL_X
 
 
-def test_fused_engine_4096(dp):
-    """largest supported side: [1,1,4096,4096] (radix 16x16x16 tiles), fused vs cuFFT engine, 3 iterations."""
+@pytest.mark.parametrize("B", [1, 2])
+def test_fused_engine_4096(dp, B):
+    """largest supported side: [B,1,4096,4096] (radix 16x16x16 tiles), fused vs cuFFT engine, 3 iterations.  B = 1: half-spectrum
+    engine; B = 2: plane-pair engine, whose 4096-point tiles fit one per SM and run 512 threads per CTA (ColThreads, RowZPersistSmem::SOLO)."""
     g = torch.Generator(device="cuda").manual_seed(5)
-    b = torch.rand(1, 1, 4096, 4096, device="cuda", generator=g)
+    b = torch.rand(B, 1, 4096, 4096, device="cuda", generator=g)
     psf = orc.point_spread_function(15, 5)
     res = {}
     for backend in (2, 1):
