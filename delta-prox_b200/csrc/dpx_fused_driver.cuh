@@ -41,6 +41,18 @@ DPX_TILE_FOR(1080, 15, 9, 8)
 DPX_TILE_FOR(1200, 15, 10, 8)
 DPX_TILE_FOR(1440, 15, 12, 8)
 DPX_TILE_FOR(2160, 15, 9, 16)
+DPX_TILE_FOR(160, 10, 4, 4)        // further products of the same radices (second pass 10 / 12 next to a last pass of 4 or 16):
+DPX_TILE_FOR(400, 10, 10, 4)       // VGA / SVGA sides 480, 600 (column only), 800, 1152 and the 2^k * {9, 25} sides around them
+DPX_TILE_FOR(480, 12, 10, 4)
+DPX_TILE_FOR(576, 12, 12, 4)
+DPX_TILE_FOR(800, 10, 10, 8)       // radix 10 throughout: three co-resident row CTAs (85 registers) without the radix-20 spills
+DPX_TILE_FOR(1152, 12, 12, 8)
+DPX_TILE_FOR(2304, 12, 12, 16)
+DPX_TILE_FOR(3200, 20, 10, 16)
+DPX_TILE_FOR(600, 15, 10, 4)       // column lengths only (odd radix 15 / 9 passes)
+DPX_TILE_FOR(864, 12, 9, 8)
+DPX_TILE_FOR(2400, 15, 10, 16)
+DPX_TILE_FOR(2880, 20, 9, 16)
 #undef DPX_TILE_FOR
 
 // sizes usable as a row length (W) and as a column length (H) / as a column length only
@@ -48,13 +60,13 @@ DPX_TILE_FOR(2160, 15, 9, 16)
 #define DPX_W_SIZES(X) X(2048)
 #define DPX_H_ONLY_SIZES(X)
 #elif defined(DPX_EMU)                                 // CPU emulator build (tests/emu): the sizes its tests run, one per radix family
-#define DPX_W_SIZES(X) X(64) X(128) X(256) X(1024) X(192) X(384) X(320) X(640) X(1280) X(960) X(1920) X(2560)
+#define DPX_W_SIZES(X) X(64) X(128) X(256) X(1024) X(192) X(384) X(320) X(640) X(1280) X(960) X(1920) X(2560) X(480)
 #define DPX_H_ONLY_SIZES(X) X(1080) X(4096)            // 2560-point rows / 4096-point columns: the 512-thread, one-CTA-per-SM tiles
 #else
 #define DPX_W_SIZES(X)                                                                                                          \
   X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(192) X(384) X(768) X(1536) X(3072) X(320) X(640) X(1280) X(2560) X(960) \
-  X(1600) X(1920) X(3840)
-#define DPX_H_ONLY_SIZES(X) X(720) X(1080) X(1200) X(1440) X(2160)
+  X(1600) X(1920) X(3840) X(160) X(400) X(480) X(576) X(800) X(1152) X(2304) X(3200)
+#define DPX_H_ONLY_SIZES(X) X(720) X(1080) X(1200) X(1440) X(2160) X(600) X(864) X(2400) X(2880)
 #endif
 #define DPX_CASE_TRUE(N) case N:
 #define DPX_CASE_CALL(N) case N: f(std::integral_constant<int, N>{}); return true;

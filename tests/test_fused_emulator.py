@@ -92,7 +92,8 @@ def test_fused_kernels_match_oracle(emu, H, W, method):
 
 @pytest.mark.parametrize("H,W,method", [(64, 128, "admm"), (128, 64, "hqs"), (1024, 64, "admm"),      # H = 1024: k_col_tma
                                         (192, 192, "admm"), (64, 1280, "hqs"),                   # 1280: radix-20 first pass
-                                        (64, 1920, "hqs")])                                      # 20*12*8 as a row length
+                                        (64, 1920, "hqs"),                                       # 20*12*8 as a row length
+                                        (480, 480, "admm")])                                     # 12*10*4: radix-10 second pass over 4-point blocks
                                         # (720, 1200, 1440, 1600, 2160, 3840 points: tests/test_parity_gpu.py, against the cuFFT engine)
 def test_fused_kernels_single_term_fast_path(emu, H, W, method):
     """One psi term: the in-place register path of k_row (template SINGLE)."""

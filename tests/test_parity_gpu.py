@@ -421,7 +421,10 @@ def test_fused_engine_matches_oracle(dp, H, W, method):
 @pytest.mark.parametrize("B,H,W", [(1, 2048, 2048), (2, 768, 1024), (2, 1536, 384), (1, 192, 3072), (2, 1280, 640), (1, 320, 2560),
                                    # camera formats: heights 720 = 10*9*8, 1080 = 15*9*8, 1200 = 15*10*8, 1440 = 15*12*8, 2160 = 15*9*16
                                    # (radix 9 / 15 column passes), widths 960 = 12*10*8, 1600 = 20*10*8, 1920 = 20*12*8, 3840 = 20*12*16
-                                   (2, 1080, 1920), (1, 720, 1280), (2, 1440, 2560), (1, 1200, 1600), (2, 2160, 3840), (3, 960, 960)])
+                                   (2, 1080, 1920), (1, 720, 1280), (2, 1440, 2560), (1, 1200, 1600), (2, 2160, 3840), (3, 960, 960),
+                                   # VGA / SVGA and further products of the radices: 480 = 12*10*4, 600 = 15*10*4 (column), 800 = 10*10*8,
+                                   # 864 = 12*9*8 (column), 1152 = 12*12*8, 576, 400, 160, 2304 = 12*12*16, 2880 = 20*9*16, 2400 / 3200
+                                   (2, 480, 640), (1, 600, 800), (2, 864, 1152), (1, 576, 400), (2, 160, 160), (1, 2880, 2304), (2, 2400, 3200)])
 def test_fused_engine_headline_size_vs_cufft(dp, B, H, W):
     """5 ADMM iterations: the fused engine (plane pairs for B = 2; radix-12 / radix-10 / radix-20 first pass for the 3 * 2^k and 5 * 2^k
     sides -- 768 x 1024 is the reference's own test image, tests/test_algorithms.py:6-20) and the cuFFT engine agree to fp32 round-off."""
