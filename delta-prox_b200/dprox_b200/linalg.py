@@ -192,7 +192,7 @@ def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: f
     key = ("pcg", cache_key, tuple(b.shape), b.dtype, b.device, rtol, max_iters)
     st = cache.get(key) if (cache is not None and check_every is None and Minv is None) else None
     if st is not None:
-        x, r, p, gamma, rmax, poll, graph = st
+        x, r, p, gamma, rmax, poll, graph, _tol = st              # _tol: the gate's threshold, read by the captured step
         if x0 is None:
             x.fill_(1.0)
         else:
@@ -249,7 +249,9 @@ def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: f
             elif check_every and (it + 1) % check_every == 0 and float(ops.absmax(r)) < rtol:
                 break
         if graph is not None:
-            cache[key] = (x, r, p, gamma, rmax, poll, graph)
+            # every tensor the captured step reads must outlive this call -- the 4-byte threshold included: freed, its block
+            # is handed to the next small allocation and the replayed gate compares max|r| with whatever lands there
+            cache[key] = (x, r, p, gamma, rmax, poll, graph, tol)
             return x.clone()
         return x
     # general preconditioner: y = Minv(r) is a user callable; dots/axpys stay native (host test: Minv is user code anyway)

@@ -500,6 +500,40 @@ def test_cg_graph_replay_matches_eager_steps(dp, solver, monkeypatch):
     assert rel(outs["1"], outs["0"]) < 2e-5, rel(outs["1"], outs["0"])
 
 
+@pytest.mark.parametrize("solver", ["cg", "pcg"])
+def test_cg_graph_replay_survives_allocator_churn(dp, solver, monkeypatch):
+    """BASELINE config 3 as bench.py runs it (CS-MRI plugin operator + TV, ADMM, PCG inner solve; one captured step per iteration
+    index because the tree holds a BlackBox), solved repeatedly with small allocations in between: everything the captured step
+    reads has to stay alive between solves (the gate's threshold of `pcg` did not: its freed block was reused and later solves stopped
+    their inner iterations early -- 0.28 instead of 0.0075 from the truth in the bench).  Replay == eager on the third solve."""
+    g = torch.Generator().manual_seed(5)
+    Bn, H, W, T_ = 2, 64, 64, 8
+    img = torch.zeros(Bn, 1, H, W)
+    img[:, :, 16:48, 20:40] = 1.0
+    img[1, :, 24:36, 8:56] += 0.5
+    mask = (torch.rand(1, 1, H, W, generator=g) < 0.4).float()
+    mask[..., :3, :3] = 1
+    img, mask = img.cuda(), mask.cuda()
+    fwd = lambda x, step=0: mask * torch.fft.fft2(x, norm="ortho")
+    adj = lambda y, step=0: torch.real(torch.fft.ifft2(mask * y, norm="ortho")).contiguous()
+    y0 = fwd(img)
+    x0 = adj(y0)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DPX_CG_GRAPH", mode)
+        x = dp.Variable()
+        f1, f2 = dp.norm1(dp.grad(x, dim=0)), dp.norm1(dp.grad(x, dim=1))
+        cfg = dp.LinearSolveConfig(rtol=1e-6, max_iters=30, solver_type=solver)
+        s = dp.compile(dp.sum_squares(dp.LinOpFactory(fwd, adj)(x), y0) + f1 + f2, method="admm", device="cuda", linear_solve_config=cfg)
+        with torch.no_grad():
+            for rep in range(3):
+                churn = [torch.full((1,), 1e3 * (k + 1), device="cuda") for k in range(64)]     # reuse whatever small blocks were freed
+                outs[mode] = s.solve(x0=x0, rhos=1.0, lams={f1: 0.05, f2: 0.05}, max_iter=T_)
+                del churn
+    assert rel(outs["1"], outs["0"]) < 2e-5, rel(outs["1"], outs["0"])
+    assert rel(outs["1"], img) < 0.2
+
+
 def test_cfg4_size_hqs_vs_oracle(dp):
     """BASELINE config 4 per GPU at its stated size: HQS deconv + nonneg on [2,3,1024,1024] (plane-pair engine, TMA-staged rows,
     radix-16*8*8 tiles), 24 iterations, against the oracle; x and v."""
