@@ -16,6 +16,7 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
+from . import _cabi as cabi
 from . import ops
 
 
@@ -28,6 +29,24 @@ class LinearSolveConfig:
     solver_type: str = "cg"
     solver_kwargs: dict = field(default_factory=dict)
     use_analytic_grad: bool = True
+
+
+# CG / PCG steps enqueued by this process (eager or replayed; a few steps past convergence are gated no-ops): what bench.py's
+# cfg3 line counts its algorithmic bytes from -- a replayed step does not pass through the Python operator tree
+steps_enqueued = [0]
+# kernels of this library launched from replayed graphs (dpx_launch_count only sees launches issued through the C-ABI by the host)
+replayed_launches = [0]
+
+
+class _Replay:
+    """A captured CG step plus the number of this library's launches it holds (counted while it was recorded)."""
+
+    def __init__(self, graph, n_launches):
+        self.graph, self.n_launches = graph, n_launches
+
+    def replay(self):
+        self.graph.replay()
+        replayed_launches[0] += self.n_launches
 
 
 class _StopPoll:
@@ -86,9 +105,10 @@ def _capture(body: Callable):
     try:
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = cabi.lib().dpx_launch_count()
         with torch.cuda.graph(g):
             body()
-        return g
+        return _Replay(g, int(cabi.lib().dpx_launch_count() - n0))
     except Exception:                                            # noqa: BLE001 -- any failure means "run eagerly"
         try:
             torch.cuda.synchronize()
@@ -130,6 +150,7 @@ def cg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: fl
                 break
             graph.replay()
             poll.push()
+            steps_enqueued[0] += 1
         return x.clone()
     x = torch.zeros_like(b) if x0 is None else x0.clone()
     r = b.clone() if x0 is None else ops.axpby(1.0, b, -1.0, A(x))
@@ -162,9 +183,11 @@ def cg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: fl
         if graph is not None:
             graph.replay()
             poll.push()
+            steps_enqueued[0] += 1
             continue
         if it == 0:
             p = r.clone()
+        steps_enqueued[0] += 1
         q = A(p)
         pq = ops.dot(p, q)
         if poll is not None:
@@ -207,6 +230,7 @@ def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: f
                 break
             graph.replay()
             poll.push()
+            steps_enqueued[0] += 1
         return x.clone()
     x = torch.ones_like(b) if x0 is None else x0.clone()
     r = ops.axpby(1.0, b, -1.0, A(x))
@@ -233,7 +257,9 @@ def pcg(A: Callable, b: torch.Tensor, x0: Optional[torch.Tensor] = None, rtol: f
             if graph is not None:
                 graph.replay()
                 poll.push()
+                steps_enqueued[0] += 1
                 continue
+            steps_enqueued[0] += 1
             q = A(p)
             pq = ops.dot(p, q, per_sample=False)
             if poll is not None and rmax is not None:
