@@ -9,6 +9,7 @@ template <class TH>
 cudaError_t col(dim3 grid, size_t smem, const ColParams& p, cudaStream_t s) {
   cudaError_t e = prep(k_col<TH>, smem);
   if (e != cudaSuccess) return e;
+  if (p.pdl) return launch_pdl(k_col<TH>, grid, ColThreads<TH>::value, smem, s, p);
   k_col<TH><<<grid, ColThreads<TH>::value, smem, s>>>(p);
   return cudaGetLastError();
 }

@@ -51,6 +51,7 @@ struct RowParams {
   const float2* tw;              // twiddle records of the W-tile (fft::TwiddleLayout)
   const void* smap = nullptr;    // persistent pair kernel: tensor map of S {H*8 floats, G, pairs} in global memory, or nullptr = LDGSTS staging
   int* ctr = nullptr;            // persistent pair kernel: dynamic tile counter of this launch (zeroed), or nullptr = static round robin
+  int pdl = 0;                   // persistent pair kernel launched as a programmatic dependent: wait for the previous grid before any global access
   unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
 };
 
@@ -69,6 +70,7 @@ struct ColParams {
   const float2* tw;              // twiddle records of the H-tile
   unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
   int bulk = 0;                  // staged tile through TMA bulk copies (needs 16 bytes of shared memory behind the tile)
+  int pdl = 0;                   // launched as a programmatic dependent: wait for the previous grid before touching S
 };
 
 DPX_HD size_t s_index(int p, int g, int h, int c, int H, int G) {
@@ -83,7 +85,15 @@ DPX_HD float2 ld_stream2(const float2* p) { return *p; }
 DPX_HD float4 ld_stream4(const float4* p) { return *p; }
 DPX_HD void prefetch_l2(const void*) {}
 DPX_HD void trace_stamp(unsigned long long*, int, int) {}
+DPX_HD void griddep_launch_dependents() {}
+DPX_HD void griddep_wait() {}
 #else
+// Programmatic dependent launch (launch attribute programmaticStreamSerialization, DPX_PDL=1): a kernel lets the next one in the
+// stream begin scheduling CTAs as soon as all of its own CTAs have started, and the next one blocks at griddep_wait() -- until the
+// previous grid has completed and its memory is visible -- before it touches anything an earlier kernel of the solve wrote.  What
+// overlaps with the previous kernel's tail: the launch itself, CTA scheduling, barrier set-up, the L2 prefetch of solve constants.
+DPX_HD void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DPX_HD void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 DPX_HD void trace_stamp(unsigned long long* tr, int rec, int slot) {
   if (tr) {
     unsigned long long t;
@@ -636,6 +646,14 @@ __global__ void __launch_bounds__(ColThreads<TH>::value, (TH::SMEM_FLOAT2 * size
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TH>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TH>::B_OFF;
   mbar_t* stage_bar = reinterpret_cast<mbar_t*>(sm + TH::SMEM_FLOAT2);    // (P.bulk) one transaction barrier behind the tile
+  if (P.pdl) {
+    griddep_launch_dependents();
+    {  // F(K^T b) is a constant of the solve: its records can be pulled into L2 while the previous kernel drains
+      const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * NG + g) * H * CG);
+      for (int o = tid * 128; o < H * CG * 8; o += NTH * 128) prefetch_l2(nf + o);
+    }
+    griddep_wait();
+  }
   if (STAGE && P.bulk) {
     // TMA bulk copies: 8 rows x CG columns = 256 contiguous bytes in global memory AND at the padded position (one spare point
     // follows every 8 points), so the tile arrives through the async proxy -- no LSU wavefronts, no per-thread address stream
@@ -653,7 +671,7 @@ __global__ void __launch_bounds__(ColThreads<TH>::value, (TH::SMEM_FLOAT2 * size
     }
     cp_async_commit();
   }
-  {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
+  if (!P.pdl) {  // pull this CTA's F(K^T b) records into L2 now; they are consumed two passes later
     const char* nf = reinterpret_cast<const char*>(P.fbp + ((size_t)p * NG + g) * H * CG);
     for (int o = tid * 128; o < H * CG * 8; o += NTH * 128) prefetch_l2(nf + o);
   }
@@ -1145,6 +1163,7 @@ __global__ void __launch_bounds__(RowZPersistSmem<TW>::THREADS, RowZPersistSmem<
     mbar_init(bars + 1, 1);
     mbar_fence_init();
   }
+  if (P.pdl) { griddep_launch_dependents(); griddep_wait(); }
   __syncthreads();
   int tile = blockIdx.x;
   RowZTile cur = rowz_tile(P, tile < n_tiles ? tile : 0, tpp, n_tiles);

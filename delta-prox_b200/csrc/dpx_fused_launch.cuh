@@ -19,6 +19,18 @@ template <class TH> cudaError_t col(dim3 grid, size_t smem, const ColParams& p, 
 template <class TH> cudaError_t col_tma(dim3 grid, size_t smem, const ColParams& p, int n_tiles, int nb, cudaStream_t s);
 template <class TH, typename V> cudaError_t pack(const V* src, V* dst, int planes, int H, int W, int G, V zero, cudaStream_t s);
 
+// launch as a programmatic dependent of the previous kernel in the stream (the kernel calls griddepcontrol.wait: see griddep_wait)
+template <class K, class... A>
+inline cudaError_t launch_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // shared by the instantiating translation units
 template <class K>
 inline cudaError_t prep(K kernel, size_t smem) {

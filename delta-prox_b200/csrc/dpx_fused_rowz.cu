@@ -16,6 +16,7 @@ template <class TW, int PM>
 cudaError_t rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s) {
   cudaError_t e = prep(k_rowz_mid_persist<TW, PM>, smem);
   if (e != cudaSuccess) return e;
+  if (p.pdl) return launch_pdl(k_rowz_mid_persist<TW, PM>, grid, RowZPersistSmem<TW>::THREADS, smem, s, p, n_tiles);
   k_rowz_mid_persist<TW, PM><<<grid, RowZPersistSmem<TW>::THREADS, smem, s>>>(p, n_tiles);
   return cudaGetLastError();
 }

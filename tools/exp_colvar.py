@@ -66,7 +66,7 @@ def main():
         try:
             solver, b = build(4)
             st = solver.solve(x0=b, rhos=1.0, lams=0.02, max_iter=6, return_full_states=True)
-            cur = [st[0].clone(), st[1][0].clone(), st[2][0].clone()]
+            cur = [st[0].clone(), st[1][0].clone()] + ([st[2][0].clone()] if len(st) > 2 and len(st[2]) else [])
             if ref is None:
                 ref = cur
             out["rel_vs_first"] = [rel(c, r) for c, r in zip(cur, ref)]
