@@ -36,14 +36,18 @@ struct CudaBackend {
   template <class TW, int MODE, bool SINGLE>
   void row(dim3 grid, size_t smem, const RowParams& p) {
     if (rc) return;
-    done(launch::row<TW, MODE, SINGLE>(grid, smem, p, s));
+    RowParams q = p;
+    q.pdl = pdl;
+    done(launch::row<TW, MODE, SINGLE>(grid, smem, q, s));
   }
   int n_persist = 0;                                  // CTAs of the persistent row kernel (2 per SM); 0 disables it
   int persistent_ctas() const { return n_persist; }
   template <class TW>
   void row_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {
     if (rc) return;
-    done(launch::row_persist<TW>(grid, smem, p, n_tiles, s));
+    RowParams q = p;
+    q.pdl = pdl;
+    done(launch::row_persist<TW>(grid, smem, q, n_tiles, s));
   }
   int n_sm = 0;                                       // SMs for the persistent TMA column kernel; 0 disables it
   int sm_count() const { return n_sm; }
@@ -71,7 +75,9 @@ struct CudaBackend {
   template <class TW, int MODE, bool SINGLE>
   void rowz(dim3 grid, size_t smem, const RowParams& p) {
     if (rc) return;
-    done(launch::rowz<TW, MODE, SINGLE>(grid, smem, p, s));
+    RowParams q = p;
+    q.pdl = pdl;
+    done(launch::rowz<TW, MODE, SINGLE>(grid, smem, q, s));
   }
   template <class TW, int PM = PM_MID>
   void rowz_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles) {

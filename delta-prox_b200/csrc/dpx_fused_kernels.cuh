@@ -51,7 +51,7 @@ struct RowParams {
   const float2* tw;              // twiddle records of the W-tile (fft::TwiddleLayout)
   const void* smap = nullptr;    // persistent pair kernel: tensor map of S {H*8 floats, G, pairs} in global memory, or nullptr = LDGSTS staging
   int* ctr = nullptr;            // persistent pair kernel: dynamic tile counter of this launch (zeroed), or nullptr = static round robin
-  int pdl = 0;                   // persistent pair kernel launched as a programmatic dependent: wait for the previous grid before any global access
+  int pdl = 0;                   // row kernel launched as a programmatic dependent: wait for the previous grid before any global access
   unsigned long long* trace = nullptr;   // optional phase timestamps (DPX_TRACE), else nullptr
 };
 
@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, (TW::N <= 2048 && SINGLE) ? 3 : 2) k
   const int r0 = blockIdx.x * ROWS;
   const int b = p / P.C;
   const int H = P.H;
+  if (P.pdl) { griddep_launch_dependents(); griddep_wait(); }     // programmatic dependent launch: see griddep_wait
 
   // ---- 0. twiddle records ([q/2][j], fft::load_twiddles) -> shared memory ------------------------------------------
   {
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_row_mid_persist(RowParams P, in
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
   const PsiTerm& tm = P.psi.t[0];
   const int hqs = P.hqs;
+  if (P.pdl) { griddep_launch_dependents(); griddep_wait(); }     // programmatic dependent launch: see griddep_wait
 
   int tile = blockIdx.x;
   if (tile < n_tiles) {
@@ -954,6 +956,7 @@ __global__ void __launch_bounds__(kThreads, TW::N <= 2048 ? 3 : 1) k_rowz(RowPar
   const float2* __restrict__ twA = P.tw + fft::TwiddleLayout<TW>::A_OFF;
   const float2* __restrict__ twB = P.tw + fft::TwiddleLayout<TW>::B_OFF;
   constexpr int NT1 = NSEQ * (W / RC);
+  if (P.pdl) { griddep_launch_dependents(); griddep_wait(); }     // programmatic dependent launch: see griddep_wait
 
   {  // pull this CTA's dual rows into L2 now; they are consumed two FFT passes later
     const size_t eA = ((size_t)pA * H + h0) * W, eB = ((size_t)pB * H + h0) * W;

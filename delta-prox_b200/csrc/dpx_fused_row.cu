@@ -9,6 +9,7 @@ template <class TW, int MODE, bool SINGLE>
 cudaError_t row(dim3 grid, size_t smem, const RowParams& p, cudaStream_t s) {
   cudaError_t e = prep(k_row<TW, MODE, SINGLE>, smem);
   if (e != cudaSuccess) return e;
+  if (p.pdl) return launch_pdl(k_row<TW, MODE, SINGLE>, grid, kThreads, smem, s, p);
   k_row<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
@@ -16,6 +17,7 @@ template <class TW>
 cudaError_t row_persist(dim3 grid, size_t smem, const RowParams& p, int n_tiles, cudaStream_t s) {
   cudaError_t e = prep(k_row_mid_persist<TW>, smem);
   if (e != cudaSuccess) return e;
+  if (p.pdl) return launch_pdl(k_row_mid_persist<TW>, grid, kThreads, smem, s, p, n_tiles);
   k_row_mid_persist<TW><<<grid, kThreads, smem, s>>>(p, n_tiles);
   return cudaGetLastError();
 }

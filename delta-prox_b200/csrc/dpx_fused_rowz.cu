@@ -9,6 +9,7 @@ template <class TW, int MODE, bool SINGLE>
 cudaError_t rowz(dim3 grid, size_t smem, const RowParams& p, cudaStream_t s) {
   cudaError_t e = prep(k_rowz<TW, MODE, SINGLE>, smem);
   if (e != cudaSuccess) return e;
+  if (p.pdl) return launch_pdl(k_rowz<TW, MODE, SINGLE>, grid, kThreads, smem, s, p);
   k_rowz<TW, MODE, SINGLE><<<grid, kThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
