@@ -15,7 +15,12 @@ import dprox_b200 as dp  # noqa: E402
 psf = np.ones((5, 5, 1), "float32") / 25.0
 # round 2: (2, 2048, 64) takes the TMA-staged column tile (bulk copies + transaction barrier), every pair case the tensor-map
 # staging of the spectrum rows and the dynamic tile counter; (2, 1080, 64): radix-15 / radix-9 column passes
-for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64, "hqs"), (2, 2048, 64, "admm"), (2, 1080, 64, "admm")):
+# closing round-2 cases (DPX_SANITIZE=new runs only these): 512-thread one-CTA-per-SM tiles (2560-point rows, 4096-point columns), a size
+# added to the tile table (480 = 12*10*4), an odd batch (half-spectrum kernels) -- all launched as programmatic dependents
+NEW = ((2, 64, 2560, "admm"), (2, 4096, 64, "admm"), (2, 480, 480, "hqs"), (1, 64, 128, "admm"))
+ONLY_NEW = os.environ.get("DPX_SANITIZE") == "new"
+OLD = ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64, "hqs"), (2, 2048, 64, "admm"), (2, 1080, 64, "admm"))
+for B, H, W, method in (NEW if ONLY_NEW else OLD + NEW):
     g = torch.Generator(device="cuda").manual_seed(B + H)
     b = torch.rand(B, 3, H, W, device="cuda", generator=g) - 0.3
     x = dp.Variable()
@@ -23,6 +28,9 @@ for B, H, W, method in ((2, 64, 128, "admm"), (1, 128, 64, "admm"), (2, 1024, 64
     out = s.solve(x0=b, rhos=1.0, lams=0.02, max_iter=4)
     torch.cuda.synchronize()
     print(B, H, W, method, float(out.abs().mean()))
+
+if ONLY_NEW:
+    sys.exit(0)
 
 # fp32-class FFDNet: fp16-pair split convolution (tcgen05, two TMEM accumulators), forward + data gradient at a ragged size
 from dprox_b200.denoisers import FFDNetColorDenoiser  # noqa: E402
