@@ -1,5 +1,5 @@
 // dpx_fused_launch.cuh — launchers of the fused-engine kernels, declared here and explicitly instantiated for every supported size in
-// three translation units (dpx_fused_col.cu, dpx_fused_row.cu, dpx_fused_rowz.cu) so that they compile in parallel; the engine
+// four translation units (dpx_fused_col.cu, dpx_fused_row.cu, dpx_fused_rowz.cu, dpx_fused_rowzp.cu) so that they compile in parallel; the engine
 // (dpx_fused_fft.cu) only sees the declarations.  Each launcher sets the dynamic shared-memory attribute, launches on `s` and
 // returns the launch status.
 #pragma once
