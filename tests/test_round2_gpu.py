@@ -505,7 +505,8 @@ def test_cg_graph_replay_survives_allocator_churn(dp, solver, monkeypatch):
     """BASELINE config 3 as bench.py runs it (CS-MRI plugin operator + TV, ADMM, PCG inner solve; one captured step per iteration
     index because the tree holds a BlackBox), solved repeatedly with small allocations in between: everything the captured step
     reads has to stay alive between solves (the gate's threshold of `pcg` did not: its freed block was reused and later solves stopped
-    their inner iterations early -- 0.28 instead of 0.0075 from the truth in the bench).  Replay == eager on the third solve."""
+    their inner iterations early -- 0.28 instead of 0.0075 from the truth in the bench).  Replay == eager on the third solve
+    (checked on a B200 with the fix taken out: the pcg case fails, the cg case -- whose threshold was always cached -- passes)."""
     g = torch.Generator().manual_seed(5)
     Bn, H, W, T_ = 2, 64, 64, 8
     img = torch.zeros(Bn, 1, H, W)
